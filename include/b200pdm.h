@@ -1,0 +1,220 @@
+/*
+ * b200pdm.h -- C ABI of the B200-native (sm_100a) hot path for rezashkv/unlearn-ft.
+ *
+ * The reference (pure Python, `pdm` package) has no FFI: its hot path is the chain
+ *   pdm/training/trainer.py:2403-2488 (UnetFineTuner.step) -> pdm/models/unet/unet_2d_conditional.py:1417-1728
+ *   -> pdm/models/unet/blocks.py (gated/pruned blocks) -> diffusers -> torch -> cuDNN/cuBLAS/SDPA/ATen.
+ * Every entry point below names the reference call site (file:line under /root/reference) whose device work it
+ * replaces.  The Python mirror of the reference's class surface (unlearn_ft_b200/pdm/...) binds these with ctypes.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless noted; no torch types;
+ *   - every call enqueues on `stream` and returns immediately: 0 on success, a negative B200PDM_ERR_* otherwise;
+ *     nothing here allocates device memory, synchronises the device, or throws;
+ *   - activations are bf16, channels-last ("NHWC"): a [B,C,H,W] tensor is a row-major [B*H*W, ld] matrix whose
+ *     first C columns are valid, ld % 8 == 0 (16-byte rows; TMA requirement);
+ *   - weights used as tensor-core operands are bf16 "shadow" copies of the fp32 masters, kept in the layout
+ *     [C_out][kh*kw][C_in_ld] for convolutions and [N][K] for linears (same element order as the masters);
+ *   - gradients of parameters are fp32 and are ACCUMULATED into the caller's buffers.
+ */
+#ifndef B200PDM_H_
+#define B200PDM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200pdm_stream_t; /* cudaStream_t */
+
+#define B200PDM_OK 0
+#define B200PDM_ERR_ARG -1
+#define B200PDM_ERR_CUDA -2
+#define B200PDM_ERR_UNSUPPORTED -3
+#define B200PDM_ERR_DRIVER -4
+
+/* Library/ABI version and last CUDA error string (host pointers). */
+int b200pdm_version(void);
+const char* b200pdm_last_error(void);
+/* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
+uint64_t b200pdm_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core core: one persistent, warp-specialised tcgen05 kernel (TMA -> smem ring -> tcgen05.mma -> TMEM ->
+ * epilogue warps) driven by an operand "addressing program".  All GEMM-shaped reference call sites map onto it.
+ * ------------------------------------------------------------------------------------------------------------ */
+enum {
+  B200PDM_OP_K2D = 0,        /* K-major matrix  elem(mn,k) = ptr[z2*bs2 + z1*bs1 + mn*ld + k]                  */
+  B200PDM_OP_MN2D = 1,       /* MN-major matrix elem(mn,k) = ptr[z2*bs2 + z1*bs1 + k*ld + mn]                  */
+  B200PDM_OP_CONV_ACT = 2,   /* A only: implicit-GEMM rows = output pixels, K = taps x channels, NHWC source    */
+  B200PDM_OP_CONV_W = 3,     /* B only: conv weight [O][taps][I_ld], N = O, K = taps x I                       */
+  B200PDM_OP_CONV_WT = 4,    /* B only: same memory, transposed use (dgrad): N = I, K = taps x O               */
+  B200PDM_OP_CONV_ACT_MN = 5 /* B only: wgrad: N = (tap, channel) of the NHWC source, K = output pixels        */
+};
+
+typedef struct {
+  int mode;
+  const void* ptr; /* bf16 */
+  int64_t ld;      /* row pitch in elements (2D modes), pixel pitch (ACT modes), I_ld (W modes)           */
+  int64_t bs1, bs2;/* batch strides in elements (2D modes)                                                */
+  /* convolution geometry (ACT/W modes) */
+  int batch, h_in, w_in, channels; /* NHWC source: [batch, h_in, w_in, channels]; W modes: channels = I  */
+  int h_out, w_out;                /* output grid the GEMM rows / K pixels enumerate                       */
+  int stride;                      /* 1 or 2                                                               */
+  int taps;                        /* 9 (3x3, pad 1) or 1                                                  */
+  int flip;                        /* 1: use tap (2-kh, 2-kw) for the shift (dgrad)                        */
+  int out_channels;                /* W modes: O                                                           */
+} b200pdm_operand;
+
+typedef struct {
+  b200pdm_operand a, b;
+  int64_t M, N, K;  /* logical GEMM extents; for conv modes K = taps * reduced channels (informational)   */
+  int Z1, Z2;       /* batch grid, z = z2*Z1 + z1; use 1,1 for a plain GEMM                                */
+  void* out;        /* bf16 or fp32 [M, N] row-major, pitch ldo, batch strides obs1/obs2                   */
+  int out_fp32;
+  int64_t ldo, obs1, obs2;
+  const float* bias;        /* fp32 [N] or NULL                                                           */
+  const float* rowbias;     /* fp32 [M / rows_per_group, ld_rowbias] or NULL (time-embedding broadcast)   */
+  int64_t ld_rowbias;
+  int rows_per_group;
+  const void* residual;     /* bf16 [M, N] pitch ldr (+ rbs1/rbs2 batch strides) or NULL                  */
+  int64_t ldr, rbs1, rbs2;
+  float alpha;              /* out = alpha*acc + bias + rowbias + residual                                */
+  int accumulate;           /* fp32 out only: out += ... (atomic adds; required when splits > 1)          */
+  int splits;               /* split-K factor, 0/1 = none                                                  */
+  int block_n;              /* 0 = choose                                                                  */
+} b200pdm_gemm_desc;
+
+/* Generic launch. */
+int b200pdm_gemm(const b200pdm_gemm_desc* desc, b200pdm_stream_t stream);
+
+/* out[M,N] = x[M,K] . w[N,K]^T + bias + residual.            Replaces F.linear at pdm/models/unet/blocks.py:49
+ * (GEGLU proj), :244,:251-252,:283 (attention projections), diffusers Transformer2DModel.proj_in/proj_out
+ * (called at blocks.py:1172,1221), FeedForward.net[2], TimestepEmbedding (unet_2d_conditional.py:1521) and
+ * time_emb_proj (blocks.py:337,538).                                                                       */
+int b200pdm_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                       const void* residual, int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M,
+                       int64_t N, int64_t K, b200pdm_stream_t stream);
+/* dx[M,K] = dy[M,N] . w[N,K] (+ residual[M,K]); autograd backward of the call sites above.                 */
+int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual,
+                         int64_t ldr, void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K,
+                         b200pdm_stream_t stream);
+/* dw[N,K] += dy[M,N]^T . x[M,K]   (fp32 accumulate, split-K).                                              */
+int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
+                         int64_t M, int64_t N, int64_t K, b200pdm_stream_t stream);
+
+/* 3x3 (pad 1, stride 1|2) or 1x1 convolution as implicit GEMM over NHWC bf16:
+ *   out[b,ho,wo,:Cout] = sum_tap x[b, ho*s+kh-1, wo*s+kw-1, :Cin] . w[:, tap, :Cin]^T + bias + rowbias[b] + residual
+ * Replaces conv1/conv2/conv_shortcut at blocks.py:332,374,377,533,575,578 (rowbias = the time-embedding add of
+ * blocks.py:339-341), conv_in/conv_out at unet_2d_conditional.py:1616,1723 and the Down/Upsample2D convs.   */
+int b200pdm_conv_fwd(const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias,
+                     const float* rowbias, int64_t ld_rowbias, const void* residual, int64_t ldr, void* out,
+                     int64_t ldo, int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride,
+                     b200pdm_stream_t stream);
+/* dx[b,h,w,:Cin] = sum_tap dy[b, h+1-kh, w+1-kw, :Cout] . w[:, tap, :Cin] (+ residual)  (stride 1 only).    */
+int b200pdm_conv_dgrad(const void* dy, int64_t lddy, const void* w, int64_t w_ild, const void* residual,
+                       int64_t ldr, void* dx, int64_t lddx, int batch, int h, int w_sp, int c_in, int c_out,
+                       int ksize, b200pdm_stream_t stream);
+/* dw[Cout][tap][:Cin] += sum_pixels dy[p,:Cout]^T . x[shift_tap(p), :Cin]   (fp32 accumulate, split-K).      */
+int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t w_ild,
+                       int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride,
+                       b200pdm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HBM-bound kernels
+ * ------------------------------------------------------------------------------------------------------------ */
+/* GroupNorm (+ optional SiLU) over NHWC bf16.  groups*cpg == C.  Saves stats = interleaved (mean, rstd),
+ * fp32 [2*B*groups].
+ * Replaces norm1+nonlinearity / norm2+nonlinearity at blocks.py:318-319,348,371,519-520,549,572,
+ * conv_norm_out+conv_act at unet_2d_conditional.py:1720-1722, and Transformer2DModel.norm (silu=0).        */
+int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                          float* stats, int batch, int hw, int C, int groups, float eps, int silu,
+                          b200pdm_stream_t stream);
+/* dx, and dgamma/dbeta += (fp32).  workspace: fp32 [2 * batch * groups].                                    */
+int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
+                          const float* beta, const float* stats, void* dx, int64_t lddx, float* dgamma,
+                          float* dbeta, float* workspace, int batch, int hw, int C, int groups, int silu,
+                          b200pdm_stream_t stream);
+/* LayerNorm over the last dim of [rows, C] bf16 (diffusers BasicTransformerBlock.norm1/2/3).                */
+int b200pdm_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                          float* mean, float* rstd, int64_t rows, int C, float eps, b200pdm_stream_t stream);
+int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma,
+                          float* dbeta, int64_t rows, int C, b200pdm_stream_t stream);
+/* GEGLU: out[r, f] = p[r, f] * gelu_erf(p[r, F + f]) for p = proj output [rows, 2F] (blocks.py:54-59).      */
+int b200pdm_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t ldo, int64_t rows, int F,
+                      b200pdm_stream_t stream);
+int b200pdm_geglu_bwd(const void* dout, int64_t lddo, const void* proj, int64_t ldp, void* dproj, int64_t lddp,
+                      int64_t rows, int F, b200pdm_stream_t stream);
+/* Row softmax of fp32 scores -> bf16 probabilities (unfused attention path, blocks.py:275-277).             */
+int b200pdm_softmax_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols, float scale,
+                        b200pdm_stream_t stream);
+/* ds = scale * p * (dp - sum(dp*p)) ; dp fp32 in, ds bf16 out.                                              */
+int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ldp, void* ds, int64_t ldds,
+                        int64_t rows, int cols, float scale, b200pdm_stream_t stream);
+/* Column sums: out[n] += sum_m x[m, n]  (bias gradients).                                                   */
+int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream);
+/* Elementwise helpers over [rows, C] bf16 matrices with pitches. */
+int b200pdm_add(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows, int C,
+                b200pdm_stream_t stream);
+int b200pdm_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int C,
+                   b200pdm_stream_t stream);
+int b200pdm_silu_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream);
+int b200pdm_silu_bwd_f32(const float* dy, const float* x, float* dx, int64_t n, b200pdm_stream_t stream);
+/* Nearest 2x upsample NHWC (diffusers Upsample2D, F.interpolate(scale=2, nearest)) and its adjoint.         */
+int b200pdm_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int batch, int h, int w, int C,
+                           b200pdm_stream_t stream);
+int b200pdm_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int batch, int h, int w, int C,
+                           b200pdm_stream_t stream);
+/* Zero-insertion 2x (adjoint of stride-2 subsampling): y[b,2h,2w,:] = x[b,h,w,:], zeros elsewhere.          */
+int b200pdm_zero_insert2x(const void* x, int64_t ldx, void* y, int64_t ldy, int batch, int h, int w, int C,
+                          b200pdm_stream_t stream);
+/* NCHW fp32 <-> NHWC bf16 (model boundary: sample in, .sample out; unet_2d_conditional.py:1417,1725).       */
+int b200pdm_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int batch, int C, int hw,
+                                  b200pdm_stream_t stream);
+int b200pdm_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int batch, int C, int hw,
+                                  b200pdm_stream_t stream);
+/* Sinusoidal timestep embedding, flip_sin_to_cos=True, shift 0 (diffusers Timesteps; unet...py:1514-1519):
+ * out[b, :half] = cos(t*f), out[b, half:] = sin(t*f), f_i = exp(-ln(10000) * i / half); bf16 out.           */
+int b200pdm_timestep_embedding(const int64_t* t, void* out, int64_t ldo, int batch, int dim,
+                               b200pdm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused distillation loss (trainer.py:2451-2486): min-SNR weighted MSE(pred, target) + output-KD MSE(pred, teacher)
+ * + mean over feature maps of MSE(student_feat, teacher_feat), forward AND gradients in one pass per tensor.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* pred/target/teacher: fp32 [B, n_per_sample]; snr_w: fp32 [B] (min(snr+1,gamma)/(snr+1), trainer.py:2457-2466).
+ * sums[0] += sum_b w_b * mean_chw (p-y)^2 / B     (diff loss)
+ * sums[1] += mean (p - p_T)^2                     (distillation loss)
+ * dpred = w_diff * 2 w_b (p-y)/(B n) + w_kd * 2 (p-p_T)/(B n)                                              */
+int b200pdm_pred_loss(const float* pred, const float* target, const float* teacher, const float* snr_w,
+                      float* dpred, float* sums, int batch, int64_t n_per_sample, float w_diff, float w_kd,
+                      b200pdm_stream_t stream);
+/* One feature pair (bf16, same pitch layout): sums[2] += mean((s-t)^2) / n_maps ; ds = scale * 2 (s-t)/numel
+ * with scale = w_block / n_maps (trainer.py:2475-2481).                                                    */
+int b200pdm_feature_loss(const void* s, const void* t, void* ds, float* sums, int64_t numel, float inv_maps,
+                         float w_block, b200pdm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-tensor AdamW over the flat parameter arena (torch.optim.AdamW semantics; trainer.py:265-284,2327,2814).
+ * One launch updates p, m, v (fp32), writes the bf16 shadow copy and optionally zeroes the gradient.
+ * The bilevel trainer (trainer.py:2795-2816) calls it with a second (m, v, step) state set.
+ * ------------------------------------------------------------------------------------------------------------ */
+int b200pdm_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int64_t step, float grad_scale, int zero_grad,
+                       b200pdm_stream_t stream);
+/* shadow = bf16(p) (after load_state_dict / a foreign optimizer touched the masters). */
+int b200pdm_refresh_shadow(const float* p, void* shadow_bf16, int64_t n, b200pdm_stream_t stream);
+
+/* Forward diffusion (diffusers DDIMScheduler.add_noise / get_velocity at trainer.py:2430,2443):
+ * noisy = sa[t_b] x0 + sb[t_b] eps ; target = sa[t_b] eps - sb[t_b] x0 ; fp32.                             */
+int b200pdm_diffusion_prep(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
+                           const float* sqrt_1macp, float* noisy, float* vtarget, int batch, int64_t n_per_sample,
+                           b200pdm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PDM_H_ */

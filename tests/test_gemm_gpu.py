@@ -1,0 +1,165 @@
+"""Parity of the tcgen05 GEMM / implicit-GEMM convolution core against torch fp32 references (bf16 inputs).
+
+Tolerance (north star): 2e-2 relative for bf16 kernels; here inputs are bf16-exact so the only differences are the
+fp32 accumulation order and the final bf16 rounding -> we check max-abs error relative to the output scale.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _k():
+    from unlearn_ft_b200 import kernels
+    return kernels
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def rand2d(rows, cols, seed, scale=1.0):
+    k = _k()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = k.alloc2d(rows, cols)
+    t.copy_(torch.randn(rows, cols, device="cuda", generator=g) * scale)
+    return t
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (1232, 320, 1024), (4096, 176, 320),
+                                   (16, 1280, 320), (300, 170, 200), (128, 2720, 640)])
+def test_linear_fwd(M, N, K):
+    k = _k()
+    x, w = rand2d(M, K, 1), rand2d(N, K, 2, 0.05)
+    bias = torch.randn(N, device="cuda")
+    res = rand2d(M, N, 3)
+    out = k.linear_fwd(x, w, bias, res)
+    ref = x.float() @ w.float().t() + bias + res.float()
+    assert rel_err(out, ref) < 1e-2
+    out32 = k.linear_fwd(x, w, None, None, out_fp32=True)
+    assert rel_err(out32, x.float() @ w.float().t()) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1232, 320, 1024), (4096, 176, 320), (300, 170, 200)])
+def test_linear_dgrad(M, N, K):
+    k = _k()
+    dy, w = rand2d(M, N, 1), rand2d(N, K, 2, 0.05)
+    dx = k.linear_dgrad(dy, w)
+    assert rel_err(dx, dy.float() @ w.float()) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (4096, 320, 320), (1232, 176, 1024), (65536, 170, 320), (300, 72, 200)])
+def test_linear_wgrad(M, N, K):
+    k = _k()
+    dy, x = rand2d(M, N, 1), rand2d(M, K, 2)
+    dw = torch.zeros(N, k.round8(K), device="cuda")[:, :K]
+    k.linear_wgrad(dy, x, dw)
+    ref = dy.float().t() @ x.float()
+    assert rel_err(dw, ref) < 1e-3
+    k.linear_wgrad(dy, x, dw)  # accumulates
+    assert rel_err(dw, 2 * ref) < 1e-3
+
+
+def nhwc(x):  # [B,C,H,W] fp32 -> 2d bf16
+    k = _k()
+    B, C, H, W = x.shape
+    t = k.alloc2d(B * H * W, C)
+    t.copy_(x.permute(0, 2, 3, 1).reshape(B * H * W, C))
+    return t
+
+
+def from2d(t, B, H, W):
+    return t.float().reshape(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def pack_w(w):  # [O,I,kh,kw] fp32 -> bf16 [O, taps, I] view with padded I
+    k = _k()
+    O, I, kh, kw = w.shape
+    ild = k.round8(I)
+    buf = torch.zeros(O, kh * kw, ild, device="cuda", dtype=torch.bfloat16)
+    buf[:, :, :I] = w.permute(0, 2, 3, 1).reshape(O, kh * kw, I)
+    return buf[:, :, :I]
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, ksize, stride
+    (2, 64, 64, 64, 128, 3, 1),
+    (2, 64, 64, 320, 170, 3, 1),
+    (3, 32, 32, 170, 320, 3, 1),
+    (2, 16, 16, 680, 1280, 3, 1),
+    (4, 8, 8, 1280, 680, 3, 1),
+    (3, 8, 8, 128, 64, 3, 1),
+    (2, 64, 64, 4, 320, 3, 1),
+    (2, 64, 64, 320, 4, 3, 1),
+    (2, 32, 32, 320, 640, 1, 1),
+    (2, 64, 64, 320, 320, 3, 2),
+    (2, 16, 16, 1280, 1280, 3, 2),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co,ks,st", CONV_CASES)
+def test_conv_fwd(B, H, W, Ci, Co, ks, st):
+    k = _k()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, Ci, H, W, device="cuda", generator=g).bfloat16().float()
+    w = (torch.randn(Co, Ci, ks, ks, device="cuda", generator=g) * 0.05).bfloat16().float()
+    bias = torch.randn(Co, device="cuda", generator=g)
+    temb = torch.randn(B, Co, device="cuda", generator=g)
+    out = k.conv_fwd(nhwc(x), pack_w(w), B, H, W, Co, ks, st, bias=bias, rowbias=temb)
+    ref = F.conv2d(x, w, bias, stride=st, padding=ks // 2) + temb[:, :, None, None]
+    assert rel_err(from2d(out, B, H // st, W // st), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co,ks,st", [c for c in CONV_CASES if c[6] == 1])
+def test_conv_dgrad(B, H, W, Ci, Co, ks, st):
+    k = _k()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dy = torch.randn(B, Co, H, W, device="cuda", generator=g).bfloat16().float()
+    w = (torch.randn(Co, Ci, ks, ks, device="cuda", generator=g) * 0.05).bfloat16().float()
+    dx = k.conv_dgrad(nhwc(dy), pack_w(w), B, H, W, Ci, ks)
+    ref = torch.nn.grad.conv2d_input((B, Ci, H, W), w, dy, padding=ks // 2)
+    assert rel_err(from2d(dx, B, H, W), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co,ks,st", CONV_CASES)
+def test_conv_wgrad(B, H, W, Ci, Co, ks, st):
+    k = _k()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, Ci, H, W, device="cuda", generator=g).bfloat16().float()
+    dy = torch.randn(B, Co, H // st, W // st, device="cuda", generator=g).bfloat16().float()
+    ild = k.round8(Ci)
+    dw = torch.zeros(Co, ks * ks, ild, device="cuda")[:, :, :Ci]
+    k.conv_wgrad(nhwc(dy), nhwc(x), dw, B, H, W, ks, st)
+    ref = torch.nn.grad.conv2d_weight(x, (Co, Ci, ks, ks), dy, stride=st, padding=ks // 2)
+    ref = ref.permute(0, 2, 3, 1).reshape(Co, ks * ks, Ci)
+    assert rel_err(dw, ref) < 2e-3
+
+
+def test_bmm_attention_shapes():
+    """QK^T (K-major x K-major, batched over (head, batch) with strides) and PV (K-major x MN-major)."""
+    k = _k()
+    B, L, Lk, H, D = 2, 256, 77, 5, 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q = torch.randn(B, L, H * D, device="cuda", generator=g).bfloat16()
+    kk = torch.randn(B, Lk, H * D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Lk, H * D, device="cuda", generator=g).bfloat16()
+    Lkp = k.round8(Lk)
+    s = torch.zeros(B, H, L, Lkp, device="cuda", dtype=torch.float32)
+    k.bmm(q, kk, s, M=L, N=Lk, K=D, Z1=H, Z2=B, a_ld=H * D, a_bs=(D, L * H * D), b_ld=H * D, b_bs=(D, Lk * H * D),
+          o_ld=Lkp, o_bs=(L * Lkp, H * L * Lkp), alpha=0.125)
+    qh = q.float().view(B, L, H, D).transpose(1, 2)
+    kh = kk.float().view(B, Lk, H, D).transpose(1, 2)
+    vh = v.float().view(B, Lk, H, D).transpose(1, 2)
+    ref = (qh @ kh.transpose(-1, -2)) * 0.125
+    assert rel_err(s[..., :Lk], ref) < 1e-4
+    p = torch.zeros(B, H, L, Lkp, device="cuda", dtype=torch.bfloat16)
+    k.softmax_fwd(s, p, B * H * L, Lk, 1.0)
+    pref = torch.softmax(ref, -1)
+    assert rel_err(p[..., :Lk], pref) < 1e-2
+    o = torch.zeros(B, L, H * D, device="cuda", dtype=torch.bfloat16)
+    k.bmm(p, v, o, b_mn=True, M=L, N=D, K=Lk, Z1=H, Z2=B, a_ld=Lkp, a_bs=(L * Lkp, H * L * Lkp), b_ld=H * D,
+          b_bs=(D, Lk * H * D), o_ld=H * D, o_bs=(D, L * H * D))
+    oref = (p[..., :Lk].float() @ vh).transpose(1, 2).reshape(B, L, H * D)
+    assert rel_err(o, oref) < 1e-2

@@ -1,0 +1,202 @@
+"""Parity of the HBM-bound kernels (norms, GEGLU, softmax, resampling, loss, AdamW) against torch fp32 references."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _k():
+    from unlearn_ft_b200 import kernels
+    return kernels
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def rand2d(rows, cols, seed, scale=1.0, shift=0.0):
+    k = _k()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = k.alloc2d(rows, cols)
+    t.copy_(torch.randn(rows, cols, device="cuda", generator=g) * scale + shift)
+    return t
+
+
+@pytest.mark.parametrize("B,hw,C,G,silu,eps", [(2, 4096, 320, 32, 1, 1e-5), (2, 1024, 170, 17, 1, 1e-5),
+                                                (3, 64, 2560, 32, 1, 1e-5), (2, 256, 1280, 32, 0, 1e-6),
+                                                (2, 1024, 960, 32, 1, 1e-5), (2, 256, 1040, 26, 1, 1e-5)])
+def test_groupnorm_fwd_bwd(B, hw, C, G, silu, eps):
+    k = _k()
+    x = rand2d(B * hw, C, 0, 2.0, 0.5)
+    dy = rand2d(B * hw, C, 1)
+    gamma = torch.randn(C, device="cuda") * 0.5 + 1
+    beta = torch.randn(C, device="cuda") * 0.5
+    y, stats = k.groupnorm_fwd(x, gamma, beta, B, hw, G, eps, silu)
+    xr = x.float().reshape(B, hw, C).permute(0, 2, 1).contiguous().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.group_norm(xr, G, gr, br, eps)
+    if silu:
+        yr = F.silu(yr)
+    assert rel_err(y, yr.permute(0, 2, 1).reshape(B * hw, C)) < 1e-2
+    yr.backward(dy.float().reshape(B, hw, C).permute(0, 2, 1))
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = k.groupnorm_bwd(dy, x, gamma, beta, stats, dgamma, dbeta, B, hw, G, silu)
+    assert rel_err(dx, xr.grad.permute(0, 2, 1).reshape(B * hw, C)) < 1e-2
+    assert rel_err(dgamma, gr.grad) < 2e-3
+    assert rel_err(dbeta, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1024, 640), (300, 1280)])
+def test_layernorm_fwd_bwd(rows, C):
+    k = _k()
+    x, dy = rand2d(rows, C, 0, 2.0, 0.3), rand2d(rows, C, 1)
+    gamma = torch.randn(C, device="cuda") * 0.5 + 1
+    beta = torch.randn(C, device="cuda") * 0.5
+    y, mean, rstd = k.layernorm_fwd(x, gamma, beta, 1e-5)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    assert rel_err(y, yr) < 1e-2
+    yr.backward(dy.float())
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = k.layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta)
+    assert rel_err(dx, xr.grad) < 1e-2
+    assert rel_err(dgamma, gr.grad) < 2e-3
+    assert rel_err(dbeta, br.grad) < 2e-3
+
+
+def test_geglu():
+    k = _k()
+    rows, Fh = 1000, 680
+    p, d = rand2d(rows, 2 * Fh, 0), rand2d(rows, Fh, 1)
+    pr = p.float().requires_grad_(True)
+    h, g = pr.chunk(2, -1)
+    yr = h * F.gelu(g)
+    y = k.geglu_fwd(p)
+    assert rel_err(y, yr) < 1e-2
+    yr.backward(d.float())
+    dp = k.geglu_bwd(d, p)
+    assert rel_err(dp, pr.grad) < 1e-2
+
+
+def test_softmax_bwd():
+    k = _k()
+    rows, cols = 512, 1000
+    s = torch.randn(rows, 1000, device="cuda") * 3
+    p = torch.zeros(rows, 1000, device="cuda", dtype=torch.bfloat16)
+    k.softmax_fwd(s, p, rows, cols, 0.125)
+    sr = s.clone().requires_grad_(True)
+    pr = torch.softmax(sr * 0.125, -1)
+    assert rel_err(p, pr) < 1e-2
+    dp = torch.randn(rows, cols, device="cuda")
+    # use the bf16-rounded p as the reference's p so only the kernel arithmetic is compared
+    pb = p.float()
+    ref = 0.125 * pb * (dp - (dp * pb).sum(-1, keepdim=True))
+    ds = torch.zeros(rows, cols, device="cuda", dtype=torch.bfloat16)
+    k.softmax_bwd(dp, p, ds, rows, cols, 0.125)
+    assert rel_err(ds, ref) < 1e-2
+
+
+def test_colsum_add_copy():
+    k = _k()
+    x, y = rand2d(5000, 170, 0), rand2d(5000, 170, 1)
+    out = torch.zeros(170, device="cuda")
+    k.colsum(x, out)
+    assert rel_err(out, x.float().sum(0)) < 1e-4
+    assert rel_err(k.add(x, y), x.float() + y.float()) < 1e-2
+    dst = k.alloc2d(5000, 512, zero=True)
+    k.copy2d(x, dst[:, 320:320 + 170])
+    assert torch.equal(dst[:, 320:490], x) and dst[:, :320].abs().sum() == 0
+
+
+def test_resample():
+    k = _k()
+    B, H, W, C = 2, 8, 16, 170
+    x = rand2d(B * H * W, C, 0)
+    up = k.upsample2x_fwd(x, B, H, W)
+    xr = x.float().reshape(B, H, W, C).permute(0, 3, 1, 2)
+    ref = F.interpolate(xr, scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).reshape(B * 4 * H * W, C)
+    assert torch.equal(up.float(), ref)
+    dy = rand2d(B * 4 * H * W, C, 1)
+    dx = k.upsample2x_bwd(dy, B, H, W)
+    dref = dy.float().reshape(B, H, 2, W, 2, C).sum((2, 4)).reshape(B * H * W, C)
+    assert rel_err(dx, dref) < 1e-2
+    zi = k.zero_insert2x(x, B, H, W).float().reshape(B, 2 * H, 2 * W, C)
+    assert torch.equal(zi[:, ::2, ::2], x.float().reshape(B, H, W, C))
+    assert zi[:, 1::2].abs().sum() == 0 and zi[:, :, 1::2].abs().sum() == 0
+
+
+def test_layout_and_timestep():
+    k = _k()
+    x = torch.randn(3, 4, 64, 64, device="cuda")
+    t2 = k.nchw_f32_to_nhwc_bf16(x)
+    assert torch.equal(t2.float().reshape(3, 64, 64, 4).permute(0, 3, 1, 2), x.bfloat16().float())
+    back = k.nhwc_bf16_to_nchw_f32(t2, 3, 64, 64)
+    assert torch.equal(back, x.bfloat16().float())
+    t = torch.tensor([0, 1, 500, 999], device="cuda")
+    emb = k.timestep_embedding(t, 320).float()
+    half = 160
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    arg = t[:, None].float() * freq[None]
+    ref = torch.cat([torch.cos(arg), torch.sin(arg)], -1)
+    assert (emb - ref).abs().max() < 1e-2
+
+
+def test_losses():
+    k = _k()
+    B, n = 4, 4 * 64 * 64
+    pred, tgt, tea = (torch.randn(B, n, device="cuda") for _ in range(3))
+    w = torch.rand(B, device="cuda") + 0.1
+    sums = torch.zeros(4, device="cuda")
+    dpred = k.pred_loss(pred, tgt, tea, w, sums, 1.0, 2.0)
+    pr = pred.clone().requires_grad_(True)
+    l_d = (((pr - tgt) ** 2).mean(1) * w).mean()
+    l_k = F.mse_loss(pr, tea)
+    (1.0 * l_d + 2.0 * l_k).backward()
+    assert abs(sums[0].item() - l_d.item()) / l_d.item() < 1e-5
+    assert abs(sums[1].item() - l_k.item()) / l_k.item() < 1e-5
+    assert rel_err(dpred, pr.grad) < 1e-5
+    s = torch.randn(2, 1280, 16, 16, device="cuda").bfloat16()
+    t = torch.randn(2, 1280, 16, 16, device="cuda").bfloat16()
+    ds = k.feature_loss(s, t, sums, 9, 0.1)
+    sr = s.float().requires_grad_(True)
+    lb = F.mse_loss(sr, t.float()) / 9
+    (0.1 * lb).backward()
+    assert abs(sums[2].item() - lb.item()) / lb.item() < 1e-4
+    assert rel_err(ds, sr.grad) < 1e-2
+
+
+def test_adamw_matches_torch():
+    k = _k()
+    n = 1_000_003
+    p = torch.randn(n, device="cuda")
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    shadow = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ref_p.grad = g.clone()
+        opt.step()
+        k.adamw_step(p, g, m, v, shadow, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+        assert g.abs().sum() == 0  # zeroed
+    assert rel_err(p, ref_p.data) < 1e-5
+    assert torch.equal(shadow, p.bfloat16())
+
+
+def test_diffusion_prep():
+    k = _k()
+    B = 4
+    x0, eps = torch.randn(B, 4, 64, 64, device="cuda"), torch.randn(B, 4, 64, 64, device="cuda")
+    t = torch.tensor([0, 10, 500, 999], device="cuda")
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, device="cuda") ** 2
+    acp = torch.cumprod(1 - betas, 0)
+    sa, sb = acp.sqrt(), (1 - acp).sqrt()
+    noisy, vt = k.diffusion_prep(x0, eps, t, sa, sb)
+    a, s = sa[t].view(B, 1, 1, 1), sb[t].view(B, 1, 1, 1)
+    assert rel_err(noisy, a * x0 + s * eps) < 1e-6
+    assert rel_err(vt, a * eps - s * x0) < 1e-6

@@ -1,0 +1,430 @@
+// HBM-bound elementwise / small-reduction kernels: GEGLU, row softmax, column sums, add/copy with pitches,
+// SiLU on the time embedding, nearest-2x upsample and adjoints, layout conversion at the model boundary,
+// sinusoidal timestep embedding, forward-diffusion prep.  All use 16-byte bf16x8 accesses on the common path and
+// grid-stride loops sized to a multiple of the SM count.
+#include "common.cuh"
+#include "../../include/b200pdm.h"
+
+#include <atomic>
+
+namespace b200 {
+extern std::atomic<uint64_t> g_launches;
+void set_err(const char* fmt, const char* a);
+
+static inline int grid_for(int64_t work_items, int threads) {
+  int64_t b = (work_items + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+// ---------------------------------------------------------------- GEGLU
+// proj [rows, 2F] : value half [0,F), gate half [F,2F).  out = value * gelu_erf(gate).
+__global__ void geglu_fwd_kernel(const bf16* __restrict__ p, int64_t ldp, bf16* __restrict__ o, int64_t ldo,
+                                 int64_t rows, int F, int fvec) {
+  const int64_t total = rows * fvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / fvec;
+    int c0 = (int)(i - r * fvec) * 8;
+    float h[8], g[8], y[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p + r * ldp + c0), h);
+    unpack8(*reinterpret_cast<const bf16x8*>(p + r * ldp + F + c0), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = h[j] * gelu_erf_f(g[j]);
+    *reinterpret_cast<bf16x8*>(o + r * ldo + c0) = pack8(y);
+  }
+}
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ d, int64_t ldd, const bf16* __restrict__ p, int64_t ldp,
+                                 bf16* __restrict__ dp, int64_t lddp, int64_t rows, int F, int fvec) {
+  const int64_t total = rows * fvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / fvec;
+    int c0 = (int)(i - r * fvec) * 8;
+    float h[8], g[8], dy[8], dh[8], dg[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(p + r * ldp + c0), h);
+    unpack8(*reinterpret_cast<const bf16x8*>(p + r * ldp + F + c0), g);
+    unpack8(*reinterpret_cast<const bf16x8*>(d + r * ldd + c0), dy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dh[j] = dy[j] * gelu_erf_f(g[j]);
+      dg[j] = dy[j] * h[j] * gelu_erf_grad_f(g[j]);
+    }
+    *reinterpret_cast<bf16x8*>(dp + r * lddp + c0) = pack8(dh);
+    *reinterpret_cast<bf16x8*>(dp + r * lddp + F + c0) = pack8(dg);
+  }
+}
+
+// ---------------------------------------------------------------- softmax (unfused attention path)
+// one block per row; fp32 scores in, bf16 probabilities out. p = softmax(scale * s).
+__global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf16* __restrict__ p, int64_t ldp, int cols,
+                                   float scale) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float* sr = s + row * lds;
+  bf16* pr = p + row * ldp;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, sr[c]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf((sr[c] - mx) * scale);
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) pr[c] = __float2bfloat16(__expf((sr[c] - mx) * scale) * inv);
+}
+// ds = scale * p * (dp - sum_j dp_j p_j)
+__global__ void softmax_bwd_kernel(const float* __restrict__ dp, int64_t lddp, const bf16* __restrict__ p, int64_t ldp,
+                                   bf16* __restrict__ ds, int64_t ldds, int cols, float scale) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float* dr = dp + row * lddp;
+  const bf16* pr = p + row * ldp;
+  bf16* sr = ds + row * ldds;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) dot += dr[c] * __bfloat162float(pr[c]);
+  dot = block_sum(dot, red);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    sr[c] = __float2bfloat16(scale * __bfloat162float(pr[c]) * (dr[c] - dot));
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+// grid (col_blocks, row_slices); block (32, 8): thread (tx,ty) sums column tx over its rows; smem reduce over ty.
+__global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t rows, int cols,
+                              int rows_per_slice) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t r1 = min(rows, r0 + rows_per_slice);
+  float acc = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += __bfloat162float(x[r * ldx + c]);
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ---------------------------------------------------------------- add / copy with pitches
+__global__ void add_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ b, int64_t ldb,
+                           bf16* __restrict__ o, int64_t ldo, int64_t rows, int C, int cvec) {
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cvec;
+    int c0 = (int)(i - r * cvec) * 8;
+    int nv = min(8, C - c0);
+    if (nv == 8) {
+      float x[8], y[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(a + r * lda + c0), x);
+      unpack8(*reinterpret_cast<const bf16x8*>(b + r * ldb + c0), y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += y[j];
+      *reinterpret_cast<bf16x8*>(o + r * ldo + c0) = pack8(x);
+    } else {
+      for (int j = 0; j < nv; ++j)
+        o[r * ldo + c0 + j] =
+            __float2bfloat16(__bfloat162float(a[r * lda + c0 + j]) + __bfloat162float(b[r * ldb + c0 + j]));
+    }
+  }
+}
+__global__ void copy2d_kernel(const bf16* __restrict__ s, int64_t lds, bf16* __restrict__ d, int64_t ldd, int64_t rows,
+                              int C, int cvec) {
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cvec;
+    int c0 = (int)(i - r * cvec) * 8;
+    int nv = min(8, C - c0);
+    if (nv == 8) {
+      *reinterpret_cast<bf16x8*>(d + r * ldd + c0) = *reinterpret_cast<const bf16x8*>(s + r * lds + c0);
+    } else {
+      for (int j = 0; j < nv; ++j) d[r * ldd + c0 + j] = s[r * lds + c0 + j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- SiLU on the (small) time embedding
+__global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(silu_f(x[i]));
+}
+__global__ void silu_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
+                                    int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * silu_grad_f(x[i]);
+}
+
+// ---------------------------------------------------------------- nearest 2x upsample, adjoint, zero insertion
+// mode 0: y[b,2h+dy,2w+dx,:] = x[b,h,w,:]   (index over y)
+// mode 1: dx[b,h,w,:] = sum_{dy,dx} dy[b,2h+dy,2w+dx,:]   (index over x)
+// mode 2: y[b,2h,2w,:] = x ; other positions 0   (index over y)
+template <int MODE>
+__global__ void resample2x_kernel(const bf16* __restrict__ src, int64_t lds, bf16* __restrict__ dst, int64_t ldd,
+                                  int batch, int h, int w, int C, int cvec) {
+  // (h, w) is the LOW resolution grid
+  const int H2 = 2 * h, W2 = 2 * w;
+  const int64_t total = (MODE == 1 ? (int64_t)batch * h * w : (int64_t)batch * H2 * W2) * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t pix = i / cvec;
+    int c0 = (int)(i - pix * cvec) * 8;
+    int nv = min(8, C - c0);
+    if (MODE == 1) {
+      int ww = (int)(pix % w);
+      int64_t t = pix / w;
+      int hh = (int)(t % h);
+      int b = (int)(t / h);
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const bf16* sp = src + (((int64_t)b * H2 + 2 * hh + dy) * W2 + 2 * ww + dx) * lds + c0;
+          if (nv == 8) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(sp), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          } else {
+            for (int j = 0; j < nv; ++j) acc[j] += __bfloat162float(sp[j]);
+          }
+        }
+      bf16* dp = dst + pix * ldd + c0;
+      if (nv == 8)
+        *reinterpret_cast<bf16x8*>(dp) = pack8(acc);
+      else
+        for (int j = 0; j < nv; ++j) dp[j] = __float2bfloat16(acc[j]);
+    } else {
+      int ww = (int)(pix % W2);
+      int64_t t = pix / W2;
+      int hh = (int)(t % H2);
+      int b = (int)(t / H2);
+      bf16* dp = dst + pix * ldd + c0;
+      const bool zero = (MODE == 2) && ((hh | ww) & 1);
+      const bf16* sp = src + (((int64_t)b * h + (hh >> 1)) * w + (ww >> 1)) * lds + c0;
+      if (nv == 8) {
+        bf16x8 v;
+        if (zero) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v.v[j] = __floats2bfloat162_rn(0.f, 0.f);
+        } else {
+          v = *reinterpret_cast<const bf16x8*>(sp);
+        }
+        *reinterpret_cast<bf16x8*>(dp) = v;
+      } else {
+        for (int j = 0; j < nv; ++j) dp[j] = zero ? __float2bfloat16(0.f) : sp[j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- model-boundary layout conversion
+// NCHW fp32 -> NHWC bf16 (tiny C: 4 latent channels) and back.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t ldy, int batch, int C,
+                                    int hw) {
+  const int64_t total = (int64_t)batch * hw * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int p = (int)(t % hw);
+    int b = (int)(t / hw);
+    y[((int64_t)b * hw + p) * ldy + c] = __float2bfloat16(x[((int64_t)b * C + c) * hw + p]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ y, int batch, int C,
+                                    int hw) {
+  const int64_t total = (int64_t)batch * hw * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int p = (int)(i % hw);
+    int64_t t = i / hw;
+    int c = (int)(t % C);
+    int b = (int)(t / C);
+    y[i] = __bfloat162float(x[((int64_t)b * hw + p) * ldx + c]);
+  }
+}
+
+// ---------------------------------------------------------------- timestep embedding (flip_sin_to_cos, shift 0)
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, bf16* __restrict__ out, int64_t ldo, int batch,
+                                          int dim) {
+  const int half = dim / 2;
+  const int total = batch * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int b = i / half, k = i - b * half;
+    // diffusers get_timestep_embedding: exponent = -ln(max_period) * arange(half) / (half - shift), shift = 0
+    float freq = expf(-9.210340371976184f * (float)k / (float)half);
+    float arg = (float)t[b] * freq;
+    float s, c;
+    sincosf(arg, &s, &c);
+    out[(int64_t)b * ldo + k] = __float2bfloat16(c);          // flip_sin_to_cos: [cos | sin]
+    out[(int64_t)b * ldo + half + k] = __float2bfloat16(s);
+  }
+}
+
+// ---------------------------------------------------------------- forward diffusion prep
+__global__ void diffusion_prep_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                      const int64_t* __restrict__ t, const float* __restrict__ sa,
+                                      const float* __restrict__ sb, float* __restrict__ noisy, float* __restrict__ vt,
+                                      int batch, int64_t n) {
+  const int64_t total = (int64_t)batch * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / n);
+    float a = sa[t[b]], s = sb[t[b]];
+    float x = x0[i], e = noise[i];
+    if (noisy) noisy[i] = a * x + s * e;
+    if (vt) vt[i] = a * e - s * x;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+#define BF(p) reinterpret_cast<bf16*>(p)
+#define CBF(p) reinterpret_cast<const bf16*>(p)
+
+extern "C" {
+
+int b200pdm_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t ldo, int64_t rows, int F,
+                      b200pdm_stream_t stream) {
+  if (F % 8 || ldp % 8 || ldo % 8) {
+    set_err("geglu: F and pitches must be multiples of 8", "");
+    return B200PDM_ERR_UNSUPPORTED;
+  }
+  const int fvec = F / 8;
+  geglu_fwd_kernel<<<grid_for(rows * fvec, 256), 256, 0, STREAM>>>(CBF(proj), ldp, BF(out), ldo, rows, F, fvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_geglu_bwd(const void* dout, int64_t lddo, const void* proj, int64_t ldp, void* dproj, int64_t lddp,
+                      int64_t rows, int F, b200pdm_stream_t stream) {
+  if (F % 8 || ldp % 8 || lddo % 8 || lddp % 8) return B200PDM_ERR_UNSUPPORTED;
+  const int fvec = F / 8;
+  geglu_bwd_kernel<<<grid_for(rows * fvec, 256), 256, 0, STREAM>>>(CBF(dout), lddo, CBF(proj), ldp, BF(dproj), lddp, rows,
+                                                                  F, fvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_softmax_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols, float scale,
+                        b200pdm_stream_t stream) {
+  if (rows <= 0) return B200PDM_OK;
+  int threads = cols >= 1024 ? 256 : 128;
+  softmax_fwd_kernel<<<(unsigned)rows, threads, 0, STREAM>>>(s, lds, BF(p), ldp, cols, scale);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ldp, void* ds, int64_t ldds, int64_t rows,
+                        int cols, float scale, b200pdm_stream_t stream) {
+  if (rows <= 0) return B200PDM_OK;
+  int threads = cols >= 1024 ? 256 : 128;
+  softmax_bwd_kernel<<<(unsigned)rows, threads, 0, STREAM>>>(dp, lddp, CBF(p), ldp, BF(ds), ldds, cols, scale);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream) {
+  int col_blocks = (cols + 31) / 32;
+  int slices = (148 * 4 + col_blocks - 1) / col_blocks;
+  int64_t rps = (rows + slices - 1) / slices;
+  if (rps < 64) rps = 64;
+  slices = (int)((rows + rps - 1) / rps);
+  dim3 grid(col_blocks, slices), block(32, 8);
+  colsum_kernel<<<grid, block, 0, STREAM>>>(CBF(x), ldx, out, rows, cols, (int)rps);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_add(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows, int C,
+                b200pdm_stream_t stream) {
+  if (lda % 8 || ldb % 8 || ldo % 8) return B200PDM_ERR_UNSUPPORTED;
+  const int cvec = (C + 7) / 8;
+  add_kernel<<<grid_for(rows * cvec, 256), 256, 0, STREAM>>>(CBF(a), lda, CBF(b), ldb, BF(out), ldo, rows, C, cvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int C, b200pdm_stream_t stream) {
+  if (lds % 8 || ldd % 8) return B200PDM_ERR_UNSUPPORTED;
+  const int cvec = (C + 7) / 8;
+  copy2d_kernel<<<grid_for(rows * cvec, 256), 256, 0, STREAM>>>(CBF(src), lds, BF(dst), ldd, rows, C, cvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_silu_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream) {
+  silu_f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(x, BF(y), n);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_silu_bwd_f32(const float* dy, const float* x, float* dx, int64_t n, b200pdm_stream_t stream) {
+  silu_bwd_f32_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(dy, x, dx, n);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int batch, int h, int w, int C,
+                           b200pdm_stream_t stream) {
+  if (ldx % 8 || ldy % 8) return B200PDM_ERR_UNSUPPORTED;
+  const int cvec = (C + 7) / 8;
+  resample2x_kernel<0><<<grid_for((int64_t)batch * 4 * h * w * cvec, 256), 256, 0, STREAM>>>(CBF(x), ldx, BF(y), ldy,
+                                                                                             batch, h, w, C, cvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx, int batch, int h, int w, int C,
+                           b200pdm_stream_t stream) {
+  if (lddy % 8 || lddx % 8) return B200PDM_ERR_UNSUPPORTED;
+  const int cvec = (C + 7) / 8;
+  resample2x_kernel<1><<<grid_for((int64_t)batch * h * w * cvec, 256), 256, 0, STREAM>>>(CBF(dy), lddy, BF(dx), lddx,
+                                                                                         batch, h, w, C, cvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_zero_insert2x(const void* x, int64_t ldx, void* y, int64_t ldy, int batch, int h, int w, int C,
+                          b200pdm_stream_t stream) {
+  if (ldx % 8 || ldy % 8) return B200PDM_ERR_UNSUPPORTED;
+  const int cvec = (C + 7) / 8;
+  resample2x_kernel<2><<<grid_for((int64_t)batch * 4 * h * w * cvec, 256), 256, 0, STREAM>>>(CBF(x), ldx, BF(y), ldy,
+                                                                                             batch, h, w, C, cvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int batch, int C, int hw,
+                                  b200pdm_stream_t stream) {
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)batch * C * hw, 256), 256, 0, STREAM>>>(x, BF(y), ldy, batch, C, hw);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int batch, int C, int hw,
+                                  b200pdm_stream_t stream) {
+  nhwc_to_nchw_kernel<<<grid_for((int64_t)batch * C * hw, 256), 256, 0, STREAM>>>(CBF(x), ldx, y, batch, C, hw);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_timestep_embedding(const int64_t* t, void* out, int64_t ldo, int batch, int dim, b200pdm_stream_t stream) {
+  if (dim % 2) return B200PDM_ERR_ARG;
+  timestep_embedding_kernel<<<grid_for((int64_t)batch * dim / 2, 128), 128, 0, STREAM>>>(t, BF(out), ldo, batch, dim);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_diffusion_prep(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
+                           const float* sqrt_1macp, float* noisy, float* vtarget, int batch, int64_t n_per_sample,
+                           b200pdm_stream_t stream) {
+  diffusion_prep_kernel<<<grid_for((int64_t)batch * n_per_sample, 256), 256, 0, STREAM>>>(
+      x0, noise, t, sqrt_acp, sqrt_1macp, noisy, vtarget, batch, n_per_sample);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+
+}  // extern "C"

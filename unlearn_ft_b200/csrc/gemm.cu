@@ -1,0 +1,805 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution core for sm_100a.
+//
+//   warp 0 (one lane)  : TMA producer   - cp.async.bulk.tensor tiles of A and B into a swizzle-128B smem ring
+//   warp 1 (one lane)  : MMA issuer     - tcgen05.mma (M=128, N=block_n, K=16) into a double-buffered TMEM accumulator
+//   warps 2..5         : epilogue       - tcgen05.ld accumulator rows, alpha/bias/time-embedding/residual, store
+//
+// The A/B tiles are addressed by a small "operand program" evaluated by the producer thread, which is what turns the
+// same kernel into: linear fwd/dgrad/wgrad (K-major or MN-major 2D operands, batched), 3x3/1x1 convolution fprop
+// (NHWC activations fetched tap by tap with 4D TMA boxes; out-of-bounds = zero padding), convolution dgrad (tap
+// flip + weight matrix read MN-major) and convolution wgrad (both operands MN-major, K = output pixels).
+//
+// Reference call sites replaced: see include/b200pdm.h (linear/conv entries).
+#include "common.cuh"
+#include "../../include/b200pdm.h"
+
+#include <atomic>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+namespace b200 {
+
+std::atomic<uint64_t> g_launches{0};
+static char g_err[512] = "";
+void set_err(const char* fmt, const char* a = "") { snprintf(g_err, sizeof(g_err), fmt, a); }
+const char* get_err() { return g_err; }
+
+// ------------------------------------------------------------------------------------------------
+// Driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// rank-R bf16 tensor map, 128B swizzle, zero OOB fill. dims/strides innermost first; strides in ELEMENTS
+// (strides[0] is implicit 1 and ignored).
+static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                    const uint32_t* box, const uint32_t* estr) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_err("cuTensorMapEncodeTiled entry point not available");
+    return B200PDM_ERR_DRIVER;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = estr ? estr[i] : 1;
+  }
+  for (int i = 1; i < rank; ++i) {
+    gstr[i - 1] = strides_el[i] * 2;
+    if (gstr[i - 1] % 16 != 0) {
+      set_err("tensor map stride not a multiple of 16 bytes");
+      return B200PDM_ERR_ARG;
+    }
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) {
+    set_err("tensor map base not 16-byte aligned");
+    return B200PDM_ERR_ARG;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu %llu box %u %u %u %u)",
+             (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
+             (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), bx[0], bx[1],
+             rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+    return B200PDM_ERR_DRIVER;
+  }
+  return B200PDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-side parameters
+// ------------------------------------------------------------------------------------------------
+struct OpDev {
+  int mode;
+  int Z1;
+  int cblks;   // 64-wide channel blocks per tap (conv modes)
+  int taps;
+  int Wo, HoWo;  // output grid (pixel decomposition)
+  int stride;
+  int flip;
+};
+
+struct GemmDev {
+  OpDev a, b;
+  int M;             // valid output rows (per batch)
+  int n_per_group;   // valid output cols per N-group
+  int n_groups;      // 1, or taps for conv wgrad
+  int64_t out_group_stride;
+  int tiles_m, tiles_n_per_group, Z, splits;
+  int kblocks, kb_per_split;
+  int block_n, stages;
+  uint32_t idesc;
+  // epilogue
+  void* out;
+  int out_fp32;
+  int64_t ldo, obs1, obs2;
+  const float* bias;
+  const float* rowbias;
+  int64_t ld_rowbias;
+  int rows_per_group;
+  const bf16* residual;
+  int64_t ldr, rbs1, rbs2;
+  float alpha;
+  int accumulate;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kAtomBytes = 64 * 64 * 2;              // one [64 k][64 mn] MN-major atom = 8 KiB
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int m_tile,
+                                       int kb, int z) {
+  switch (op.mode) {
+    case B200PDM_OP_K2D:
+      tma_load_4d(dst, map, bar, kb * kBlockK, m_tile * kBlockM, z % op.Z1, z / op.Z1);
+      break;
+    case B200PDM_OP_MN2D:
+      tma_load_4d(dst, map, bar, m_tile * kBlockM, kb * kBlockK, z % op.Z1, z / op.Z1);
+      tma_load_4d(dst + kAtomBytes, map, bar, m_tile * kBlockM + 64, kb * kBlockK, z % op.Z1, z / op.Z1);
+      break;
+    case B200PDM_OP_CONV_ACT: {
+      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      int kh = 1, kw = 1;
+      if (op.taps == 9) {
+        kh = tap / 3;
+        kw = tap - kh * 3;
+        if (op.flip) {
+          kh = 2 - kh;
+          kw = 2 - kw;
+        }
+      }
+      int pix0 = m_tile * kBlockM;
+      int n0 = pix0 / op.HoWo;
+      int rem = pix0 - n0 * op.HoWo;
+      int h0 = rem / op.Wo;
+      int w0 = rem - h0 * op.Wo;
+      tma_load_4d(dst, map, bar, cb * kBlockK, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, n0);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+__device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int grp,
+                                       int nt, int block_n, int kb, int z) {
+  const int n0 = nt * block_n;
+  switch (op.mode) {
+    case B200PDM_OP_K2D:
+      tma_load_4d(dst, map, bar, kb * kBlockK, n0, z % op.Z1, z / op.Z1);
+      break;
+    case B200PDM_OP_MN2D:
+      for (int j = 0; j < block_n / 64; ++j)
+        tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, kb * kBlockK, z % op.Z1, z / op.Z1);
+      break;
+    case B200PDM_OP_CONV_W: {
+      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      tma_load_3d(dst, map, bar, cb * kBlockK, tap, n0);
+      break;
+    }
+    case B200PDM_OP_CONV_WT: {
+      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      for (int j = 0; j < block_n / 64; ++j) tma_load_3d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK);
+      break;
+    }
+    case B200PDM_OP_CONV_ACT_MN: {
+      int kh = 1, kw = 1;
+      if (op.taps == 9) {
+        kh = grp / 3;
+        kw = grp - kh * 3;
+      }
+      int pix0 = kb * kBlockK;
+      int b0 = pix0 / op.HoWo;
+      int rem = pix0 - b0 * op.HoWo;
+      int h0 = rem / op.Wo;
+      int w0 = rem - h0 * op.Wo;
+      for (int j = 0; j < block_n / 64; ++j)
+        tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, b0);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_b_bytes = p.block_n * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * kStageABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.stages * stage_b_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = p.tiles_n_per_group * p.n_groups;
+  const int tiles_per_split = p.tiles_m * tiles_n * p.Z;
+  const int total_tiles = tiles_per_split * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      const uint32_t tx_bytes = kStageABytes + stage_b_bytes;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int split = t / tiles_per_split;
+        int r = t - split * tiles_per_split;
+        int z = r / (p.tiles_m * tiles_n);
+        r -= z * (p.tiles_m * tiles_n);
+        int m_tile = r / tiles_n;
+        int n_tile = r - m_tile * tiles_n;
+        int grp = n_tile / p.tiles_n_per_group;
+        int nt = n_tile - grp * p.tiles_n_per_group;
+        int kb0 = split * p.kb_per_split;
+        int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          load_a(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
+          load_b(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int split = t / tiles_per_split;
+        int kb0 = split * p.kb_per_split;
+        int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * kAccStride;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * kStageABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * stage_b_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            uint64_t adesc, bdesc;
+            if (A_MN)
+              adesc = make_smem_desc_sw128(a_addr + k * 2048, kAtomBytes, 1024);
+            else
+              adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            if (B_MN)
+              bdesc = make_smem_desc_sw128(b_addr + k * 2048, kAtomBytes, 1024);
+            else
+              bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int split = t / tiles_per_split;
+      int r = t - split * tiles_per_split;
+      int z = r / (p.tiles_m * tiles_n);
+      r -= z * (p.tiles_m * tiles_n);
+      int m_tile = r / tiles_n;
+      int n_tile = r - m_tile * tiles_n;
+      int grp = n_tile / p.tiles_n_per_group;
+      int nt = n_tile - grp * p.tiles_n_per_group;
+      const int z1 = z % p.a.Z1, z2 = z / p.a.Z1;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const int row = m_tile * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int col_base = nt * p.block_n;  // within group
+      const int n_valid = p.n_per_group - col_base;
+      const int64_t out_off =
+          z1 * p.obs1 + z2 * p.obs2 + static_cast<int64_t>(row) * p.ldo + grp * p.out_group_stride + col_base;
+      const bf16* res_row =
+          p.residual ? p.residual + z1 * p.rbs1 + z2 * p.rbs2 + static_cast<int64_t>(row) * p.ldr + col_base : nullptr;
+      const float* rb_row =
+          p.rowbias ? p.rowbias + static_cast<int64_t>(row / p.rows_per_group) * p.ld_rowbias + col_base : nullptr;
+      const float* bias = p.bias ? p.bias + col_base : nullptr;
+      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        if (p.block_n - c0 >= 32) {
+          tmem_ld_32x32(taddr + c0, v);
+        } else {  // block_n % 32 == 16 tail
+          uint32_t h[16];
+          tmem_ld_32x16(taddr + c0, h);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = h[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0;
+        }
+        tmem_ld_wait();
+        const int nv = min(32, n_valid - c0);  // valid columns in this chunk
+        if (row_ok && nv > 0) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) f[j] += __ldg(bias + c0 + j);
+          }
+          if (rb_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) f[j] += __ldg(rb_row + c0 + j);
+          }
+          if (res_row) {
+            if (nv == 32 && ((reinterpret_cast<uintptr_t>(res_row + c0) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                bf16x8 rv = *reinterpret_cast<const bf16x8*>(res_row + c0 + g * 8);
+                float rf[8];
+                unpack8(rv, rf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[g * 8 + j] += rf[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
+            }
+          }
+          if (p.out_fp32) {
+            float* o = reinterpret_cast<float*>(p.out) + out_off + c0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) atomicAdd(o + j, f[j]);
+            } else if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) o[j] = f[j];
+            }
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + c0;
+            if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float t8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t8[j] = f[g * 8 + j];
+                *reinterpret_cast<bf16x8*>(o + g * 8) = pack8(t8);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) o[j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// Pixel box (bw, bh, bn) covering `pixels` consecutive output pixels (full rows), or failure.
+static bool pixel_box(int pixels, int Ho, int Wo, int* bw, int* bh, int* bn) {
+  if (Wo >= pixels) {
+    if (Wo % pixels) return false;
+    *bw = pixels, *bh = 1, *bn = 1;
+    return true;
+  }
+  if (pixels % Wo) return false;
+  int rows = pixels / Wo;
+  if (Ho >= rows) {
+    if (Ho % rows) return false;
+    *bw = Wo, *bh = rows, *bn = 1;
+    return true;
+  }
+  if (rows % Ho) return false;
+  *bw = Wo, *bh = Ho, *bn = rows / Ho;
+  return true;
+}
+
+static int pick_block_n(int64_t n, bool mn_major) {
+  const int g = mn_major ? 64 : 16;
+  int64_t n_pad = (n + g - 1) / g * g;
+  if (n_pad <= 256) return static_cast<int>(n_pad);
+  int best = 256;
+  int64_t best_cost = INT64_MAX;
+  for (int bn = 256; bn >= 128; bn -= g) {
+    int64_t tiles = (n + bn - 1) / bn;
+    int64_t cost = tiles * bn;  // padded MMA columns
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, CUtensorMap* map, OpDev* dev,
+                             int64_t mn_extent, int64_t k_extent, int Z1, int Z2) {
+  memset(dev, 0, sizeof(*dev));
+  dev->mode = op.mode;
+  dev->Z1 = Z1 > 0 ? Z1 : 1;
+  dev->taps = op.taps > 0 ? op.taps : 1;
+  dev->stride = op.stride > 0 ? op.stride : 1;
+  dev->flip = op.flip;
+  const int rows = is_a ? kBlockM : block_n;
+  uint64_t dims[5], str[5];
+  uint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+  switch (op.mode) {
+    case B200PDM_OP_K2D: {
+      dims[0] = k_extent, dims[1] = mn_extent, dims[2] = Z1, dims[3] = Z2;
+      str[0] = 1, str[1] = op.ld, str[2] = (Z1 > 1 ? op.bs1 : op.ld), str[3] = (Z2 > 1 ? op.bs2 : op.ld);
+      box[0] = 64, box[1] = rows, box[2] = 1, box[3] = 1;
+      return make_map(map, op.ptr, 4, dims, str, box, es);
+    }
+    case B200PDM_OP_MN2D: {
+      dims[0] = mn_extent, dims[1] = k_extent, dims[2] = Z1, dims[3] = Z2;
+      str[0] = 1, str[1] = op.ld, str[2] = (Z1 > 1 ? op.bs1 : op.ld), str[3] = (Z2 > 1 ? op.bs2 : op.ld);
+      box[0] = 64, box[1] = 64, box[2] = 1, box[3] = 1;
+      return make_map(map, op.ptr, 4, dims, str, box, es);
+    }
+    case B200PDM_OP_CONV_ACT:
+    case B200PDM_OP_CONV_ACT_MN: {
+      const int pixels = (op.mode == B200PDM_OP_CONV_ACT) ? kBlockM : kBlockK;
+      int bw, bh, bn;
+      if (!pixel_box(pixels, op.h_out, op.w_out, &bw, &bh, &bn)) {
+        set_err("conv: output grid does not tile into full-row pixel boxes");
+        return B200PDM_ERR_UNSUPPORTED;
+      }
+      dev->Wo = op.w_out;
+      dev->HoWo = op.h_out * op.w_out;
+      dev->cblks = (op.channels + 63) / 64;
+      dims[0] = op.channels, dims[1] = op.w_in, dims[2] = op.h_in, dims[3] = op.batch;
+      str[0] = 1, str[1] = op.ld, str[2] = (uint64_t)op.w_in * op.ld, str[3] = (uint64_t)op.h_in * op.w_in * op.ld;
+      box[0] = 64, box[1] = bw * dev->stride, box[2] = bh * dev->stride, box[3] = bn;
+      es[1] = dev->stride, es[2] = dev->stride;
+      if (dev->taps == 1 && dev->stride == 1) {
+        // 1x1: the (kw-1, kh-1) shift is zero because load_a/load_b force the centre tap
+      }
+      return make_map(map, op.ptr, 4, dims, str, box, es);
+    }
+    case B200PDM_OP_CONV_W: {
+      dev->cblks = (op.channels + 63) / 64;
+      dims[0] = op.channels, dims[1] = dev->taps, dims[2] = op.out_channels;
+      str[0] = 1, str[1] = op.ld, str[2] = (uint64_t)dev->taps * op.ld;
+      box[0] = 64, box[1] = 1, box[2] = rows;
+      return make_map(map, op.ptr, 3, dims, str, box, es);
+    }
+    case B200PDM_OP_CONV_WT: {
+      dev->cblks = (op.out_channels + 63) / 64;  // K runs over O
+      dims[0] = op.channels, dims[1] = dev->taps, dims[2] = op.out_channels;
+      str[0] = 1, str[1] = op.ld, str[2] = (uint64_t)dev->taps * op.ld;
+      box[0] = 64, box[1] = 1, box[2] = 64;
+      return make_map(map, op.ptr, 3, dims, str, box, es);
+    }
+  }
+  set_err("unknown operand mode");
+  return B200PDM_ERR_ARG;
+}
+
+static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
+  if (!d || !d->a.ptr || !d->b.ptr || !d->out) {
+    set_err("gemm: null pointer");
+    return B200PDM_ERR_ARG;
+  }
+  const bool a_mn = d->a.mode == B200PDM_OP_MN2D;
+  const bool b_mn = d->b.mode == B200PDM_OP_MN2D || d->b.mode == B200PDM_OP_CONV_WT ||
+                    d->b.mode == B200PDM_OP_CONV_ACT_MN;
+  const int Z1 = d->Z1 > 0 ? d->Z1 : 1, Z2 = d->Z2 > 0 ? d->Z2 : 1;
+
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  // N grouping (conv wgrad: one group per tap)
+  p.n_groups = 1;
+  p.n_per_group = static_cast<int>(d->N);
+  p.out_group_stride = 0;
+  if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {
+    p.n_groups = d->b.taps > 0 ? d->b.taps : 1;
+    p.n_per_group = d->b.channels;
+    p.out_group_stride = d->ldo / p.n_groups;  // dW row = [taps][I_ld]
+  }
+  int block_n = d->block_n > 0 ? d->block_n : pick_block_n(p.n_per_group, b_mn);
+  if (block_n % 16 || block_n > 256 || block_n < 16 || (b_mn && block_n % 64)) {
+    set_err("gemm: bad block_n");
+    return B200PDM_ERR_ARG;
+  }
+  p.block_n = block_n;
+  p.tiles_n_per_group = cdiv(p.n_per_group, block_n);
+  p.M = static_cast<int>(d->M);
+  p.tiles_m = cdiv(d->M, kBlockM);
+  p.Z = Z1 * Z2;
+
+  // K blocks
+  int kblocks;
+  if (d->a.mode == B200PDM_OP_CONV_ACT) {
+    int taps = d->a.taps > 0 ? d->a.taps : 1;
+    kblocks = taps * cdiv(d->a.channels, 64);
+  } else if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {
+    kblocks = cdiv((int64_t)d->b.batch * d->b.h_out * d->b.w_out, 64);
+  } else {
+    kblocks = cdiv(d->K, 64);
+  }
+  if (kblocks <= 0) {
+    set_err("gemm: empty K");
+    return B200PDM_ERR_ARG;
+  }
+  p.kblocks = kblocks;
+  int splits = d->splits > 1 ? d->splits : 1;
+  if (splits > kblocks) splits = kblocks;
+  p.kb_per_split = cdiv(kblocks, splits);
+  splits = cdiv(kblocks, p.kb_per_split);
+  p.splits = splits;
+  if (splits > 1 && !(d->out_fp32 && d->accumulate)) {
+    set_err("gemm: split-K needs fp32 accumulate output");
+    return B200PDM_ERR_ARG;
+  }
+
+  CUtensorMap map_a, map_b;
+  int rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2);
+  if (rc) return rc;
+  rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->N, d->K, Z1, Z2);
+  if (rc) return rc;
+
+  const int stage_bytes = kStageABytes + block_n * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.idesc = make_idesc_bf16(block_n, a_mn ? 1 : 0, b_mn ? 1 : 0);
+
+  p.out = d->out;
+  p.out_fp32 = d->out_fp32;
+  p.ldo = d->ldo;
+  p.obs1 = d->obs1;
+  p.obs2 = d->obs2;
+  p.bias = d->bias;
+  p.rowbias = d->rowbias;
+  p.ld_rowbias = d->ld_rowbias;
+  p.rows_per_group = d->rows_per_group > 0 ? d->rows_per_group : 1;
+  p.residual = reinterpret_cast<const bf16*>(d->residual);
+  p.ldr = d->ldr;
+  p.rbs1 = d->rbs1;
+  p.rbs2 = d->rbs2;
+  p.alpha = d->alpha;
+  p.accumulate = d->accumulate;
+
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+  const long total_tiles = (long)p.tiles_m * p.tiles_n_per_group * p.n_groups * p.Z * p.splits;
+  int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
+
+  auto launch = [&](auto kern) -> int {
+    static thread_local const void* configured[4] = {nullptr, nullptr, nullptr, nullptr};
+    (void)configured;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_err("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return B200PDM_ERR_CUDA;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_err("gemm launch: %s", cudaGetErrorString(e));
+      return B200PDM_ERR_CUDA;
+    }
+    g_launches++;
+    return B200PDM_OK;
+  };
+  if (!a_mn && !b_mn) return launch(gemm_kernel<0, 0>);
+  if (!a_mn && b_mn) return launch(gemm_kernel<0, 1>);
+  if (a_mn && !b_mn) return launch(gemm_kernel<1, 0>);
+  return launch(gemm_kernel<1, 1>);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200pdm_version(void) { return 100; }
+const char* b200pdm_last_error(void) { return get_err(); }
+uint64_t b200pdm_launch_count(void) { return g_launches.load(); }
+
+int b200pdm_gemm(const b200pdm_gemm_desc* desc, b200pdm_stream_t stream) {
+  return launch_gemm(desc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200pdm_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const void* residual,
+                       int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M, int64_t N, int64_t K,
+                       b200pdm_stream_t stream) {
+  b200pdm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_K2D, d.a.ptr = x, d.a.ld = ldx;
+  d.b.mode = B200PDM_OP_K2D, d.b.ptr = w, d.b.ld = ldw;
+  d.M = M, d.N = N, d.K = K, d.Z1 = 1, d.Z2 = 1;
+  d.out = out, d.out_fp32 = out_fp32, d.ldo = ldo;
+  d.bias = bias, d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
+  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual, int64_t ldr,
+                         void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, b200pdm_stream_t stream) {
+  // dx[M,K] = dy[M,N] . w[N,K]: reduction over N; B(n'=k, k'=n) = w[n][k] is MN-major.
+  b200pdm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_K2D, d.a.ptr = dy, d.a.ld = lddy;
+  d.b.mode = B200PDM_OP_MN2D, d.b.ptr = w, d.b.ld = ldw;
+  d.M = M, d.N = K, d.K = N, d.Z1 = 1, d.Z2 = 1;
+  d.out = dx, d.out_fp32 = 0, d.ldo = lddx;
+  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
+  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int pick_splits(long tiles, int kblocks) {
+  // fill the machine about twice over, keep >= 4 k-blocks per split
+  int sms = num_sms();
+  long want = (2L * sms + tiles - 1) / tiles;
+  long max_by_k = kblocks / 4 > 0 ? kblocks / 4 : 1;
+  long s = want < max_by_k ? want : max_by_k;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+
+int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw, int64_t M,
+                         int64_t N, int64_t K, b200pdm_stream_t stream) {
+  // dw[N,K] += dy[M,N]^T . x[M,K]: reduction over M; A(m'=n, k'=m) = dy[m][n] MN-major, B(n'=k, k'=m) = x[m][k] MN-major.
+  b200pdm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_MN2D, d.a.ptr = dy, d.a.ld = lddy;
+  d.b.mode = B200PDM_OP_MN2D, d.b.ptr = x, d.b.ld = ldx;
+  d.M = N, d.N = K, d.K = M, d.Z1 = 1, d.Z2 = 1;
+  d.out = dw, d.out_fp32 = 1, d.ldo = lddw, d.alpha = 1.f, d.accumulate = 1;
+  int bn = pick_block_n(K, true);
+  long tiles = (long)cdiv(N, kBlockM) * cdiv(K, bn);
+  d.splits = pick_splits(tiles, cdiv(M, 64));
+  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200pdm_conv_fwd(const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias, const float* rowbias,
+                     int64_t ld_rowbias, const void* residual, int64_t ldr, void* out, int64_t ldo, int batch, int h_in,
+                     int w_in, int c_in, int c_out, int ksize, int stride, b200pdm_stream_t stream) {
+  if ((ksize != 3 && ksize != 1) || (stride != 1 && stride != 2)) {
+    set_err("conv_fwd: unsupported ksize/stride");
+    return B200PDM_ERR_UNSUPPORTED;
+  }
+  const int h_out = h_in / stride, w_out = w_in / stride;
+  b200pdm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = x, d.a.ld = ldx;
+  d.a.batch = batch, d.a.h_in = h_in, d.a.w_in = w_in, d.a.channels = c_in;
+  d.a.h_out = h_out, d.a.w_out = w_out, d.a.stride = stride, d.a.taps = ksize * ksize;
+  d.b.mode = B200PDM_OP_CONV_W, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
+  d.b.taps = ksize * ksize;
+  d.M = (int64_t)batch * h_out * w_out, d.N = c_out, d.K = (int64_t)ksize * ksize * c_in, d.Z1 = 1, d.Z2 = 1;
+  d.out = out, d.out_fp32 = 0, d.ldo = ldo;
+  d.bias = bias, d.rowbias = rowbias, d.ld_rowbias = ld_rowbias, d.rows_per_group = h_out * w_out;
+  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
+  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200pdm_conv_dgrad(const void* dy, int64_t lddy, const void* w, int64_t w_ild, const void* residual, int64_t ldr,
+                       void* dx, int64_t lddx, int batch, int h, int w_sp, int c_in, int c_out, int ksize,
+                       b200pdm_stream_t stream) {
+  if (ksize != 3 && ksize != 1) {
+    set_err("conv_dgrad: unsupported ksize");
+    return B200PDM_ERR_UNSUPPORTED;
+  }
+  b200pdm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = dy, d.a.ld = lddy;
+  d.a.batch = batch, d.a.h_in = h, d.a.w_in = w_sp, d.a.channels = c_out;
+  d.a.h_out = h, d.a.w_out = w_sp, d.a.stride = 1, d.a.taps = ksize * ksize, d.a.flip = 1;
+  d.b.mode = B200PDM_OP_CONV_WT, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
+  d.b.taps = ksize * ksize;
+  d.M = (int64_t)batch * h * w_sp, d.N = c_in, d.K = (int64_t)ksize * ksize * c_out, d.Z1 = 1, d.Z2 = 1;
+  d.out = dx, d.out_fp32 = 0, d.ldo = lddx;
+  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
+  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t w_ild, int batch,
+                       int h_in, int w_in, int c_in, int c_out, int ksize, int stride, b200pdm_stream_t stream) {
+  if ((ksize != 3 && ksize != 1) || (stride != 1 && stride != 2)) {
+    set_err("conv_wgrad: unsupported ksize/stride");
+    return B200PDM_ERR_UNSUPPORTED;
+  }
+  const int h_out = h_in / stride, w_out = w_in / stride;
+  const int taps = ksize * ksize;
+  b200pdm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  const int64_t pixels = (int64_t)batch * h_out * w_out;
+  d.a.mode = B200PDM_OP_MN2D, d.a.ptr = dy, d.a.ld = lddy;  // A(m'=co, k'=pixel)
+  d.b.mode = B200PDM_OP_CONV_ACT_MN, d.b.ptr = x, d.b.ld = ldx;
+  d.b.batch = batch, d.b.h_in = h_in, d.b.w_in = w_in, d.b.channels = c_in;
+  d.b.h_out = h_out, d.b.w_out = w_out, d.b.stride = stride, d.b.taps = taps;
+  d.M = c_out, d.N = (int64_t)taps * c_in, d.K = pixels, d.Z1 = 1, d.Z2 = 1;
+  d.out = dw, d.out_fp32 = 1, d.ldo = (int64_t)taps * w_ild, d.alpha = 1.f, d.accumulate = 1;
+  int bn = pick_block_n(c_in, true);
+  long tiles = (long)cdiv(c_out, kBlockM) * cdiv(c_in, bn) * taps;
+  d.splits = pick_splits(tiles, cdiv(pixels, 64));
+  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+"""Tensor-level wrappers over the C ABI (``include/b200pdm.h``).
+
+Convention: an activation matrix is a 2-D bf16 ``torch.Tensor`` of shape ``[rows, C]`` with strides ``(ld, 1)``,
+``ld % 8 == 0`` and a 16-byte aligned base -- i.e. a channels-last feature map ``[B, H, W, C]`` flattened over pixels.
+``alloc2d`` creates such tensors; column slices of them (``t[:, a:b]`` with ``a % 8 == 0``) stay valid.
+PyTorch is used for device memory and the current CUDA stream only; every numerical operation is a call into
+``libb200pdm.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, Operand, check
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def round8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def alloc2d(rows: int, cols: int, device=None, dtype=BF16, zero: bool = False) -> torch.Tensor:
+    ld = round8(cols)
+    buf = (torch.zeros if zero else torch.empty)(rows, ld, device=device or "cuda", dtype=dtype)
+    return buf[:, :cols] if ld != cols else buf
+
+
+def _chk2d(t: torch.Tensor, name: str, dtype=BF16):
+    if t.dim() != 2 or t.dtype != dtype or t.stride(1) != 1 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a 2-D {dtype} CUDA tensor with unit inner stride, got {tuple(t.shape)} "
+                         f"{t.dtype} strides {t.stride()}")
+    if dtype == BF16 and (t.stride(0) % 8 or t.data_ptr() % 16):
+        raise ValueError(f"{name}: row pitch must be a multiple of 8 elements and the base 16-byte aligned")
+
+
+# ------------------------------------------------------------------------------------------------ GEMM-class
+def linear_fwd(x, w, bias=None, residual=None, out=None, out_fp32=False):
+    """out[M,N] = x[M,K] @ w[N,K]^T + bias + residual  (F.linear; reference blocks.py:49,244,251-252,283)."""
+    _chk2d(x, "x"), _chk2d(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"linear_fwd: K mismatch {x.shape} vs {w.shape}")
+    if out is None:
+        out = alloc2d(M, N, x.device, F32 if out_fp32 else BF16)
+    if residual is not None:
+        _chk2d(residual, "residual")
+    check(_lib.lib().b200pdm_linear_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                        _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                        out.data_ptr(), out.stride(0), int(out.dtype == F32), M, N, K, _stream()),
+          "linear_fwd")
+    return out
+
+
+def linear_dgrad(dy, w, residual=None, out=None):
+    """dx[M,K] = dy[M,N] @ w[N,K] (+ residual)."""
+    _chk2d(dy, "dy"), _chk2d(w, "w")
+    M, N = dy.shape
+    K = w.shape[1]
+    if out is None:
+        out = alloc2d(M, K, dy.device)
+    check(_lib.lib().b200pdm_linear_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), _ptr(residual),
+                                          residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                                          out.stride(0), M, N, K, _stream()), "linear_dgrad")
+    return out
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N,K] (fp32) += dy[M,N]^T @ x[M,K]."""
+    _chk2d(dy, "dy"), _chk2d(x, "x"), _chk2d(dw, "dw", F32)
+    M, N = dy.shape
+    K = x.shape[1]
+    check(_lib.lib().b200pdm_linear_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
+                                          dw.stride(0), M, N, K, _stream()), "linear_wgrad")
+    return dw
+
+
+def conv_fwd(x, w, B, H, W, c_out, ksize=3, stride=1, bias=None, rowbias=None, residual=None, out=None):
+    """NHWC implicit-GEMM convolution. x: [B*H*W, Cin]; w: bf16 [Cout, taps, Cin] view with strides (taps*ild, ild, 1)."""
+    _chk2d(x, "x")
+    c_in = x.shape[1]
+    Ho, Wo = H // stride, W // stride
+    if out is None:
+        out = alloc2d(B * Ho * Wo, c_out, x.device)
+    ild = w.stride(1) if w.dim() == 3 else w.stride(0)
+    check(_lib.lib().b200pdm_conv_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), ild, _ptr(bias), _ptr(rowbias),
+                                      rowbias.stride(0) if rowbias is not None else 0, _ptr(residual),
+                                      residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                                      out.stride(0), B, H, W, c_in, c_out, ksize, stride, _stream()), "conv_fwd")
+    return out
+
+
+def conv_dgrad(dy, w, B, H, W, c_in, ksize=3, residual=None, out=None):
+    """dx[B*H*W, Cin] for a stride-1 convolution (dy at the same resolution)."""
+    _chk2d(dy, "dy")
+    c_out = dy.shape[1]
+    if out is None:
+        out = alloc2d(B * H * W, c_in, dy.device)
+    ild = w.stride(1) if w.dim() == 3 else w.stride(0)
+    check(_lib.lib().b200pdm_conv_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), ild, _ptr(residual),
+                                        residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                                        out.stride(0), B, H, W, c_in, c_out, ksize, _stream()), "conv_dgrad")
+    return out
+
+
+def conv_wgrad(dy, x, dw, B, H, W, ksize=3, stride=1):
+    """dw (fp32 [Cout, taps, Cin] view, strides (taps*ild, ild, 1)) += conv weight gradient."""
+    _chk2d(dy, "dy"), _chk2d(x, "x")
+    c_out, c_in = dy.shape[1], x.shape[1]
+    ild = dw.stride(1) if dw.dim() == 3 else dw.stride(0)
+    check(_lib.lib().b200pdm_conv_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(), ild, B,
+                                        H, W, c_in, c_out, ksize, stride, _stream()), "conv_wgrad")
+    return dw
+
+
+def gemm(desc: GemmDesc):
+    check(_lib.lib().b200pdm_gemm(C.byref(desc), _stream()), "gemm")
+
+
+def bmm(a, b, out, *, a_mn=False, b_mn=False, M, N, K, Z1=1, Z2=1, a_ld, a_bs=(0, 0), b_ld, b_bs=(0, 0), o_ld,
+        o_bs=(0, 0), alpha=1.0):
+    """Batched GEMM over raw strided bf16 operands (attention). Pointers are taken from the tensors' data_ptr()."""
+    d = GemmDesc()
+    d.a = Operand(mode=_lib.OP_MN2D if a_mn else _lib.OP_K2D, ptr=a.data_ptr(), ld=a_ld, bs1=a_bs[0], bs2=a_bs[1])
+    d.b = Operand(mode=_lib.OP_MN2D if b_mn else _lib.OP_K2D, ptr=b.data_ptr(), ld=b_ld, bs1=b_bs[0], bs2=b_bs[1])
+    d.M, d.N, d.K, d.Z1, d.Z2 = M, N, K, Z1, Z2
+    d.out, d.out_fp32, d.ldo, d.obs1, d.obs2 = out.data_ptr(), int(out.dtype == F32), o_ld, o_bs[0], o_bs[1]
+    d.alpha = alpha
+    gemm(d)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ norms
+def groupnorm_fwd(x, gamma, beta, B, hw, groups, eps, silu, out=None):
+    _chk2d(x, "x")
+    Cn = x.shape[1]
+    if out is None:
+        out = alloc2d(B * hw, Cn, x.device)
+    stats = torch.empty(2 * B * groups, device=x.device, dtype=F32)
+    check(_lib.lib().b200pdm_groupnorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                           out.stride(0), stats.data_ptr(), B, hw, Cn, groups, eps, int(silu),
+                                           _stream()), "groupnorm_fwd")
+    return out, stats
+
+
+def groupnorm_bwd(dy, x, gamma, beta, stats, dgamma, dbeta, B, hw, groups, silu, out=None):
+    _chk2d(dy, "dy"), _chk2d(x, "x")
+    Cn = x.shape[1]
+    if out is None:
+        out = alloc2d(B * hw, Cn, x.device)
+    ws = torch.empty(2 * B * groups, device=x.device, dtype=F32)
+    check(_lib.lib().b200pdm_groupnorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
+                                           beta.data_ptr(), stats.data_ptr(), out.data_ptr(), out.stride(0),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), B, hw, Cn, groups,
+                                           int(silu), _stream()), "groupnorm_bwd")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5, save=True, out=None):
+    _chk2d(x, "x")
+    rows, Cn = x.shape
+    if out is None:
+        out = alloc2d(rows, Cn, x.device)
+    mean = torch.empty(rows, device=x.device, dtype=F32) if save else None
+    rstd = torch.empty(rows, device=x.device, dtype=F32) if save else None
+    check(_lib.lib().b200pdm_layernorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                           out.stride(0), _ptr(mean), _ptr(rstd), rows, Cn, eps, _stream()),
+          "layernorm_fwd")
+    return out, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None):
+    _chk2d(dy, "dy"), _chk2d(x, "x")
+    rows, Cn = x.shape
+    if out is None:
+        out = alloc2d(rows, Cn, x.device)
+    check(_lib.lib().b200pdm_layernorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
+                                           mean.data_ptr(), rstd.data_ptr(), out.data_ptr(), out.stride(0),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), rows, Cn, _stream()), "layernorm_bwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def geglu_fwd(proj, out=None):
+    _chk2d(proj, "proj")
+    rows, F2 = proj.shape
+    Fh = F2 // 2
+    if out is None:
+        out = alloc2d(rows, Fh, proj.device)
+    check(_lib.lib().b200pdm_geglu_fwd(proj.data_ptr(), proj.stride(0), out.data_ptr(), out.stride(0), rows, Fh,
+                                       _stream()), "geglu_fwd")
+    return out
+
+
+def geglu_bwd(dout, proj, out=None):
+    rows, F2 = proj.shape
+    if out is None:
+        out = alloc2d(rows, F2, proj.device)
+    check(_lib.lib().b200pdm_geglu_bwd(dout.data_ptr(), dout.stride(0), proj.data_ptr(), proj.stride(0), out.data_ptr(),
+                                       out.stride(0), rows, F2 // 2, _stream()), "geglu_bwd")
+    return out
+
+
+def softmax_fwd(s, p, rows, cols, scale):
+    check(_lib.lib().b200pdm_softmax_fwd(s.data_ptr(), s.stride(-2), p.data_ptr(), p.stride(-2), rows, cols, scale,
+                                         _stream()), "softmax_fwd")
+    return p
+
+
+def softmax_bwd(dp, p, ds, rows, cols, scale):
+    check(_lib.lib().b200pdm_softmax_bwd(dp.data_ptr(), dp.stride(-2), p.data_ptr(), p.stride(-2), ds.data_ptr(),
+                                         ds.stride(-2), rows, cols, scale, _stream()), "softmax_bwd")
+    return ds
+
+
+def colsum(x, out):
+    """out[n] (fp32) += sum_m x[m, n]."""
+    _chk2d(x, "x")
+    check(_lib.lib().b200pdm_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], _stream()),
+          "colsum")
+    return out
+
+
+def add(a, b, out=None):
+    _chk2d(a, "a"), _chk2d(b, "b")
+    if out is None:
+        out = alloc2d(a.shape[0], a.shape[1], a.device)
+    check(_lib.lib().b200pdm_add(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                                 a.shape[0], a.shape[1], _stream()), "add")
+    return out
+
+
+def copy2d(src, dst):
+    _chk2d(src, "src"), _chk2d(dst, "dst")
+    check(_lib.lib().b200pdm_copy2d(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), src.shape[0],
+                                    src.shape[1], _stream()), "copy2d")
+    return dst
+
+
+def silu_f32_to_bf16(x):
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(_lib.lib().b200pdm_silu_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu")
+    return y
+
+
+def silu_bwd_f32(dy, x):
+    dx = torch.empty_like(x)
+    check(_lib.lib().b200pdm_silu_bwd_f32(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "silu_bwd")
+    return dx
+
+
+def upsample2x_fwd(x, B, H, W):
+    out = alloc2d(B * 4 * H * W, x.shape[1], x.device)
+    check(_lib.lib().b200pdm_upsample2x_fwd(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), B, H, W,
+                                            x.shape[1], _stream()), "upsample2x_fwd")
+    return out
+
+
+def upsample2x_bwd(dy, B, H, W):
+    """(H, W) is the LOW resolution."""
+    out = alloc2d(B * H * W, dy.shape[1], dy.device)
+    check(_lib.lib().b200pdm_upsample2x_bwd(dy.data_ptr(), dy.stride(0), out.data_ptr(), out.stride(0), B, H, W,
+                                            dy.shape[1], _stream()), "upsample2x_bwd")
+    return out
+
+
+def zero_insert2x(x, B, H, W):
+    out = alloc2d(B * 4 * H * W, x.shape[1], x.device)
+    check(_lib.lib().b200pdm_zero_insert2x(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), B, H, W,
+                                           x.shape[1], _stream()), "zero_insert2x")
+    return out
+
+
+def nchw_f32_to_nhwc_bf16(x):
+    B, Cn, H, W = x.shape
+    x = x.contiguous().float()
+    out = alloc2d(B * H * W, Cn, x.device)
+    check(_lib.lib().b200pdm_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), out.stride(0), B, Cn, H * W, _stream()),
+          "nchw_to_nhwc")
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x, B, H, W):
+    Cn = x.shape[1]
+    out = torch.empty(B, Cn, H, W, device=x.device, dtype=F32)
+    check(_lib.lib().b200pdm_nhwc_bf16_to_nchw_f32(x.data_ptr(), x.stride(0), out.data_ptr(), B, Cn, H * W, _stream()),
+          "nhwc_to_nchw")
+    return out
+
+
+def timestep_embedding(t, dim):
+    t = t.to(torch.int64).contiguous()
+    out = alloc2d(t.shape[0], dim, t.device)
+    check(_lib.lib().b200pdm_timestep_embedding(t.data_ptr(), out.data_ptr(), out.stride(0), t.shape[0], dim, _stream()),
+          "timestep_embedding")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ loss / optimiser
+def pred_loss(pred, target, teacher, snr_w, sums, w_diff, w_kd, want_grad=True):
+    B = pred.shape[0]
+    n = pred.numel() // B
+    dpred = torch.empty_like(pred) if want_grad else None
+    check(_lib.lib().b200pdm_pred_loss(pred.data_ptr(), _ptr(target), _ptr(teacher), _ptr(snr_w), _ptr(dpred),
+                                       sums.data_ptr(), B, n, w_diff, w_kd, _stream()), "pred_loss")
+    return dpred
+
+
+def feature_loss(s, t, sums, n_maps, w_block, want_grad=True):
+    ds = torch.empty_like(s) if want_grad else None
+    check(_lib.lib().b200pdm_feature_loss(s.data_ptr(), t.data_ptr(), _ptr(ds), sums.data_ptr(), s.numel(),
+                                          1.0 / n_maps, w_block, _stream()), "feature_loss")
+    return ds
+
+
+def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, zero_grad=True):
+    check(_lib.lib().b200pdm_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), p.numel(),
+                                        lr, beta1, beta2, eps, wd, step, grad_scale, int(zero_grad), _stream()),
+          "adamw_step")
+
+
+def refresh_shadow(p, shadow):
+    check(_lib.lib().b200pdm_refresh_shadow(p.data_ptr(), shadow.data_ptr(), p.numel(), _stream()), "refresh_shadow")
+
+
+def diffusion_prep(x0, noise, t, sqrt_acp, sqrt_1macp):
+    B = x0.shape[0]
+    noisy, vt = torch.empty_like(x0), torch.empty_like(x0)
+    check(_lib.lib().b200pdm_diffusion_prep(x0.data_ptr(), noise.data_ptr(), t.data_ptr(), sqrt_acp.data_ptr(),
+                                            sqrt_1macp.data_ptr(), noisy.data_ptr(), vt.data_ptr(), B,
+                                            x0.numel() // B, _stream()), "diffusion_prep")
+    return noisy, vt
