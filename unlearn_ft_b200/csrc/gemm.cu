@@ -364,7 +364,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int j = 16; j < 32; ++j) v[j] = 0;
         }
         tmem_ld_wait();
-        const int nv = min(32, n_valid - c0);  // valid columns in this chunk
+        const int nv = min(min(32, p.block_n - c0), n_valid - c0);  // valid columns in this chunk
         if (row_ok && nv > 0) {
           float f[32];
 #pragma unroll
