@@ -132,17 +132,18 @@ int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx,
 int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                           float* stats, int batch, int hw, int C, int groups, float eps, int silu,
                           b200pdm_stream_t stream);
-/* dx, and dgamma/dbeta += (fp32).  workspace: fp32 [2 * batch * groups].                                    */
+/* dx (+ optional residual: a second gradient stream merged in the same pass), and dgamma/dbeta += (fp32).
+ * workspace: fp32 [2 * batch * groups].                                                                     */
 int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
-                          const float* beta, const float* stats, void* dx, int64_t lddx, float* dgamma,
-                          float* dbeta, float* workspace, int batch, int hw, int C, int groups, int silu,
-                          b200pdm_stream_t stream);
+                          const float* beta, const float* stats, const void* residual, int64_t ldr, void* dx,
+                          int64_t lddx, float* dgamma, float* dbeta, float* workspace, int batch, int hw, int C,
+                          int groups, int silu, b200pdm_stream_t stream);
 /* LayerNorm over the last dim of [rows, C] bf16 (diffusers BasicTransformerBlock.norm1/2/3).                */
 int b200pdm_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                           float* mean, float* rstd, int64_t rows, int C, float eps, b200pdm_stream_t stream);
 int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
-                          const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma,
-                          float* dbeta, int64_t rows, int C, b200pdm_stream_t stream);
+                          const float* mean, const float* rstd, const void* residual, int64_t ldr, void* dx,
+                          int64_t lddx, float* dgamma, float* dbeta, int64_t rows, int C, b200pdm_stream_t stream);
 /* GEGLU: out[r, f] = p[r, f] * gelu_erf(p[r, F + f]) for p = proj output [rows, 2F] (blocks.py:54-59).      */
 int b200pdm_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t ldo, int64_t rows, int F,
                       b200pdm_stream_t stream);
@@ -156,13 +157,19 @@ int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ld
                         int64_t rows, int cols, float scale, b200pdm_stream_t stream);
 /* Column sums: out[n] += sum_m x[m, n]  (bias gradients).                                                   */
 int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream);
+/* Per-sample column sums: out[r / rows_per_group, n] += x[r, n]  (gradient of the time-embedding broadcast add,
+ * blocks.py:339-341; summing it over samples gives the conv bias gradient).                                 */
+int b200pdm_colsum_grouped(const void* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int cols,
+                           int rows_per_group, b200pdm_stream_t stream);
+int b200pdm_cast_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream);
 /* Elementwise helpers over [rows, C] bf16 matrices with pitches. */
 int b200pdm_add(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows, int C,
                 b200pdm_stream_t stream);
 int b200pdm_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int C,
                    b200pdm_stream_t stream);
 int b200pdm_silu_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream);
-int b200pdm_silu_bwd_f32(const float* dy, const float* x, float* dx, int64_t n, b200pdm_stream_t stream);
+/* dx (bf16) = dy (bf16) * silu'(x) with x the saved fp32 pre-activation (contiguous). */
+int b200pdm_silu_bwd(const void* dy, const float* x, void* dx, int64_t n, b200pdm_stream_t stream);
 /* Nearest 2x upsample NHWC (diffusers Upsample2D, F.interpolate(scale=2, nearest)) and its adjoint.         */
 int b200pdm_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int batch, int h, int w, int C,
                            b200pdm_stream_t stream);
@@ -188,12 +195,13 @@ int b200pdm_timestep_embedding(const int64_t* t, void* out, int64_t ldo, int bat
 /* pred/target/teacher: fp32 [B, n_per_sample]; snr_w: fp32 [B] (min(snr+1,gamma)/(snr+1), trainer.py:2457-2466).
  * sums[0] += sum_b w_b * mean_chw (p-y)^2 / B     (diff loss)
  * sums[1] += mean (p - p_T)^2                     (distillation loss)
+ * sums[3] += w_diff * (diff term) + w_kd * (kd term)    (running weighted total; sums is fp32 [4], caller-zeroed)
  * dpred = w_diff * 2 w_b (p-y)/(B n) + w_kd * 2 (p-p_T)/(B n)                                              */
 int b200pdm_pred_loss(const float* pred, const float* target, const float* teacher, const float* snr_w,
                       float* dpred, float* sums, int batch, int64_t n_per_sample, float w_diff, float w_kd,
                       b200pdm_stream_t stream);
 /* One feature pair (bf16, same pitch layout): sums[2] += mean((s-t)^2) / n_maps ; ds = scale * 2 (s-t)/numel
- * with scale = w_block / n_maps (trainer.py:2475-2481).                                                    */
+ * with scale = w_block / n_maps (trainer.py:2475-2481); sums[3] += w_block * that term.                    */
 int b200pdm_feature_loss(const void* s, const void* t, void* ds, float* sums, int64_t numel, float inv_maps,
                          float w_block, b200pdm_stream_t stream);
 

@@ -22,6 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 TINY = dict(block_out_channels=(32, 64, 64, 64), heads=(2, 2, 2, 2), cross_attention_dim=48)
+# smallest configuration with head_dim 64 (what the sm_100a attention path is specialised for), for GPU parity
+SMALL64 = dict(block_out_channels=(128, 128, 256, 256), heads=(2, 2, 4, 4), cross_attention_dim=64)
 REF_BLOCKS = dict(down_block_types=("CrossAttnDownBlock2DHalfGated",) * 3 + ("DownBlock2DHalfGated",),
                   mid_block_type="UNetMidBlock2DCrossAttnWidthGated",
                   up_block_types=("UpBlock2DHalfGated",) + ("CrossAttnUpBlock2DHalfGated",) * 3)
@@ -152,6 +154,26 @@ def main():
             digests={k: tensor_digest(v) for k, v in m.state_dict().items()},
             n_params=sum(p.numel() for p in m.parameters()))
         print(name, "params", out[f"tiny_{name}"]["n_params"], "out abs max", float(y.abs().max()))
+
+    # 5. head_dim-64 network (B200 path vs the reference's own pruned model); outputs only, weights are a function of
+    #    deterministic_fill(seed=3)
+    gi = torch.Generator().manual_seed(77)
+    sample64 = torch.randn(2, 4, 16, 16, generator=gi)
+    ctx64 = torch.randn(2, 77, SMALL64["cross_attention_dim"], generator=gi)
+    t64 = torch.tensor([123, 940])
+    out["small64_inputs"] = dict(sample=sample64, timesteps=t64, ctx=ctx64)
+    for name, c in {"r055": dict(ratio=0.55, seed=21, drop=()), "r082_drop": dict(ratio=0.82, seed=22, drop=(1, 2, 8, 11))}.items():
+        probe = P.UNetGated(**SMALL64)
+        av = make_arch_vector(probe.get_structure(), c["ratio"], c["seed"], c["drop"])
+        m = ref_pruned_model(ref, SMALL64, av, seed=3)
+        feats = {}
+        P.cast_block_act_hooks(m, feats)
+        with torch.no_grad():
+            y = m(sample64, t64, ctx64).sample
+        out[f"small64_{name}"] = dict(arch_vector=av, sample=y, feats={k: v.clone() for k, v in feats.items()},
+                                      shapes={k: list(v.shape) for k, v in m.state_dict().items()},
+                                      n_params=sum(p.numel() for p in m.parameters()))
+        print("small64", name, "params", out[f"small64_{name}"]["n_params"], "out abs max", float(y.abs().max()))
 
     torch.save(out, os.path.join(GOLD, "reference_golden.pt"))
     meta = {"generated_by": "oracle/make_golden.py", "reference": "rezashkv/unlearn-ft @ /root/reference",

@@ -1,0 +1,78 @@
+"""CPU (no GPU): the drop-in boundary -- C-ABI exports, and the B200 model's structure / state-dict contract against the
+reference golden (models are built on the `meta` device: shapes only, no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "reference_golden.pt")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, weights_only=False)
+
+
+def test_cabi_exports_every_declared_symbol():
+    from unlearn_ft_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "b200pdm.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(b200pdm_\w+)\s*\(", header))
+    so = os.path.join(ROOT, "unlearn_ft_b200", "libb200pdm.so")
+    if not os.path.exists(so):
+        _lib.build()
+    h = ctypes.CDLL(so)
+    for name in declared:
+        assert hasattr(h, name), f"{name} declared in include/b200pdm.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.lib()
+    assert lib.b200pdm_version() >= 100
+    assert lib.b200pdm_launch_count() == 0          # nothing launched: no compute without a GPU
+
+
+def test_full_model_contract(gold):
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel, UNet2DConditionModelPruned
+    teacher = UNet2DConditionModel(device="meta", seed=None)
+    assert teacher.num_parameters() == 865_910_724 == gold["sd21_gated_params"]
+    assert teacher.get_structure() == gold["sd21_structure"]
+    assert {k: list(v.shape) for k, v in teacher.state_dict().items()} == gold["sd21_state_shapes"]
+    student = UNet2DConditionModelPruned(arch_vector=gold["av_full_seed1234_r055"], device="meta", seed=None)
+    assert student.num_parameters() == 508_224_076              # SURVEY App. C (r = 0.55)
+    with pytest.raises(RuntimeError):
+        student(torch.zeros(1, 4, 64, 64), torch.zeros(1, dtype=torch.long), torch.zeros(1, 77, 1024))
+
+
+@pytest.mark.parametrize("case", ["r055", "r082_drop"])
+def test_pruned_shapes_match_reference(gold, case):
+    from oracle.make_golden import SMALL64
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModelPruned
+    g = gold[f"small64_{case}"]
+    cfg = dict(block_out_channels=SMALL64["block_out_channels"], attention_head_dim=SMALL64["heads"],
+               cross_attention_dim=SMALL64["cross_attention_dim"])
+    m = UNet2DConditionModelPruned(cfg, arch_vector=g["arch_vector"], device="meta", seed=None)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == g["shapes"]
+    assert m.num_parameters() == g["n_params"]
+
+
+def test_arch_vector_classmethods_match_reference(gold):
+    from unlearn_ft_b200.pdm.models import HyperStructure
+    st = gold["sd21_structure"]
+    torch.manual_seed(1234)
+    av = HyperStructure.get_random_arch_vector(0.55, st)
+    assert torch.equal(av, gold["av_full_seed1234_r055"])
+    sep = HyperStructure.transform_arch_vector(av, st)
+    assert [int(w.shape[1]) for w in sep["width"]] == gold["av_full_split_lens"]
+    assert [float(d) for d in sep["depth"]] == gold["av_full_depth"]
+
+
+def test_hard_concrete_and_snr_match_reference(gold):
+    from unlearn_ft_b200.pdm.utils import compute_snr, hard_concrete
+
+    class S:
+        alphas_cumprod = torch.cumprod(1 - torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000) ** 2, 0)
+
+    assert torch.equal(hard_concrete(gold["hard_concrete_in"]), gold["hard_concrete_out"])
+    assert torch.equal(compute_snr(S, gold["snr_timesteps"]), gold["snr"])

@@ -56,18 +56,20 @@ _SIGS = {
     "b200pdm_conv_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, c_p],
     "b200pdm_conv_wgrad": [c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p],
     "b200pdm_groupnorm_fwd": [c_p, i64, c_p, c_p, c_p, i64, c_p, i32, i32, i32, i32, f32, i32, c_p],
-    "b200pdm_groupnorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p],
+    "b200pdm_groupnorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, i64, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p],
     "b200pdm_layernorm_fwd": [c_p, i64, c_p, c_p, c_p, i64, c_p, c_p, i64, i32, f32, c_p],
-    "b200pdm_layernorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, c_p, i64, i32, c_p],
+    "b200pdm_layernorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, i64, c_p, c_p, i64, i32, c_p],
     "b200pdm_geglu_fwd": [c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_geglu_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_softmax_fwd": [c_p, i64, c_p, i64, i64, i32, f32, c_p],
     "b200pdm_softmax_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, f32, c_p],
     "b200pdm_colsum": [c_p, i64, c_p, i64, i32, c_p],
+    "b200pdm_colsum_grouped": [c_p, i64, c_p, i64, i64, i32, i32, c_p],
+    "b200pdm_cast_f32_to_bf16": [c_p, c_p, i64, c_p],
     "b200pdm_add": [c_p, i64, c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_copy2d": [c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_silu_f32_to_bf16": [c_p, c_p, i64, c_p],
-    "b200pdm_silu_bwd_f32": [c_p, c_p, c_p, i64, c_p],
+    "b200pdm_silu_bwd": [c_p, c_p, c_p, i64, c_p],
     "b200pdm_upsample2x_fwd": [c_p, i64, c_p, i64, i32, i32, i32, i32, c_p],
     "b200pdm_upsample2x_bwd": [c_p, i64, c_p, i64, i32, i32, i32, i32, c_p],
     "b200pdm_zero_insert2x": [c_p, i64, c_p, i64, i32, i32, i32, i32, c_p],

@@ -108,6 +108,31 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __
   }
 }
 
+// out[g, c] += sum over rows r of group g (r / rows_per_group == g); grid (col_blocks, groups * slices_per_group)
+__global__ void colsum_grouped_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo,
+                                      int cols, int rows_per_group, int slices, int rows_per_slice) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int g = blockIdx.y / slices, s = blockIdx.y - g * slices;
+  const int64_t base = (int64_t)g * rows_per_group;
+  const int r0 = s * rows_per_slice, r1 = min(rows_per_group, r0 + rows_per_slice);
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += __bfloat162float(x[(base + r) * ldx + c]);
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+    atomicAdd(out + (int64_t)g * ldo + c, t);
+  }
+}
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+
 // ---------------------------------------------------------------- add / copy with pitches
 __global__ void add_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ b, int64_t ldb,
                            bf16* __restrict__ o, int64_t ldo, int64_t rows, int C, int cvec) {
@@ -150,10 +175,10 @@ __global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __res
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(silu_f(x[i]));
 }
-__global__ void silu_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
-                                    int64_t n) {
+__global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, bf16* __restrict__ dx,
+                                int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    dx[i] = dy[i] * silu_grad_f(x[i]);
+    dx[i] = __float2bfloat16(__bfloat162float(dy[i]) * silu_grad_f(x[i]));
 }
 
 // ---------------------------------------------------------------- nearest 2x upsample, adjoint, zero insertion
@@ -337,6 +362,27 @@ int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int col
   g_launches++;
   return B200PDM_OK;
 }
+int b200pdm_colsum_grouped(const void* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int cols,
+                           int rows_per_group, b200pdm_stream_t stream) {
+  if (rows_per_group <= 0 || rows % rows_per_group) return B200PDM_ERR_ARG;
+  const int groups = (int)(rows / rows_per_group);
+  int col_blocks = (cols + 31) / 32;
+  int slices = (148 * 4 + col_blocks * groups - 1) / (col_blocks * groups);
+  int rps = (rows_per_group + slices - 1) / slices;
+  if (rps < 32) rps = 32;
+  slices = (rows_per_group + rps - 1) / rps;
+  dim3 grid(col_blocks, groups * slices), block(32, 8);
+  colsum_grouped_kernel<<<grid, block, 0, STREAM>>>(CBF(x), ldx, out, ldo, cols, rows_per_group, slices, rps);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_cast_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream) {
+  cast_f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(x, BF(y), n);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
 int b200pdm_add(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows, int C,
                 b200pdm_stream_t stream) {
   if (lda % 8 || ldb % 8 || ldo % 8) return B200PDM_ERR_UNSUPPORTED;
@@ -360,8 +406,8 @@ int b200pdm_silu_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_
   g_launches++;
   return B200PDM_OK;
 }
-int b200pdm_silu_bwd_f32(const float* dy, const float* x, float* dx, int64_t n, b200pdm_stream_t stream) {
-  silu_bwd_f32_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(dy, x, dx, n);
+int b200pdm_silu_bwd(const void* dy, const float* x, void* dx, int64_t n, b200pdm_stream_t stream) {
+  silu_bwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(CBF(dy), x, BF(dx), n);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

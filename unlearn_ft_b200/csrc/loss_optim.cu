@@ -44,14 +44,23 @@ __global__ void pred_loss_kernel(const float* __restrict__ pred, const float* __
   sd = block_sum(sd, red);
   sk = block_sum(sk, red);
   if (threadIdx.x == 0) {
-    if (target) atomicAdd(&sums[0], sd * wb * inv_bn);
-    if (teacher) atomicAdd(&sums[1], sk * inv_bn);
+    float tot = 0.f;
+    if (target) {
+      atomicAdd(&sums[0], sd * wb * inv_bn);
+      tot += w_diff * sd * wb * inv_bn;
+    }
+    if (teacher) {
+      atomicAdd(&sums[1], sk * inv_bn);
+      tot += w_kd * sk * inv_bn;
+    }
+    atomicAdd(&sums[3], tot);  // running weighted total (trainer.py:2473-2486)
   }
 }
 
 // feature-KD: bf16 student/teacher maps (contiguous, numel % 8 == 0 on the vector path).
 __global__ void feature_loss_kernel(const bf16* __restrict__ s, const bf16* __restrict__ t, bf16* __restrict__ ds,
-                                    float* __restrict__ sums, int64_t numel, float inv_maps, float gscale) {
+                                    float* __restrict__ sums, int64_t numel, float inv_maps, float gscale,
+                                    float w_block) {
   __shared__ float red[32];
   const int64_t nvec = numel >> 3;
   float acc = 0.f;
@@ -76,7 +85,11 @@ __global__ void feature_loss_kernel(const bf16* __restrict__ s, const bf16* __re
     }
   }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(&sums[2], acc * inv_maps / (float)numel);
+  if (threadIdx.x == 0) {
+    const float c = acc * inv_maps / (float)numel;
+    atomicAdd(&sums[2], c);
+    atomicAdd(&sums[3], w_block * c);
+  }
 }
 
 // Flat AdamW: one thread handles 4 consecutive parameters (float4 I/O), bf16 shadow written as 8 bytes.
@@ -170,7 +183,7 @@ int b200pdm_feature_loss(const void* s, const void* t, void* ds, float* sums, in
   if (blocks < 1) blocks = 1;
   const float gscale = w_block * inv_maps * 2.f / (float)numel;
   feature_loss_kernel<<<(int)blocks, 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(s), reinterpret_cast<const bf16*>(t),
-                                                      reinterpret_cast<bf16*>(ds), sums, numel, inv_maps, gscale);
+                                                      reinterpret_cast<bf16*>(ds), sums, numel, inv_maps, gscale, w_block);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

@@ -168,8 +168,9 @@ __global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ dy, int64_t lddy, 
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ stats,
-                                    const float* __restrict__ ws, bf16* __restrict__ dx, int64_t lddx, int hw, int C,
-                                    int cpg, int groups, int silu, float inv_n, int64_t total_vec, int cvec) {
+                                    const float* __restrict__ ws, const bf16* __restrict__ res, int64_t ldr,
+                                    bf16* __restrict__ dx, int64_t lddx, int hw, int C, int cpg, int groups, int silu,
+                                    float inv_n, int64_t total_vec, int cvec) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = i / cvec;
     int cv = (int)(i - row * cvec);
@@ -202,6 +203,17 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
         if (silu) dz *= silu_grad_f(xh * ga + __ldg(beta + c));
         float s1 = __ldg(ws + 2 * sg) * inv_n, s2 = __ldg(ws + 2 * sg + 1) * inv_n;
         o[j] = r * (ga * dz - s1 - xh * s2);
+      }
+    }
+    if (res) {  // fused gradient merge: dx += residual (e.g. the skip/shortcut branch's gradient)
+      const bf16* rp = res + row * ldr + c0;
+      if (nv == 8) {
+        float rf[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(rp), rf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rf[j];
+      } else {
+        for (int j = 0; j < nv; ++j) o[j] += __bfloat162float(rp[j]);
       }
     }
     bf16* op = dx + row * lddx + c0;
@@ -275,9 +287,9 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, const flo
 template <int MAXV>
 __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
                               const float* __restrict__ gamma, const float* __restrict__ mean,
-                              const float* __restrict__ rstd, bf16* __restrict__ dx, int64_t lddx,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int C,
-                              int rows_per_block) {
+                              const float* __restrict__ rstd, const bf16* __restrict__ res, int64_t ldr,
+                              bf16* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
+                              float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block) {
   extern __shared__ float sh[];  // dgamma[C], dbeta[C]
   float* sdg = sh;
   float* sdb = sh + C;
@@ -325,6 +337,12 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const b
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = r * (gd[k][j] - s1 - xh[k][j] * s2);
+        if (res) {
+          float rf[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(res + row * ldr + vi * 8), rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rf[j];
+        }
         *reinterpret_cast<bf16x8*>(dx + row * lddx + vi * 8) = pack8(o);
       }
     }
@@ -391,8 +409,9 @@ int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
 
 // workspace: fp32 [2 * batch * groups].
 int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
-                          const float* beta, const float* stats, void* dx, int64_t lddx, float* dgamma, float* dbeta,
-                          float* workspace, int batch, int hw, int C, int groups, int silu, b200pdm_stream_t stream_) {
+                          const float* beta, const float* stats, const void* residual, int64_t ldr, void* dx,
+                          int64_t lddx, float* dgamma, float* dbeta, float* workspace, int batch, int hw, int C,
+                          int groups, int silu, b200pdm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (groups <= 0 || C % groups) return B200PDM_ERR_ARG;
   const int cpg = C / groups;
@@ -417,6 +436,7 @@ int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   if (blocks > 148 * 16) blocks = 148 * 16;
   gn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), lddy,
                                                  reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, workspace,
+                                                 reinterpret_cast<const bf16*>(residual), ldr,
                                                  reinterpret_cast<bf16*>(dx), lddx, hw, C, cpg, groups, silu,
                                                  1.f / ((float)hw * cpg), total_vec, cvec);
   B200_CHECK_LAUNCH();
@@ -447,8 +467,8 @@ int b200pdm_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
 }
 
 int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
-                          const float* mean, const float* rstd, void* dx, int64_t lddx, float* dgamma, float* dbeta,
-                          int64_t rows, int C, b200pdm_stream_t stream_) {
+                          const float* mean, const float* rstd, const void* residual, int64_t ldr, void* dx,
+                          int64_t lddx, float* dgamma, float* dbeta, int64_t rows, int C, b200pdm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (C % 8 || C > 8 * 32 * 5 || ldx % 8 || lddy % 8 || lddx % 8) {
     set_err("layernorm_bwd: C must be a multiple of 8 and <= 1280", "");
@@ -462,12 +482,14 @@ int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   bf16* dxb = reinterpret_cast<bf16*>(dx);
+  const bf16* rb = reinterpret_cast<const bf16*>(residual);
+  if (residual && ldr % 8) return B200PDM_ERR_UNSUPPORTED;
   if (C <= 8 * 32 * 2)
-    ln_bwd_kernel<2><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, dxb, lddx, dgamma, dbeta, rows,
-                                                 C, rows_per_block);
+    ln_bwd_kernel<2><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+                                                 dbeta, rows, C, rows_per_block);
   else
-    ln_bwd_kernel<5><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, dxb, lddx, dgamma, dbeta, rows,
-                                                 C, rows_per_block);
+    ln_bwd_kernel<5><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+                                                 dbeta, rows, C, rows_per_block);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

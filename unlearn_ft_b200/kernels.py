@@ -155,15 +155,17 @@ def groupnorm_fwd(x, gamma, beta, B, hw, groups, eps, silu, out=None):
     return out, stats
 
 
-def groupnorm_bwd(dy, x, gamma, beta, stats, dgamma, dbeta, B, hw, groups, silu, out=None):
+def groupnorm_bwd(dy, x, gamma, beta, stats, dgamma, dbeta, B, hw, groups, silu, out=None, residual=None):
     _chk2d(dy, "dy"), _chk2d(x, "x")
     Cn = x.shape[1]
     if out is None:
         out = alloc2d(B * hw, Cn, x.device)
     ws = torch.empty(2 * B * groups, device=x.device, dtype=F32)
     check(_lib.lib().b200pdm_groupnorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
-                                           beta.data_ptr(), stats.data_ptr(), out.data_ptr(), out.stride(0),
-                                           dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), B, hw, Cn, groups,
+                                           beta.data_ptr(), stats.data_ptr(), _ptr(residual),
+                                           residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                                           out.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), B, hw, Cn,
+                                           groups,
                                            int(silu), _stream()), "groupnorm_bwd")
     return out
 
@@ -181,14 +183,16 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, save=True, out=None):
     return out, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, out=None, residual=None):
     _chk2d(dy, "dy"), _chk2d(x, "x")
     rows, Cn = x.shape
     if out is None:
         out = alloc2d(rows, Cn, x.device)
     check(_lib.lib().b200pdm_layernorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
-                                           mean.data_ptr(), rstd.data_ptr(), out.data_ptr(), out.stride(0),
-                                           dgamma.data_ptr(), dbeta.data_ptr(), rows, Cn, _stream()), "layernorm_bwd")
+                                           mean.data_ptr(), rstd.data_ptr(), _ptr(residual),
+                                           residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                                           out.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), rows, Cn, _stream()),
+          "layernorm_bwd")
     return out
 
 
@@ -233,6 +237,32 @@ def colsum(x, out):
     return out
 
 
+def colsum_grouped(x, out, rows_per_group):
+    """out[g, n] (fp32, zero-initialised by the caller) += sum of the rows of group g."""
+    _chk2d(x, "x")
+    check(_lib.lib().b200pdm_colsum_grouped(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0],
+                                            x.shape[1], rows_per_group, _stream()), "colsum_grouped")
+    return out
+
+
+def cast_f32_to_bf16(x, out=None):
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(_lib.lib().b200pdm_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "cast")
+    return out
+
+
+def cast2d_f32_to_bf16(x):
+    """fp32 [rows, C] made by alloc2d (pitch round8(C)) -> bf16 matrix with the same pitch."""
+    rows, cols = x.shape
+    ld = x.stride(0)
+    if ld != round8(cols) or x.stride(1) != 1:
+        raise ValueError("cast2d_f32_to_bf16 expects an alloc2d-style fp32 matrix")
+    out = torch.empty(rows, ld, device=x.device, dtype=BF16)
+    check(_lib.lib().b200pdm_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), rows * ld - (ld - cols), _stream()), "cast2d")
+    return out[:, :cols] if ld != cols else out
+
+
 def add(a, b, out=None):
     _chk2d(a, "a"), _chk2d(b, "b")
     if out is None:
@@ -255,9 +285,10 @@ def silu_f32_to_bf16(x):
     return y
 
 
-def silu_bwd_f32(dy, x):
-    dx = torch.empty_like(x)
-    check(_lib.lib().b200pdm_silu_bwd_f32(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "silu_bwd")
+def silu_bwd(dy, x):
+    """dy: bf16 contiguous, x: fp32 contiguous (saved pre-activation) -> dx bf16."""
+    dx = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(_lib.lib().b200pdm_silu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "silu_bwd")
     return dx
 
 

@@ -1,0 +1,2 @@
+from .trainer import (BilevelUnetFineTuner, ConstantWithWarmup, FusedAdamW, GradReducer, NoiseScheduler,  # noqa: F401
+                      UnetFineTuner, cast_block_act_hooks, fused_kd_loss)
