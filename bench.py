@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one DDPM + output-KD + feature-KD training step of the APTP-pruned SD-2.1 U-Net
+(BASELINE.json config[1]): student r=0.55 (508.2 M params) + frozen full teacher (865.9 M), batch 16 per GPU,
+64x64 latents (512 px), 77x1024 text context, bf16 kernels / fp32 masters, fused AdamW.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same step driven from
+pinned host buffers through the public API (H2D of the batch + D2H of the loss inside the timed region).
+`--impl reference` times the reference's own CPU path (the oracle restatement: the reference itself needs diffusers,
+which cannot be installed here) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train samples/sec @512px pruned U-Net (DDPM+KD)"
+UNIT = "samples/s"
+# Algorithmic matmul/conv/attention FLOPs per sample for the both-loss step (SURVEY.md section 8d / BASELINE.md 3):
+# teacher fwd 0.804 + student fwd 0.464 + student bwd 2 * 0.464 (r = 0.55)
+STEP_TFLOP_PER_SAMPLE = {0.55: 2.196, 0.82: 2.823}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
+    ap.add_argument("--ratio", type=float, default=0.55)
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=1)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# clocks sampling (profiling guide recipe)
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference step) on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def build_oracle_cpu(ratio, seed=43):
+    import torch
+
+    from oracle import diffusers_restated as D
+    from oracle import pdm_restated as P
+
+    def fast_init(m):
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if p.dim() >= 2:
+                    p.normal_(0.0, 0.02, generator=g)
+                elif "norm" in n and n.endswith("weight"):
+                    p.fill_(1.0)
+                else:
+                    p.zero_()
+
+    with torch.device("meta"):
+        teacher = D.UNet2DConditionModel(**D.SD21_UNET_CONFIG)
+        student = P.UNetGated()
+    torch.manual_seed(seed)
+    av = P.get_random_arch_vector(ratio, student.get_structure())
+    teacher = teacher.to_empty(device="cpu")
+    student = student.to_empty(device="cpu")
+    fast_init(teacher), fast_init(student)
+    student.set_structure(P.transform_arch_vector(av, student.get_structure()))
+    student.prune()
+    return teacher.eval().requires_grad_(False), student.eval(), av
+
+
+def cpu_reference_run(ratio, latent, steps, warmup, batch=1):
+    """Times `steps` full training steps (teacher fwd, student fwd+bwd, AdamW) of the oracle on all host cores.
+    Bounded sample: batch 1 of the bench workload (same model, resolution, context, loss, optimiser)."""
+    import torch
+
+    from oracle import diffusers_restated as D
+    from oracle import pdm_restated as P
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    teacher, student, _ = build_oracle_cpu(ratio)
+    fs, ft = {}, {}
+    P.cast_block_act_hooks(student, fs), P.cast_block_act_hooks(teacher, ft)
+    sched = D.DDIMSchedulerLite()
+    opt = P.adamw_reference(student.parameters())
+    g = torch.Generator().manual_seed(43)
+    times = []
+    for i in range(warmup + steps):
+        lat, noise = torch.randn(batch, 4, latent, latent, generator=g), torch.randn(batch, 4, latent, latent, generator=g)
+        t = torch.randint(0, 1000, (batch,), generator=g)
+        ehs = torch.randn(batch, 77, 1024, generator=g)
+        t0 = time.perf_counter()
+        loss, _, _, _ = P.finetune_step(student, teacher, sched, lat, noise, t, ehs, fs, ft)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": batch * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} step(s) of batch {batch} (same model/resolution/loss/optimiser as the GPU workload; "
+                      f"fp32, torch {torch.__version__} CPU ops, {torch.get_num_threads()} threads, anomaly detection off)",
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------------------
+def gemm_roofline(torch, K, batch, latent):
+    """Dominant kernel = the tcgen05 implicit-GEMM convolution.  Time the largest-FLOP student conv shape of the step
+    (up_blocks.3 resnets.0 conv1: 960 -> 170 at 64x64, r = 0.55) in isolation with CUDA events on the launching
+    stream, rotating inputs through > L2 (126 MB) worth of buffers."""
+    B, H, W, Ci, Co = batch, latent, latent, 960, 170
+    nbuf = 6
+    xs = [K.alloc2d(B * H * W, Ci) for _ in range(nbuf)]     # 6 x 126 MB > L2
+    for x in xs:
+        x.normal_()
+    w = torch.randn(Co, 9, Ci, device="cuda", dtype=torch.bfloat16) * 0.02
+    bias = torch.zeros(Co, device="cuda")
+    out = K.alloc2d(B * H * W, Co)
+    for i in range(3):
+        K.conv_fwd(xs[i % nbuf], w, B, H, W, Co, 3, 1, bias=bias, out=out)
+    torch.cuda.synchronize()
+    iters = 24
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i in range(iters):
+        ev[i][0].record()
+        K.conv_fwd(xs[i % nbuf], w, B, H, W, Co, 3, 1, bias=bias, out=out)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    flops = 2.0 * B * H * W * Co * 9 * Ci
+    return flops / (ms * 1e-3) / 1e12, ms, f"conv3x3 {Ci}->{Co} @ {H}x{W} batch {B} (implicit GEMM M={B*H*W} N={Co} K={9*Ci})"
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"APTP r={args.ratio} pruned SD-2.1 U-Net (random arch vector, random init) + frozen SD-2.1 teacher, "
+                f"DDPM+output-KD+feature-KD step, batch {args.batch}/GPU, {args.latent}x{args.latent} latent, bf16")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = cpu_reference_run(args.ratio, args.latent, max(1, min(args.steps, 3)), min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": workload, "note": "reference CPU path = oracle restatement (diffusers not "
+                           "installable offline); timed steps capped at 3, warm-up at 1 to bound the run"},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from unlearn_ft_b200 import _lib
+    from unlearn_ft_b200 import kernels as K
+    from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModel, UNet2DConditionModelPruned
+    from unlearn_ft_b200.pdm.models.unet.unet_2d_conditional import SD21_CONFIG, structure_from_config
+    from unlearn_ft_b200.pdm.training import UnetFineTuner
+
+    torch.manual_seed(43)                                           # same arch vector on every rank
+    av = HyperStructure.get_random_arch_vector(args.ratio, structure_from_config(SD21_CONFIG))
+    student = UNet2DConditionModelPruned(arch_vector=av, seed=43)   # random_init path (configs/*_random.yaml:27)
+    teacher = UNet2DConditionModel(seed=44)
+    tuner = UnetFineTuner(student, teacher, lr=1e-6, warmup_steps=250)
+    B, L = args.batch, args.latent
+    g = torch.Generator().manual_seed(1000 + rank)                  # independent data per rank
+
+    def host_batch():
+        return dict(latents=torch.randn(B, 4, L, L, generator=g).pin_memory(),
+                    noise=torch.randn(B, 4, L, L, generator=g).pin_memory(),
+                    timesteps=torch.randint(0, 1000, (B,), generator=g).pin_memory(),
+                    prompt_embeds=torch.randn(B, 77, 1024, generator=g).bfloat16().pin_memory())
+
+    host_batches = [host_batch() for _ in range(4)]
+    dev_batches = [{k: v.cuda(non_blocking=True) for k, v in hb.items()} for hb in host_batches]
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    for i in range(max(args.warmup, 3)):
+        tuner.train_step(dev_batches[i % len(dev_batches)])
+    barrier()
+
+    # ---- timed: device-resident inputs (activations + parameters >> L2, so no L2 flush is needed between steps)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        tuner.train_step(dev_batches[i % len(dev_batches)])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    launches = _lib.launch_count() - n0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+
+    # ---- timed: end to end from pinned host memory through the public API
+    barrier()
+    e0.record()
+    last = None
+    for i in range(args.steps):
+        hb = host_batches[i % len(host_batches)]
+        db = {k: v.cuda(non_blocking=True) for k, v in hb.items()}
+        loss, _, _, _ = tuner.train_step(db)
+        last = float(loss)                                      # D2H read of the step's result (4 bytes) + sync
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    samples = world * B * args.steps
+    value = samples / (ms_total * 1e-3)
+    e2e_value = samples / (ms_e2e * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf, conv_ms, conv_desc = gemm_roofline(torch, K, B, L)
+    peak_burst = peaks.get("bf16_tflops", 1590.0)
+    step_tf = STEP_TFLOP_PER_SAMPLE.get(round(args.ratio, 2), 2.196) * B / (ms_total / args.steps * 1e-3) if ms_total else 0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": world * B, "parallelism": f"dp{world}",
+                   "student_params": student.num_parameters(), "teacher_params": teacher.num_parameters(),
+                   "l2": "no flush: per-step working set (1.4 B params x 2-4 B + activations) >> 126 MB L2",
+                   "last_loss": last},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
+                     "traffic": None, "kernel": "b200::gemm_kernel<0,0> (tcgen05 implicit-GEMM conv)", "shape": conv_desc,
+                     "ms_per_launch": conv_ms,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), of measured"
+                     if peaks else "fallback 1590 TFLOP/s, of fallback",
+                     "step_algorithmic_tflops": step_tf,
+                     "step_frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", 1400.0)},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            res = cpu_reference_run(args.ratio, L, args.cpu_steps, 0)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {e!r}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

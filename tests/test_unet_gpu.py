@@ -119,7 +119,10 @@ def test_training_step_matches_oracle(gold):
     from unlearn_ft_b200.pdm.training import UnetFineTuner
     av = gold["small64_r082_drop"]["arch_vector"]
     mine, orc = build_pair(av, trainable=True)
-    teacher_o = P.UNetGated(**SMALL64)
+    from oracle import diffusers_restated as D
+    teacher_o = D.UNet2DConditionModel(**{**D.SD21_UNET_CONFIG, "block_out_channels": SMALL64["block_out_channels"],
+                                          "attention_head_dim": SMALL64["heads"],
+                                          "cross_attention_dim": SMALL64["cross_attention_dim"]})
     deterministic_fill(teacher_o, 5)
     teacher = UNet2DConditionModel(small_cfg(), seed=None)
     teacher.load_state_dict(teacher_o.state_dict())
