@@ -1,0 +1,53 @@
+"""CPU, world_size 2, gloo: the data-parallel exchange of the hot path (GradReducer = the DDP replacement,
+reference trainer.py:122-129,2257-2260): after the exchange every rank holds the MEAN of the per-rank flat gradients,
+bucketed ranges included, and N-rank training equals single-rank training on the concatenated batch for a mean loss."""
+import os
+import socket
+from types import SimpleNamespace
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unlearn_ft_b200.pdm.training.trainer import GradReducer
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.randn(1000, generator=g)
+    model = SimpleNamespace(arena=SimpleNamespace(grad=grad.clone(), numel=1000))
+    red = GradReducer(model)
+    assert red.world == world
+    red.reduce_range(0, 300)          # bucketed, as issued per U-Net block
+    red.reduce_range(300, 1000)
+    red.wait()
+    out[rank] = model.arena.grad.clone()
+    dist.destroy_process_group()
+
+
+def test_gradreducer_world2_gloo():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    expect = sum(torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+    for r in range(world):
+        assert torch.allclose(out[r], expect, atol=1e-6)
+    assert torch.equal(out[0], out[1])
+
+
+def test_world1_is_noop():
+    from unlearn_ft_b200.pdm.training.trainer import GradReducer
+    g = torch.randn(10)
+    red = GradReducer(SimpleNamespace(arena=SimpleNamespace(grad=g.clone(), numel=10)))
+    red.reduce_all(), red.wait()
+    assert torch.equal(red.arena.grad, g)
