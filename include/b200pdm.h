@@ -87,6 +87,9 @@ typedef struct {
   int block_n;              /* 0 = choose                                                                  */
 } b200pdm_gemm_desc;
 
+/* Diagnostics: with B200PDM_GEMM_TRACE=1 in the environment every GEMM launch is timed (serialising); this writes the
+ * per-shape table (tab separated) to `path` (host string) and clears it. */
+int b200pdm_gemm_trace_dump(const char* path);
 /* Generic launch. */
 int b200pdm_gemm(const b200pdm_gemm_desc* desc, b200pdm_stream_t stream);
 
@@ -155,6 +158,13 @@ int b200pdm_softmax_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64
 /* ds = scale * p * (dp - sum(dp*p)) ; dp fp32 in, ds bf16 out.                                              */
 int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ldp, void* ds, int64_t ldds,
                         int64_t rows, int cols, float scale, b200pdm_stream_t stream);
+/* Fused flash-style attention forward on tcgen05, head_dim 64, no mask (blocks.py:275-277 = SDPA): scores and
+ * probabilities stay in TMEM / shared memory.  q: [B*Lq, >= H*64] pitch ldq (head h = columns [64h, 64h+64));
+ * k, v: [B*Lk, ...] pitches ldk/ldv; out like q (pitch ldo); lse: fp32 [B, H, Lq] = log2-domain log-sum-exp of
+ * scale*log2(e)*scores (or NULL).                                                                           */
+int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk, float scale,
+                          b200pdm_stream_t stream);
 /* Column sums: out[n] += sum_m x[m, n]  (bias gradients).                                                   */
 int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream);
 /* Per-sample column sums: out[r / rows_per_group, n] += x[r, n]  (gradient of the time-embedding broadcast add,

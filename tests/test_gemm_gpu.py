@@ -163,3 +163,24 @@ def test_bmm_attention_shapes():
           b_bs=(D, Lk * H * D), o_ld=H * D, o_bs=(D, L * H * D))
     oref = (p[..., :Lk].float() @ vh).transpose(1, 2).reshape(B, L, H * D)
     assert rel_err(o, oref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 5, 4096, 4096), (2, 2, 1024, 1024), (3, 4, 256, 256), (2, 3, 64, 64),
+                                       (2, 5, 4096, 77), (2, 2, 64, 77), (1, 20, 256, 77), (2, 1, 384, 200)])
+def test_flash_attention_fwd(B, H, Lq, Lk):
+    """Fused tcgen05 attention forward vs torch SDPA (fp32 math on the same bf16 inputs)."""
+    k = _k()
+    D = 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    # q/k/v as column slices of fused projection outputs (pitch 3*H*D) like the model uses them
+    qkv = torch.randn(B * max(Lq, Lk), 3 * H * D, device="cuda", generator=g).bfloat16()
+    q, kk, v = qkv[:B * Lq, :H * D], qkv[:B * Lk, H * D:2 * H * D], qkv[:B * Lk, 2 * H * D:]
+    out, lse = k.attention_fwd(q, kk, v, B, H, Lq, Lk, D ** -0.5, want_lse=True)
+    qh = q.float().reshape(B, Lq, H, D).transpose(1, 2)
+    kh = kk.float().reshape(B, Lk, H, D).transpose(1, 2)
+    vh = v.float().reshape(B, Lk, H, D).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(B * Lq, H * D)
+    assert rel_err(out, ref) < 2e-2
+    s = (qh @ kh.transpose(-1, -2)) * D ** -0.5
+    lse_ref = torch.logsumexp(s, -1) / 0.6931471805599453
+    assert (lse.view(B, H, Lq) - lse_ref).abs().max() < 2e-2

@@ -29,8 +29,14 @@ batch = dict(latents=torch.randn(B, 4, 64, 64, generator=g).cuda(), noise=torch.
 for _ in range(args.warm):
     tuner.train_step(batch)
 torch.cuda.synchronize()
+if os.environ.get("B200PDM_GEMM_TRACE"):
+    from unlearn_ft_b200 import _lib
+    _lib.lib().b200pdm_gemm_trace_dump(b"/dev/null")   # drop warm-up rows
 torch.cuda.cudart().cudaProfilerStart()
 out = tuner.train_step(batch)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("loss", float(out[0]))
+if os.environ.get("B200PDM_GEMM_TRACE"):
+    from unlearn_ft_b200 import _lib
+    _lib.lib().b200pdm_gemm_trace_dump(b"gpurun_out/gemm_trace.tsv")

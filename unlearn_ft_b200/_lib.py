@@ -48,6 +48,7 @@ _SIGS = {
     "b200pdm_version": [],
     "b200pdm_last_error": [],
     "b200pdm_launch_count": [],
+    "b200pdm_gemm_trace_dump": [C.c_char_p],
     "b200pdm_gemm": [C.POINTER(GemmDesc), c_p],
     "b200pdm_linear_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i32, i64, i64, i64, c_p],
     "b200pdm_linear_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i64, i64, i64, c_p],
@@ -63,6 +64,7 @@ _SIGS = {
     "b200pdm_geglu_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_softmax_fwd": [c_p, i64, c_p, i64, i64, i32, f32, c_p],
     "b200pdm_softmax_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, f32, c_p],
+    "b200pdm_attention_fwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i32, i32, i32, i32, f32, c_p],
     "b200pdm_colsum": [c_p, i64, c_p, i64, i32, c_p],
     "b200pdm_colsum_grouped": [c_p, i64, c_p, i64, i64, i32, i32, c_p],
     "b200pdm_cast_f32_to_bf16": [c_p, c_p, i64, c_p],

@@ -1,0 +1,268 @@
+// Fused flash-style attention for sm_100a, head_dim 64, no mask (reference: F.scaled_dot_product_attention at
+// pdm/models/unet/blocks.py:275-277, called by HeadGatedAttnProcessor2 for self (Lq = Lk in {4096,1024,256,64}) and
+// cross (Lk = 77) attention).
+//
+// One CTA = one (sample, head, 128-query block); 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs.
+//   warp 0 (one lane) : TMA producer  - Q once, then K/V blocks of 128 keys through a 2-stage smem ring
+//   warp 1 (one lane) : MMA issuer    - S = Q K^T (tcgen05.mma M128 N128 K64 -> TMEM), O_blk = P V (M128 N64 K128)
+//   warps 2..5        : softmax       - each thread owns one query row (= one TMEM lane): online softmax in the
+//                                       log2 domain, P written as bf16 into a swizzle-128B K-major smem tile that the
+//                                       second MMA consumes, running output kept in registers (64 fp32)
+// Scores never touch HBM: traffic per launch = Q + K + V + O (+ LSE).
+#include "common.cuh"
+#include "../../include/b200pdm.h"
+
+#include <atomic>
+#include <string.h>
+
+namespace b200 {
+extern std::atomic<uint64_t> g_launches;
+void set_err(const char* fmt, const char* a);
+int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                    const uint32_t* box);
+
+constexpr int kQ = 128, kKV = 128, kD = 64;
+constexpr int kTileBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B tile
+constexpr int kAttnThreads = 192;
+
+struct AttnFwdParams {
+  int B, H, Lq, Lk, nkv;
+  float scale_log2;  // softmax scale * log2(e)
+  bf16* out;
+  int64_t ldo;
+  float* lse;  // [B, H, Lq] log2-domain log-sum-exp (may be null)
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTileBytes;
+  uint8_t* sV = smem + 3 * kTileBytes;
+  uint8_t* sP = smem + 5 * kTileBytes;  // two [128 x 64] sub-tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * kQ;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("b200pdm attention: dynamic smem not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(pv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem;         // 128 columns
+  const uint32_t tmem_pv = tmem + 128;  // 64 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_4d(sQ, &tm_q, q_full, 0, q0, h, b);
+      for (int j = 0; j < p.nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
+        tma_load_4d(sK + s * kTileBytes, &tm_k, &kv_full[s], 0, j * kKV, h, b);
+        tma_load_4d(sV + s * kTileBytes, &tm_v, &kv_full[s], 0, j * kKV, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kKV, 0, 0);  // S: N = 128 keys, A/B K-major
+      const uint32_t idesc_o = make_idesc_bf16(kD, 0, 1);   // PV: N = 64, B (= V) MN-major
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < p.nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP), v_addr = smem_u32(sV + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kKV / 16; ++k)
+          umma_bf16(tmem_pv, make_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, k > 0);
+        umma_commit(pv_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // query row within the block == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float o[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    const uint32_t p_row = smem_u32(sP) + r * 128;
+    const int sw = r & 7;
+    for (int j = 0; j < p.nkv; ++j) {
+      const int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m, mx * p.scale_log2);
+      const float alpha = exp2f(m - m_new);
+      l *= alpha;
+      // pass 2: probabilities -> bf16 P tile (K-major, swizzle-128B)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
+        tmem_ld_wait();
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+          e = (c * 32 + i < valid) ? e : 0.f;
+          pf[i] = e;
+          l += e;
+        }
+        const uint32_t base = p_row + (c >> 1) * kTileBytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(pf[g * 8 + 0], pf[g * 8 + 1]);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(pf[g * 8 + 2], pf[g * 8 + 3]);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(pf[g * 8 + 4], pf[g * 8 + 5]);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(pf[g * 8 + 6], pf[g * 8 + 7]);
+          const int chunk = ((c & 1) * 4 + g) ^ sw;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
+                       "r"(*reinterpret_cast<uint32_t*>(&a0)), "r"(*reinterpret_cast<uint32_t*>(&a1)),
+                       "r"(*reinterpret_cast<uint32_t*>(&a2)), "r"(*reinterpret_cast<uint32_t*>(&a3))
+                       : "memory");
+        }
+      }
+      m = m_new;
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+#pragma unroll
+      for (int i = 0; i < kD; ++i) o[i] *= alpha;
+      mbar_wait(pv_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_pv + lane_base + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+    }
+    const int q = q0 + r;
+    if (q < p.Lq) {
+      const float inv = 1.f / l;
+      bf16* dst = p.out + (static_cast<int64_t>(b) * p.Lq + q) * p.ldo + h * kD;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float t8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = o[g * 8 + i] * inv;
+        *reinterpret_cast<bf16x8*>(dst + g * 8) = pack8(t8);
+      }
+      if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = m + log2f(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+static int make_qkv_map(CUtensorMap* map, const void* ptr, int64_t ld, int B, int H, int L) {
+  // dims (d, token, head, batch)
+  uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+  uint64_t str[4] = {1, (uint64_t)ld, 64, (uint64_t)L * (uint64_t)ld};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return make_map_public(map, ptr, 4, dims, str, box);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                     void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk,
+                                     float scale, b200pdm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !k || !v || !out || batch <= 0 || heads <= 0 || lq <= 0 || lk <= 0) return B200PDM_ERR_ARG;
+  if (ldo % 8 || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    set_err("attention_fwd: output pitch/base must be 16-byte aligned", "");
+    return B200PDM_ERR_ARG;
+  }
+  CUtensorMap mq, mk, mv;
+  int rc = make_qkv_map(&mq, q, ldq, batch, heads, lq);
+  if (rc) return rc;
+  rc = make_qkv_map(&mk, k, ldk, batch, heads, lk);
+  if (rc) return rc;
+  rc = make_qkv_map(&mv, v, ldv, batch, heads, lk);
+  if (rc) return rc;
+  AttnFwdParams p;
+  p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nkv = (lk + kKV - 1) / kKV;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = reinterpret_cast<bf16*>(out), p.ldo = ldo, p.lse = lse;
+  const size_t smem = 7 * kTileBytes + 256;
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_err("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return B200PDM_ERR_CUDA;
+  }
+  dim3 grid((lq + kQ - 1) / kQ, heads, batch);
+  attn_fwd_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mk, mv, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_err("attention_fwd launch: %s", cudaGetErrorString(e));
+    return B200PDM_ERR_CUDA;
+  }
+  g_launches++;
+  return B200PDM_OK;
+}

@@ -14,7 +14,10 @@
 #include "../../include/b200pdm.h"
 
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <stdlib.h>
+#include <string>
 #include <stdio.h>
 #include <string.h>
 
@@ -82,6 +85,11 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
     return B200PDM_ERR_DRIVER;
   }
   return B200PDM_OK;
+}
+
+int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                    const uint32_t* box) {
+  return make_map(map, ptr, rank, dims, strides_el, box, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -559,6 +567,19 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
   return B200PDM_ERR_ARG;
 }
 
+// Optional per-shape timing table (B200PDM_GEMM_TRACE=1): every launch is bracketed by events and synchronised, so it
+// serialises the stream -- diagnostics only, never enabled in bench.py.
+struct TraceRow {
+  long count = 0;
+  double ms = 0, flops = 0;
+};
+static std::map<std::string, TraceRow> g_trace;
+static int trace_on() {
+  static int on = -1;
+  if (on < 0) on = getenv("B200PDM_GEMM_TRACE") ? 1 : 0;
+  return on;
+}
+
 static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   if (!d || !d->a.ptr || !d->b.ptr || !d->out) {
     set_err("gemm: null pointer");
@@ -650,12 +671,15 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
 
   auto launch = [&](auto kern) -> int {
-    static thread_local const void* configured[4] = {nullptr, nullptr, nullptr, nullptr};
-    (void)configured;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       set_err("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return B200PDM_ERR_CUDA;
+    }
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (trace_on()) {
+      cudaEventCreate(&t0), cudaEventCreate(&t1);
+      cudaEventRecord(t0, stream);
     }
     kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
     e = cudaGetLastError();
@@ -664,6 +688,20 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       return B200PDM_ERR_CUDA;
     }
     g_launches++;
+    if (trace_on()) {
+      cudaEventRecord(t1, stream);
+      cudaEventSynchronize(t1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      char key[256];
+      const double kk = (double)kblocks * 64;
+      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d split=%d tiles=%ld grid=%d stages=%d", d->a.mode,
+               d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.splits, total_tiles, grid, stages);
+      TraceRow& r = g_trace[key];
+      r.count++, r.ms += ms;
+      r.flops += 2.0 * (double)d->M * p.n_per_group * p.n_groups * kk * p.Z;
+      cudaEventDestroy(t0), cudaEventDestroy(t1);
+    }
     return B200PDM_OK;
   };
   if (!a_mn && !b_mn) return launch(gemm_kernel<0, 0>);
@@ -681,6 +719,18 @@ extern "C" {
 int b200pdm_version(void) { return 100; }
 const char* b200pdm_last_error(void) { return get_err(); }
 uint64_t b200pdm_launch_count(void) { return g_launches.load(); }
+
+int b200pdm_gemm_trace_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) return B200PDM_ERR_ARG;
+  fprintf(f, "ms_total\tcount\tms_avg\ttflops\tshape\n");
+  for (auto& kv : g_trace)
+    fprintf(f, "%.4f\t%ld\t%.4f\t%.1f\t%s\n", kv.second.ms, kv.second.count, kv.second.ms / kv.second.count,
+            kv.second.flops / (kv.second.ms * 1e-3) / 1e12, kv.first.c_str());
+  fclose(f);
+  g_trace.clear();
+  return B200PDM_OK;
+}
 
 int b200pdm_gemm(const b200pdm_gemm_desc* desc, b200pdm_stream_t stream) {
   return launch_gemm(desc, reinterpret_cast<cudaStream_t>(stream));

@@ -229,6 +229,17 @@ def softmax_bwd(dp, p, ds, rows, cols, scale):
     return ds
 
 
+def attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=None, want_lse=False):
+    """Fused attention forward (head_dim 64). q: [B*Lq, >=heads*64] view, k/v: [B*Lk, ...] views."""
+    if out is None:
+        out = alloc2d(B * Lq, heads * 64, q.device)
+    lse = torch.empty(B * heads * Lq, device=q.device, dtype=F32) if want_lse else None
+    check(_lib.lib().b200pdm_attention_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                           v.stride(0), out.data_ptr(), out.stride(0), _ptr(lse), B, heads, Lq, Lk,
+                                           scale, _stream()), "attention_fwd")
+    return out, lse
+
+
 def colsum(x, out):
     """out[n] (fp32) += sum_m x[m, n]."""
     _chk2d(x, "x")

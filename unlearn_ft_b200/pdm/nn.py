@@ -303,6 +303,9 @@ def attention(q, k, v, B, heads, Lq, Lk, need_bwd, out=None):
     """
     D = 64
     scale = D ** -0.5
+    if not need_bwd:   # forward-only (teacher / sampling): fused flash-style kernel, scores never leave the SM
+        o, _ = K.attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=out)
+        return o, None
     Lkp = K.round8(Lk)
     dev = q.device
     ldq, ldk, ldv = q.stride(0), k.stride(0), v.stride(0)
