@@ -165,6 +165,13 @@ int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ld
 int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                           void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk, float scale,
                           b200pdm_stream_t stream);
+/* Backward of the fused attention (flash style: probabilities are recomputed per 128x128 tile from q, k and the
+ * forward's lse; dV/dK accumulate in TMEM, dQ through fp32 vector atomics).  out/dout: forward output and its
+ * gradient; dq/dk/dv: bf16 outputs with pitches; workspace: fp32 [roundup4(B*H*Lq) + B*Lq*H*64].               */
+int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, void* dq,
+                          int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* workspace, int batch,
+                          int heads, int lq, int lk, float scale, b200pdm_stream_t stream);
 /* Column sums: out[n] += sum_m x[m, n]  (bias gradients).                                                   */
 int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream);
 /* Per-sample column sums: out[r / rows_per_group, n] += x[r, n]  (gradient of the time-embedding broadcast add,

@@ -184,3 +184,27 @@ def test_flash_attention_fwd(B, H, Lq, Lk):
     s = (qh @ kh.transpose(-1, -2)) * D ** -0.5
     lse_ref = torch.logsumexp(s, -1) / 0.6931471805599453
     assert (lse.view(B, H, Lq) - lse_ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 2, 1024, 1024), (1, 5, 4096, 4096), (3, 4, 256, 256), (2, 3, 64, 64),
+                                       (2, 2, 4096, 77), (2, 2, 64, 77), (2, 1, 384, 200)])
+def test_flash_attention_bwd(B, H, Lq, Lk):
+    """Fused attention backward vs torch autograd through SDPA (fp32 math on the same bf16 inputs)."""
+    k = _k()
+    D = 64
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.randn(B * max(Lq, Lk), 3 * H * D, device="cuda", generator=g).bfloat16()
+    q, kk, v = qkv[:B * Lq, :H * D], qkv[:B * Lk, H * D:2 * H * D], qkv[:B * Lk, 2 * H * D:]
+    do = (torch.randn(B * Lq, H * D, device="cuda", generator=g) * 0.5).bfloat16()
+    out, lse = k.attention_fwd(q, kk, v, B, H, Lq, Lk, D ** -0.5, want_lse=True)
+    dqkv = torch.zeros(B * max(Lq, Lk), 3 * H * D, device="cuda", dtype=torch.bfloat16)
+    dq, dk, dv = dqkv[:B * Lq, :H * D], dqkv[:B * Lk, H * D:2 * H * D], dqkv[:B * Lk, 2 * H * D:]
+    k.attention_bwd(q, kk, v, out, do, lse, dq, dk, dv, B, H, Lq, Lk, D ** -0.5)
+    qh = q.float().reshape(B, Lq, H, D).transpose(1, 2).requires_grad_(True)
+    kh = kk.float().reshape(B, Lk, H, D).transpose(1, 2).requires_grad_(True)
+    vh = v.float().reshape(B, Lk, H, D).transpose(1, 2).requires_grad_(True)
+    ref = F.scaled_dot_product_attention(qh, kh, vh)
+    ref.backward(do.float().reshape(B, Lq, H, D).transpose(1, 2))
+    for name, mine, r in (("dq", dq, qh.grad), ("dk", dk, kh.grad), ("dv", dv, vh.grad)):
+        L = r.shape[2]
+        assert rel_err(mine, r.transpose(1, 2).reshape(B * L, H * D)) < 3e-2, name

@@ -65,6 +65,8 @@ _SIGS = {
     "b200pdm_softmax_fwd": [c_p, i64, c_p, i64, i64, i32, f32, c_p],
     "b200pdm_softmax_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, f32, c_p],
     "b200pdm_attention_fwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i32, i32, i32, i32, f32, c_p],
+    "b200pdm_attention_bwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, c_p,
+                              i32, i32, i32, i32, f32, c_p],
     "b200pdm_colsum": [c_p, i64, c_p, i64, i32, c_p],
     "b200pdm_colsum_grouped": [c_p, i64, c_p, i64, i64, i32, i32, c_p],
     "b200pdm_cast_f32_to_bf16": [c_p, c_p, i64, c_p],

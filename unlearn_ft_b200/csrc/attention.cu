@@ -266,3 +266,334 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
   g_launches++;
   return B200PDM_OK;
 }
+
+// ================================================================================================================
+// Backward.  One CTA = one (sample, head, 128-key block); loops over 128-query blocks i:
+//   S = Q_i K^T, dP = dO_i V^T                      (tensor core -> TMEM)
+//   P = exp2(S*c - LSE), dS = P o (dP - D) * scale   (softmax threads; bf16 tiles to smem)
+//   dV += P^T dO_i, dK += dS^T Q_i                   (accumulate in TMEM across i)
+//   dQ_i = dS K                                      (TMEM -> fp32 vector atomics into dq_acc)
+// The same swizzle-128B smem tiles are consumed K-major or MN-major by changing only the UMMA descriptors, so K, Q,
+// dO, P and dS are each staged once.  D = rowsum(dO o O) is precomputed by attn_delta_kernel.
+// ================================================================================================================
+namespace b200 {
+
+struct AttnBwdParams {
+  int B, H, Lq, Lk, nq;
+  float scale, scale_log2;
+  const float* lse;    // [B, H, Lq] (log2 domain)
+  const float* delta;  // [B, H, Lq]
+  float* dq_acc;       // fp32 [B*Lq, ld_dq], head h at columns [64h, 64h+64)
+  int64_t ld_dq;
+  bf16* dk;
+  int64_t ld_dk;
+  bf16* dv;
+  int64_t ld_dv;
+};
+
+__global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t lddo, const bf16* __restrict__ O, int64_t ldo,
+                                  float* __restrict__ delta, int B, int H, int Lq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);  // (b*Lq + q)*H + h
+  if (row >= (int64_t)B * Lq * H) return;
+  const int h = (int)(row % H);
+  const int64_t tok = row / H;
+  const int b = (int)(tok / Lq), q = (int)(tok % Lq);
+  float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + tok * lddo + h * 64 + 2 * lane));
+  float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + tok * ldo + h * 64 + 2 * lane));
+  float s = warp_sum(a.x * c.x + a.y * c.y);
+  if (lane == 0) delta[((int64_t)b * H + h) * Lq + q] = s;
+}
+
+__device__ __forceinline__ void st_tile_row32(uint32_t row_base, int c, int sw, const float (&f)[32]) {
+  // 32 consecutive columns [32c, 32c+32) of this thread's row into the two-subtile K-major swizzle-128B layout
+  const uint32_t base = row_base + (c >> 1) * kTileBytes;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    __nv_bfloat162 a0 = __floats2bfloat162_rn(f[g * 8 + 0], f[g * 8 + 1]);
+    __nv_bfloat162 a1 = __floats2bfloat162_rn(f[g * 8 + 2], f[g * 8 + 3]);
+    __nv_bfloat162 a2 = __floats2bfloat162_rn(f[g * 8 + 4], f[g * 8 + 5]);
+    __nv_bfloat162 a3 = __floats2bfloat162_rn(f[g * 8 + 6], f[g * 8 + 7]);
+    const int chunk = ((c & 1) * 4 + g) ^ sw;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
+                 "r"(*reinterpret_cast<uint32_t*>(&a0)), "r"(*reinterpret_cast<uint32_t*>(&a1)),
+                 "r"(*reinterpret_cast<uint32_t*>(&a2)), "r"(*reinterpret_cast<uint32_t*>(&a3))
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kTileBytes;
+  uint8_t* sQ = smem + 2 * kTileBytes;    // [2]
+  uint8_t* sdO = smem + 4 * kTileBytes;   // [2]
+  uint8_t* sP = smem + 6 * kTileBytes;    // two sub-tiles
+  uint8_t* sdS = smem + 8 * kTileBytes;   // two sub-tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * kTileBytes);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* pds_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_empty = bars + 8;
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int k0 = kb * kKV;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) __trap();
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * kTileBytes);
+      tma_load_4d(sK, &tm_k, kv_full, 0, k0, h, b);
+      tma_load_4d(sV, &tm_v, kv_full, 0, k0, h, b);
+      for (int i = 0; i < p.nq; ++i) {
+        const int s = i & 1;
+        mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[s], 2 * kTileBytes);
+        tma_load_4d(sQ + s * kTileBytes, &tm_q, &qdo_full[s], 0, i * kQ, h, b);
+        tma_load_4d(sdO + s * kTileBytes, &tm_do, &qdo_full[s], 0, i * kQ, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_kk128 = make_idesc_bf16(128, 0, 0);  // S, dP : A K-major, B K-major, N = 128
+      const uint32_t id_mm64 = make_idesc_bf16(64, 1, 1);    // dV, dK: A MN-major (P^T / dS^T), B MN-major, N = 64
+      const uint32_t id_km64 = make_idesc_bf16(64, 0, 1);    // dQ    : A K-major (dS), B MN-major (K), N = 64
+      mbar_wait(kv_full, 0);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
+      for (int i = 0; i < p.nq; ++i) {
+        const int s = i & 1;
+        mbar_wait(&qdo_full[s], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + s * kTileBytes), do_addr = smem_u32(sdO + s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // S = Q K^T
+          umma_bf16(t_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                    id_kk128, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dP = dO V^T
+          umma_bf16(t_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                    make_smem_desc_sw128(v_addr + k * 32, 16, 1024), id_kk128, k > 0);
+        umma_commit(s_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV += P^T dO   (A: M' = keys over the two sub-tiles (LBO), K' = query rows)
+          umma_bf16(t_dv, make_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
+                    make_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK += dS^T Q
+          umma_bf16(t_dk, make_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
+                    make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
+        if (i > 0) {
+          mbar_wait(dq_empty, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_i = dS K  (A K-major over the two sub-tiles, B = K tile read MN-major)
+          umma_bf16(t_dq, make_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), id_km64, k > 0);
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t p_row = smem_u32(sP) + r * 128, ds_row = smem_u32(sdS) + r * 128;
+    const int sw = r & 7;
+    const int valid_k = min(kKV, p.Lk - k0);
+    const int64_t bh = (int64_t)b * p.H + h;
+    for (int i = 0; i < p.nq; ++i) {
+      const int q = i * kQ + r;
+      const bool q_ok = q < p.Lq;
+      const float lse = q_ok ? p.lse[bh * p.Lq + q] : 0.f;
+      const float dlt = q_ok ? p.delta[bh * p.Lq + q] : 0.f;
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv_[32];
+        tmem_ld_32x32(t_s + lane_base + c * 32, sv);
+        tmem_ld_32x32(t_dp + lane_base + c * 32, dv_);
+        tmem_ld_wait();
+        float pf[32], dsf[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float pe = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
+          pe = (q_ok && (c * 32 + j < valid_k)) ? pe : 0.f;
+          pf[j] = pe;
+          dsf[j] = pe * (__uint_as_float(dv_[j]) - dlt) * p.scale;
+        }
+        st_tile_row32(p_row, c, sw, pf);
+        st_tile_row32(ds_row, c, sw, dsf);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_dq + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (q_ok) {
+          float* dst = p.dq_acc + ((int64_t)b * p.Lq + q) * p.ld_dq + h * kD + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                         "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                         "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+    }
+    // accumulated dV / dK for key row k0 + r
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int key = k0 + r;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      bf16* dst = (which == 0 ? p.dv : p.dk) + ((int64_t)b * p.Lk + key) * (which == 0 ? p.ld_dv : p.ld_dk) + h * kD;
+      const uint32_t t = (which == 0 ? t_dv : t_dk) + lane_base;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t + c * 32, v);
+        tmem_ld_wait();
+        if (key < p.Lk) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = __uint_as_float(v[g * 8 + j]);
+            *reinterpret_cast<bf16x8*>(dst + c * 32 + g * 8) = pack8(t8);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+__global__ void cast2d_f32_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
+                                          int64_t rows, int cols8) {
+  const int64_t total = rows * cols8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols8;
+    int c0 = (int)(i - r * cols8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x + r * ldx + c0);
+    const float4 c = *reinterpret_cast<const float4*>(x + r * ldx + c0 + 4);
+    float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    *reinterpret_cast<bf16x8*>(y + r * ldy + c0) = pack8(f);
+  }
+}
+
+}  // namespace b200
+
+// q, k, v, out, dout: bf16 matrices (head h = columns [64h, 64h+64)); lse from the forward; dq/dk/dv: bf16 outputs.
+// workspace: fp32 [B*H*Lq (delta) + B*Lq*H*64 (dq accumulator)], caller provided.
+extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                     const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                     void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                     float* workspace, int batch, int heads, int lq, int lk, float scale,
+                                     b200pdm_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!q || !k || !v || !out || !dout || !lse || !dq || !dk || !dv || !workspace) return B200PDM_ERR_ARG;
+  if (lddq % 8 || lddk % 8 || lddv % 8) return B200PDM_ERR_ARG;
+  float* delta = workspace;
+  float* dq_acc = workspace + (((int64_t)batch * heads * lq + 3) / 4) * 4;
+  const int64_t ld_acc = (int64_t)heads * 64;
+  const int64_t rows = (int64_t)batch * lq * heads;
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dout), lddo,
+                                                                   reinterpret_cast<const bf16*>(out), ldo, delta,
+                                                                   batch, heads, lq);
+  if (cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)batch * lq * ld_acc, stream) != cudaSuccess)
+    return B200PDM_ERR_CUDA;
+  CUtensorMap mq, mk, mv, mdo;
+  int rc = make_qkv_map(&mq, q, ldq, batch, heads, lq);
+  if (rc) return rc;
+  rc = make_qkv_map(&mk, k, ldk, batch, heads, lk);
+  if (rc) return rc;
+  rc = make_qkv_map(&mv, v, ldv, batch, heads, lk);
+  if (rc) return rc;
+  rc = make_qkv_map(&mdo, dout, lddo, batch, heads, lq);
+  if (rc) return rc;
+  AttnBwdParams p;
+  p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nq = (lq + kQ - 1) / kQ;
+  p.scale = scale, p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse, p.delta = delta, p.dq_acc = dq_acc, p.ld_dq = ld_acc;
+  p.dk = reinterpret_cast<bf16*>(dk), p.ld_dk = lddk, p.dv = reinterpret_cast<bf16*>(dv), p.ld_dv = lddv;
+  const size_t smem = 10 * kTileBytes + 256;
+  cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_err("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return B200PDM_ERR_CUDA;
+  }
+  dim3 grid((lk + kKV - 1) / kKV, heads, batch);
+  attn_bwd_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mk, mv, mdo, p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_err("attention_bwd launch: %s", cudaGetErrorString(e));
+    return B200PDM_ERR_CUDA;
+  }
+  const int64_t nrow = (int64_t)batch * lq;
+  const int cols8 = heads * 8;
+  int64_t blocks = (nrow * cols8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast2d_f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(dq_acc, ld_acc, reinterpret_cast<bf16*>(dq), lddq, nrow,
+                                                            cols8);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return B200PDM_ERR_CUDA;
+  g_launches += 4;
+  return B200PDM_OK;
+}

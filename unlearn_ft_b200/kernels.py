@@ -240,6 +240,17 @@ def attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=None, want_lse=False):
     return out, lse
 
 
+def attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, B, heads, Lq, Lk, scale):
+    """Fused attention backward; dq/dk/dv are bf16 output views (column slices allowed)."""
+    n_delta = (B * heads * Lq + 3) // 4 * 4
+    ws = torch.empty(n_delta + B * Lq * heads * 64, device=q.device, dtype=F32)
+    check(_lib.lib().b200pdm_attention_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                           v.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0),
+                                           lse.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0),
+                                           dv.data_ptr(), dv.stride(0), ws.data_ptr(), B, heads, Lq, Lk, scale,
+                                           _stream()), "attention_bwd")
+
+
 def colsum(x, out):
     """out[n] (fp32) += sum_m x[m, n]."""
     _chk2d(x, "x")

@@ -298,14 +298,25 @@ def attention(q, k, v, B, heads, Lq, Lk, need_bwd, out=None):
     """softmax(q k^T / 8) v per (sample, head), head_dim 64, no mask (reference blocks.py:275-277).
 
     q: [B*Lq, >=heads*64] view, k/v: [B*Lk, ...] views (column slices of fused projection outputs are fine).
-    Unfused first version: scores in fp32 -> row softmax -> bf16 probabilities -> PV, all on the tcgen05 GEMM core.
-    bwd(do) -> (dq, dk, dv) written into a fresh [B*L, heads*64] buffers (or into `dqkv_out` column slices).
+    Forward and backward are the fused tcgen05 flash-style kernels (csrc/attention.cu): scores and probabilities
+    never reach HBM; the backward recomputes them per tile from q, k and the saved log-sum-exp.
+    bwd(do, dq, dk, dv) writes the gradients into the given bf16 views.
     """
+    scale = 64 ** -0.5
+    o, lse = K.attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=out, want_lse=need_bwd)
+    if not need_bwd:
+        return o, None
+
+    def bwd(do, dq, dk, dv):
+        K.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, heads, Lq, Lk, scale)
+
+    return o, bwd
+
+
+def attention_unfused(q, k, v, B, heads, Lq, Lk, need_bwd, out=None):
+    """First-version attention kept for A/B checks: batched QK^T (fp32 scores) -> row softmax -> PV on the GEMM core."""
     D = 64
     scale = D ** -0.5
-    if not need_bwd:   # forward-only (teacher / sampling): fused flash-style kernel, scores never leave the SM
-        o, _ = K.attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=out)
-        return o, None
     Lkp = K.round8(Lk)
     dev = q.device
     ldq, ldk, ldv = q.stride(0), k.stride(0), v.stride(0)
