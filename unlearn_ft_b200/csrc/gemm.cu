@@ -87,6 +87,25 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
   return B200PDM_OK;
 }
 
+// Unswizzled 2-D bf16 map over an [rows, cols] matrix (pitch ld) with a [128 rows x 32 cols] box: epilogue TMA store
+// of output chunks and TMA load of residual chunks (out-of-range rows / columns are clipped / zero-filled).
+static int make_map_epilogue(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return B200PDM_ERR_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t bx[2] = {32, 128}, es[2] = {1, 1};
+  if ((gstr[0] % 16) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return B200PDM_ERR_ARG;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err("cuTensorMapEncodeTiled (epilogue map) failed");
+    return B200PDM_ERR_DRIVER;
+  }
+  return B200PDM_OK;
+}
+
 int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
                     const uint32_t* box) {
   return make_map(map, ptr, rank, dims, strides_el, box, nullptr);
@@ -114,6 +133,8 @@ struct GemmDev {
   int tiles_m, tiles_n_per_group, Z, splits;
   int kblocks, kb_per_split;
   int block_n, stages;
+  int cluster;       // CTAs per cluster (1, 2, 4): B tile loaded once per cluster and multicast
+  int tiles_m_super; // ceil(tiles_m / cluster)
   uint32_t idesc;
   // epilogue
   void* out;
@@ -127,7 +148,22 @@ struct GemmDev {
   int64_t ldr, rbs1, rbs2;
   float alpha;
   int accumulate;
+  long long* dbg;  // optional per-role wait-cycle counters (diagnostics)
+  int epi_tma;     // bf16 output through smem staging + TMA store (coalesced, asynchronous)
+  int res_tma;     // residual chunks prefetched with TMA
 };
+
+#define DBG_WAIT(slot, stmt)                                              \
+  do {                                                                    \
+    if (p.dbg && blockIdx.x == 0) {                                       \
+      long long t0__ = clock64();                                         \
+      stmt;                                                               \
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (slot)),    \
+                static_cast<unsigned long long>(clock64() - t0__));       \
+    } else {                                                              \
+      stmt;                                                               \
+    }                                                                     \
+  } while (0)
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
@@ -136,6 +172,7 @@ constexpr int kAtomBytes = 64 * 64 * 2;              // one [64 k][64 mn] MN-maj
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kThreads = 192;
+constexpr int kEpiBufBytes = 128 * 32 * 2;  // one [128 rows x 32 cols] bf16 staging chunk
 
 __device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int m_tile,
                                        int kb, int z) {
@@ -171,25 +208,47 @@ __device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, 
   }
 }
 
+// With cluster > 1 each CTA fetches only its 1/cluster slice of the B tile (rows [rank*block_n/cluster, ...) for
+// K-major tiles, whole 64-wide atoms for MN-major tiles) and multicasts it to every CTA of the cluster.
 __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int grp,
-                                       int nt, int block_n, int kb, int z) {
+                                       int nt, int block_n, int kb, int z, int cluster, int rank) {
   const int n0 = nt * block_n;
+  const uint16_t mask = static_cast<uint16_t>((1u << cluster) - 1);
+  const int rows = block_n / cluster;             // K-major slice
+  const int atoms = (block_n / 64) / cluster;     // MN-major slice (host guarantees divisibility when cluster > 1)
   switch (op.mode) {
     case B200PDM_OP_K2D:
-      tma_load_4d(dst, map, bar, kb * kBlockK, n0, z % op.Z1, z / op.Z1);
+      if (cluster == 1)
+        tma_load_4d(dst, map, bar, kb * kBlockK, n0, z % op.Z1, z / op.Z1);
+      else
+        tma_load_4d_mc(dst + rank * rows * 128, map, bar, kb * kBlockK, n0 + rank * rows, z % op.Z1, z / op.Z1, mask);
       break;
     case B200PDM_OP_MN2D:
-      for (int j = 0; j < block_n / 64; ++j)
-        tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, kb * kBlockK, z % op.Z1, z / op.Z1);
+      if (cluster == 1) {
+        for (int j = 0; j < block_n / 64; ++j)
+          tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, kb * kBlockK, z % op.Z1, z / op.Z1);
+      } else {
+        for (int j = rank * atoms; j < (rank + 1) * atoms; ++j)
+          tma_load_4d_mc(dst + j * kAtomBytes, map, bar, n0 + 64 * j, kb * kBlockK, z % op.Z1, z / op.Z1, mask);
+      }
       break;
     case B200PDM_OP_CONV_W: {
       int tap = kb / op.cblks, cb = kb - tap * op.cblks;
-      tma_load_3d(dst, map, bar, cb * kBlockK, tap, n0);
+      if (cluster == 1)
+        tma_load_3d(dst, map, bar, cb * kBlockK, tap, n0);
+      else
+        tma_load_3d_mc(dst + rank * rows * 128, map, bar, cb * kBlockK, tap, n0 + rank * rows, mask);
       break;
     }
     case B200PDM_OP_CONV_WT: {
       int tap = kb / op.cblks, cb = kb - tap * op.cblks;
-      for (int j = 0; j < block_n / 64; ++j) tma_load_3d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK);
+      if (cluster == 1) {
+        for (int j = 0; j < block_n / 64; ++j)
+          tma_load_3d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK);
+      } else {
+        for (int j = rank * atoms; j < (rank + 1) * atoms; ++j)
+          tma_load_3d_mc(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK, mask);
+      }
       break;
     }
     case B200PDM_OP_CONV_ACT_MN: {
@@ -203,8 +262,14 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
       int rem = pix0 - b0 * op.HoWo;
       int h0 = rem / op.Wo;
       int w0 = rem - h0 * op.Wo;
-      for (int j = 0; j < block_n / 64; ++j)
-        tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, b0);
+      if (cluster == 1) {
+        for (int j = 0; j < block_n / 64; ++j)
+          tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, b0);
+      } else {
+        for (int j = rank * atoms; j < (rank + 1) * atoms; ++j)
+          tma_load_4d_mc(dst + j * kAtomBytes, map, bar, n0 + 64 * j, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, b0,
+                         mask);
+      }
       break;
     }
     default:
@@ -214,7 +279,8 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_b_bytes = p.block_n * 128;
@@ -225,22 +291,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_full = tempty_bar + 4;                          // [2]
+  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tempty_bar + 6) + 127) & ~uintptr_t(127));
+  uint8_t* sRes = sOut + 2 * kEpiBufBytes;                      // 2 x [128 rows][32 bf16] each
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.tiles_n_per_group * p.n_groups;
-  const int tiles_per_split = p.tiles_m * tiles_n * p.Z;
+  // "super tiles": one per cluster = `cluster` consecutive m-tiles sharing the same B tile
+  const int tiles_per_split = p.tiles_m_super * tiles_n * p.Z;
   const int total_tiles = tiles_per_split * p.splits;
+  const int cluster = p.cluster;
+  const int rank = cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = blockIdx.x / cluster, tile_step = gridDim.x / cluster;
+  const uint16_t cmask = static_cast<uint16_t>((1u << cluster) - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], cluster);   // every CTA of the cluster must have consumed the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
+      mbar_init(&res_full[i], 1);
     }
     fence_barrier_init();
   }
@@ -250,8 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_kernel0 = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -259,22 +336,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t tx_bytes = kStageABytes + stage_b_bytes;
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
         int split = t / tiles_per_split;
         int r = t - split * tiles_per_split;
-        int z = r / (p.tiles_m * tiles_n);
-        r -= z * (p.tiles_m * tiles_n);
-        int m_tile = r / tiles_n;
-        int n_tile = r - m_tile * tiles_n;
+        int z = r / (p.tiles_m_super * tiles_n);
+        r -= z * (p.tiles_m_super * tiles_n);
+        int m_tile = (r / tiles_n) * cluster + rank;
+        int n_tile = r % tiles_n;
         int grp = n_tile / p.tiles_n_per_group;
         int nt = n_tile - grp * p.tiles_n_per_group;
         int kb0 = split * p.kb_per_split;
         int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          DBG_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           load_a(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
-          load_b(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z);
+          load_b(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z, cluster, rank);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -289,15 +366,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
         int split = t / tiles_per_split;
         int kb0 = split * p.kb_per_split;
         int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        DBG_WAIT(2, mbar_wait(&tempty_bar[acc], acc_phase ^ 1));
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          DBG_WAIT(1, mbar_wait(&full_bar[stage], phase));
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * kStageABytes);
           const uint32_t b_addr = smem_u32(sB + stage * stage_b_bytes);
@@ -314,7 +391,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (cluster == 1)
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          else
+            umma_commit_mc(&empty_bar[stage], cmask);  // ... in every CTA of the cluster (their TMAs write here too)
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -330,26 +410,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int erow = q * 32 + lane;            // row of the tile this thread owns (== TMEM lane)
+    const bool leader = threadIdx.x == 64;     // first epilogue thread: issues TMA stores / residual prefetches
+    uint32_t chunk_ctr = 0;                    // staged chunks so far (buffer parity + residual barrier phase)
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = first_tile; t < total_tiles; t += tile_step) {
       int split = t / tiles_per_split;
       int r = t - split * tiles_per_split;
-      int z = r / (p.tiles_m * tiles_n);
-      r -= z * (p.tiles_m * tiles_n);
-      int m_tile = r / tiles_n;
-      int n_tile = r - m_tile * tiles_n;
+      int z = r / (p.tiles_m_super * tiles_n);
+      r -= z * (p.tiles_m_super * tiles_n);
+      int m_tile = (r / tiles_n) * cluster + rank;
+      int n_tile = r % tiles_n;
       int grp = n_tile / p.tiles_n_per_group;
       int nt = n_tile - grp * p.tiles_n_per_group;
       const int z1 = z % p.a.Z1, z2 = z / p.a.Z1;
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-
-      const int row = m_tile * kBlockM + q * 32 + lane;
+      const int row = m_tile * kBlockM + erow;
       const bool row_ok = row < p.M;
       const int col_base = nt * p.block_n;  // within group
       const int n_valid = p.n_per_group - col_base;
+      const int n_cols = min(p.block_n, n_valid);               // valid columns of this tile
+      const int n_staged = p.epi_tma ? (min(n_cols + 31, p.block_n) / 32) : 0;  // full 32-wide chunks via TMA store
+
+      // residual prefetch for the first two staged chunks (before the accumulator is even ready)
+      if (p.res_tma && leader) {
+        for (int c = 0; c < min(2, n_staged); ++c) {
+          const uint32_t b = (chunk_ctr + c) & 1;
+          mbar_expect_tx(&res_full[b], kEpiBufBytes);
+          tma_load_2d(sRes + b * kEpiBufBytes, &tma_res, &res_full[b], col_base + c * 32, m_tile * kBlockM);
+        }
+      }
+
+      if (threadIdx.x == 64) {
+        DBG_WAIT(3, mbar_wait(&tfull_bar[acc], acc_phase));
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+      }
+      tc_fence_after();
+      const long long t_epi0 = (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) ? clock64() : 0;
+
       const int64_t out_off =
           z1 * p.obs1 + z2 * p.obs2 + static_cast<int64_t>(row) * p.ldo + grp * p.out_group_stride + col_base;
       const bf16* res_row =
@@ -359,7 +458,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const float* bias = p.bias ? p.bias + col_base : nullptr;
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = 0; c0 < n_cols; c0 += 32) {
         uint32_t v[32];
         if (p.block_n - c0 >= 32) {
           tmem_ld_32x32(taddr + c0, v);
@@ -373,42 +472,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         tmem_ld_wait();
         const int nv = min(min(32, p.block_n - c0), n_valid - c0);  // valid columns in this chunk
-        if (row_ok && nv > 0) {
-          float f[32];
+        const bool staged = (c0 >> 5) < n_staged;                   // else: direct (masked) stores
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-          if (bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) f[j] += __ldg(bias + c0 + j);
-          }
-          if (rb_row) {
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) f[j] += __ldg(bias + c0 + j);
+        }
+        if (rb_row && row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) f[j] += __ldg(rb_row + c0 + j);
-          }
-          if (res_row) {
-            if (nv == 32 && ((reinterpret_cast<uintptr_t>(res_row + c0) & 15) == 0)) {
+          for (int j = 0; j < 32; ++j)
+            if (j < nv) f[j] += __ldg(rb_row + c0 + j);
+        }
+        if (staged) {
+          const uint32_t b = chunk_ctr & 1;
+          if (p.res_tma) {
+            mbar_wait(&res_full[b], (chunk_ctr >> 1) & 1);
+            const uint4* rp = reinterpret_cast<const uint4*>(sRes + b * kEpiBufBytes + erow * 64);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                bf16x8 rv = *reinterpret_cast<const bf16x8*>(res_row + c0 + g * 8);
-                float rf[8];
-                unpack8(rv, rf);
+            for (int g = 0; g < 4; ++g) {
+              const int gg = g;   // (a 4-way bank conflict on 4 accesses per chunk is cheaper than dynamic indexing)
+              uint4 u = rp[gg];
+              bf16x8 rv = *reinterpret_cast<bf16x8*>(&u);
+              float rf[8];
+              unpack8(rv, rf);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[g * 8 + j] += rf[j];
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
+              for (int j = 0; j < 8; ++j) f[gg * 8 + j] += rf[j];
             }
+          } else if (res_row && row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(sOut + b * kEpiBufBytes + erow * 64);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int gg = g;
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t8[j] = f[gg * 8 + j];
+            bf16x8 pk = pack8(t8);
+            op[gg] = *reinterpret_cast<uint4*>(&pk);
+          }
+          fence_proxy_async();
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // earlier stores left smem
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (leader) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tma_out)),
+                         "r"(smem_u32(sOut + b * kEpiBufBytes)), "r"(col_base + c0), "r"(m_tile * kBlockM)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            const int cn = (c0 >> 5) + 2;   // residual chunk that will reuse this buffer
+            if (p.res_tma && cn < n_staged) {
+              mbar_expect_tx(&res_full[b], kEpiBufBytes);
+              tma_load_2d(sRes + b * kEpiBufBytes, &tma_res, &res_full[b], col_base + cn * 32, m_tile * kBlockM);
+            }
+          }
+          ++chunk_ctr;
+        } else if (row_ok && nv > 0) {
+          if (res_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
           }
           if (p.out_fp32) {
             float* o = reinterpret_cast<float*>(p.out) + out_off + c0;
             if (p.accumulate) {
+              if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) atomicAdd(o + j, f[j]);
+                for (int g = 0; g < 8; ++g)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + g * 4), "f"(f[g * 4]),
+                               "f"(f[g * 4 + 1]), "f"(f[g * 4 + 2]), "f"(f[g * 4 + 3])
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) atomicAdd(o + j, f[j]);
+              }
             } else if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
               for (int g = 0; g < 8; ++g)
@@ -438,16 +581,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64)
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), static_cast<unsigned long long>(clock64() - t_epi0));
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output stores are complete
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[4] += clock64() - t_kernel0;
+  if (cluster > 1) cluster_sync_all();   // no CTA exits while a peer may still arrive on / multicast into its smem
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -505,14 +653,14 @@ static int pick_block_n(int64_t n, bool mn_major) {
 }
 
 static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, CUtensorMap* map, OpDev* dev,
-                             int64_t mn_extent, int64_t k_extent, int Z1, int Z2) {
+                             int64_t mn_extent, int64_t k_extent, int Z1, int Z2, int cluster = 1) {
   memset(dev, 0, sizeof(*dev));
   dev->mode = op.mode;
   dev->Z1 = Z1 > 0 ? Z1 : 1;
   dev->taps = op.taps > 0 ? op.taps : 1;
   dev->stride = op.stride > 0 ? op.stride : 1;
   dev->flip = op.flip;
-  const int rows = is_a ? kBlockM : block_n;
+  const int rows = is_a ? kBlockM : block_n / cluster;   // K-major B: each CTA loads (and multicasts) its slice
   uint64_t dims[5], str[5];
   uint32_t box[5], es[5] = {1, 1, 1, 1, 1};
   switch (op.mode) {
@@ -637,14 +785,30 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     return B200PDM_ERR_ARG;
   }
 
+  // cluster size: share the B tile among `cluster` m-tiles (TMA multicast) to cut L2 -> SM traffic
+  static int env_cluster = -1;
+  if (env_cluster < 0) {
+    const char* e = getenv("B200PDM_CLUSTER");
+    env_cluster = e ? atoi(e) : 2;
+    if (env_cluster != 1 && env_cluster != 2 && env_cluster != 4) env_cluster = 2;
+  }
+  int cluster = env_cluster;
+  while (cluster > 1) {
+    const bool div_ok = b_mn ? ((block_n / 64) % cluster == 0) : ((block_n / cluster) % 8 == 0);
+    if (div_ok && p.tiles_m >= cluster) break;
+    cluster >>= 1;
+  }
+  p.cluster = cluster;
+  p.tiles_m_super = cdiv(p.tiles_m, cluster);
+
   CUtensorMap map_a, map_b;
   int rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2);
   if (rc) return rc;
-  rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->N, d->K, Z1, Z2);
+  rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->N, d->K, Z1, Z2, cluster);
   if (rc) return rc;
 
   const int stage_bytes = kStageABytes + block_n * 128;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (193 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
@@ -665,10 +829,38 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   p.rbs2 = d->rbs2;
   p.alpha = d->alpha;
   p.accumulate = d->accumulate;
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = getenv("B200PDM_GEMM_DBG") ? 1 : 0;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), stream);
+  }
+  p.dbg = dbg_on ? dbg_buf : nullptr;
 
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16;
-  const long total_tiles = (long)p.tiles_m * p.tiles_n_per_group * p.n_groups * p.Z * p.splits;
-  int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + 16 + 128 + 4 * kEpiBufBytes;
+  // epilogue through TMA store (+ TMA residual prefetch) whenever the output is a plain bf16 matrix
+  CUtensorMap map_out, map_res;
+  memset(&map_out, 0, sizeof(map_out));
+  memset(&map_res, 0, sizeof(map_res));
+  p.epi_tma = (!d->out_fp32 && !d->accumulate && p.Z == 1 && p.n_groups == 1 && (d->ldo % 8 == 0) &&
+               ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0)) ? 1 : 0;
+  static int env_epi = -1;
+  if (env_epi < 0) env_epi = getenv("B200PDM_NO_EPI_TMA") ? 0 : 1;
+  if (!env_epi) p.epi_tma = 0;
+  p.res_tma = 0;
+  if (p.epi_tma) {
+    rc = make_map_epilogue(&map_out, d->out, d->M, p.n_per_group, d->ldo);
+    if (rc) return rc;
+    if (d->residual && (d->ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0)) {
+      rc = make_map_epilogue(&map_res, d->residual, d->M, p.n_per_group, d->ldr);
+      if (rc) return rc;
+      p.res_tma = 1;
+    }
+  }
+  const long total_tiles = (long)p.tiles_m_super * p.tiles_n_per_group * p.n_groups * p.Z * p.splits;  // per cluster
+  const int max_clusters = num_sms() / cluster;
+  int grid = static_cast<int>(total_tiles < max_clusters ? total_tiles : max_clusters) * cluster;
 
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -681,7 +873,18 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       cudaEventCreate(&t0), cudaEventCreate(&t1);
       cudaEventRecord(t0, stream);
     }
-    kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, p);
+    if (cluster == 1) {
+      kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_out, map_res, p);
+    } else {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr, cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_out, map_res, p);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_err("gemm launch: %s", cudaGetErrorString(e));
@@ -695,8 +898,17 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       cudaEventElapsedTime(&ms, t0, t1);
       char key[256];
       const double kk = (double)kblocks * 64;
-      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d split=%d tiles=%ld grid=%d stages=%d", d->a.mode,
-               d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.splits, total_tiles, grid, stages);
+      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d split=%d tiles=%ld grid=%d stages=%d cl=%d", d->a.mode,
+               d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.splits, total_tiles, grid, stages,
+               cluster);
+      if (p.dbg) {
+        long long h[8];
+        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        int tiles_cta0 = (int)((total_tiles + grid / cluster - 1) / (grid / cluster));
+        fprintf(stderr, "[gemm dbg] %s | cta0: total=%lld prod_wait_empty=%lld mma_wait_full=%lld mma_wait_tempty=%lld "
+                "epi_wait_tfull=%lld epi_busy=%lld (~%d tiles, %d kblocks)\n", key, h[4], h[0], h[1], h[2], h[3], h[5],
+                tiles_cta0, p.kb_per_split);
+      }
       TraceRow& r = g_trace[key];
       r.count++, r.ms += ms;
       r.flops += 2.0 * (double)d->M * p.n_per_group * p.n_groups * kk * p.Z;
