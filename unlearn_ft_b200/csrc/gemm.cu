@@ -133,6 +133,7 @@ struct GemmDev {
   int tiles_m, tiles_n_per_group, Z, splits;
   int kblocks, kb_per_split;
   int block_n, stages;
+  int pair;          // 1: cta_group::2 -- one M=256 MMA per CTA pair, each CTA stages its 128 A rows and HALF of B
   int cluster;       // CTAs per cluster (1, 2, 4): B tile loaded once per cluster and multicast
   int tiles_m_super; // ceil(tiles_m / cluster)
   uint32_t idesc;
@@ -174,15 +175,31 @@ constexpr int kAccStride = 256;  // TMEM columns between the two accumulator sta
 constexpr int kThreads = 192;
 constexpr int kEpiBufBytes = 128 * 32 * 2;  // one [128 rows x 32 cols] bf16 staging chunk
 
+template <bool PAIR>
+__device__ __forceinline__ void ld4(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  if (PAIR)
+    tma_load_4d_2sm(dst, map, bar, c0, c1, c2, c3);
+  else
+    tma_load_4d(dst, map, bar, c0, c1, c2, c3);
+}
+template <bool PAIR>
+__device__ __forceinline__ void ld3(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  if (PAIR)
+    tma_load_3d_2sm(dst, map, bar, c0, c1, c2);
+  else
+    tma_load_3d(dst, map, bar, c0, c1, c2);
+}
+
+template <bool PAIR>
 __device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int m_tile,
                                        int kb, int z) {
   switch (op.mode) {
     case B200PDM_OP_K2D:
-      tma_load_4d(dst, map, bar, kb * kBlockK, m_tile * kBlockM, z % op.Z1, z / op.Z1);
+      ld4<PAIR>(dst, map, bar, kb * kBlockK, m_tile * kBlockM, z % op.Z1, z / op.Z1);
       break;
     case B200PDM_OP_MN2D:
-      tma_load_4d(dst, map, bar, m_tile * kBlockM, kb * kBlockK, z % op.Z1, z / op.Z1);
-      tma_load_4d(dst + kAtomBytes, map, bar, m_tile * kBlockM + 64, kb * kBlockK, z % op.Z1, z / op.Z1);
+      ld4<PAIR>(dst, map, bar, m_tile * kBlockM, kb * kBlockK, z % op.Z1, z / op.Z1);
+      ld4<PAIR>(dst + kAtomBytes, map, bar, m_tile * kBlockM + 64, kb * kBlockK, z % op.Z1, z / op.Z1);
       break;
     case B200PDM_OP_CONV_ACT: {
       int tap = kb / op.cblks, cb = kb - tap * op.cblks;
@@ -200,7 +217,54 @@ __device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, 
       int rem = pix0 - n0 * op.HoWo;
       int h0 = rem / op.Wo;
       int w0 = rem - h0 * op.Wo;
-      tma_load_4d(dst, map, bar, cb * kBlockK, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, n0);
+      ld4<PAIR>(dst, map, bar, cb * kBlockK, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, n0);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// cta_group::2: CTA `rank` of the pair stages only its half of the B tile (rows / atoms [rank*half, (rank+1)*half)) at
+// the start of its own stage buffer.
+__device__ __forceinline__ void load_b_pair(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int grp,
+                                            int nt, int block_n, int kb, int z, int rank) {
+  const int n0 = nt * block_n;
+  const int rows = block_n / 2;
+  const int atoms = (block_n / 64) / 2;
+  switch (op.mode) {
+    case B200PDM_OP_K2D:
+      tma_load_4d_2sm(dst, map, bar, kb * kBlockK, n0 + rank * rows, z % op.Z1, z / op.Z1);
+      break;
+    case B200PDM_OP_MN2D:
+      for (int j = 0; j < atoms; ++j)
+        tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), kb * kBlockK, z % op.Z1, z / op.Z1);
+      break;
+    case B200PDM_OP_CONV_W: {
+      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      tma_load_3d_2sm(dst, map, bar, cb * kBlockK, tap, n0 + rank * rows);
+      break;
+    }
+    case B200PDM_OP_CONV_WT: {
+      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      for (int j = 0; j < atoms; ++j)
+        tma_load_3d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), tap, cb * kBlockK);
+      break;
+    }
+    case B200PDM_OP_CONV_ACT_MN: {
+      int kh = 1, kw = 1;
+      if (op.taps == 9) {
+        kh = grp / 3;
+        kw = grp - kh * 3;
+      }
+      int pix0 = kb * kBlockK;
+      int b0 = pix0 / op.HoWo;
+      int rem = pix0 - b0 * op.HoWo;
+      int h0 = rem / op.Wo;
+      int w0 = rem - h0 * op.Wo;
+      for (int j = 0; j < atoms; ++j)
+        tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), w0 * op.stride + kw - 1,
+                        h0 * op.stride + kh - 1, b0);
       break;
     }
     default:
@@ -277,13 +341,13 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
   }
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_b_bytes = p.block_n * 128;
+  const int stage_b_bytes = (PAIR ? p.block_n / 2 : p.block_n) * 128;
   uint8_t* sA = smem;
   uint8_t* sB = smem + p.stages * kStageABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.stages * stage_b_bytes);
@@ -300,7 +364,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // "super tiles": one per cluster = `cluster` consecutive m-tiles sharing the same B tile
   const int tiles_per_split = p.tiles_m_super * tiles_n * p.Z;
   const int total_tiles = tiles_per_split * p.splits;
-  const int cluster = p.cluster;
+  constexpr bool pair = PAIR;   // compile-time: kernels containing cta_group::2 instructions must be launched as pairs
+  const int cluster = pair ? 2 : p.cluster;       // m-tiles per super tile == CTAs per cluster
+  const int mcast = pair ? 1 : p.cluster;          // TMA multicast width (pair mode does not multicast)
   const int rank = cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int first_tile = blockIdx.x / cluster, tile_step = gridDim.x / cluster;
   const uint16_t cmask = static_cast<uint16_t>((1u << cluster) - 1);
@@ -310,18 +376,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], cluster);   // every CTA of the cluster must have consumed the stage
+      mbar_init(&empty_bar[i], mcast);     // every CTA multicasting into this stage must have consumed it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], pair ? 8 : 4);   // pair: the leader's MMA waits for both CTAs' epilogue warps
       mbar_init(&res_full[i], 1);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (pair) {
+      tmem_alloc_2sm(tmem_slot, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -349,9 +420,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           DBG_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
-          load_a(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
-          load_b(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z, cluster, rank);
+          if (pair) {
+            // both CTAs' loads complete_tx on the LEADER's full barrier, which expects the bytes of the whole pair
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
+            load_a<true>(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
+            load_b_pair(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z, rank);
+          } else {
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            load_a<false>(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
+            load_b(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z, mcast, rank);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -360,8 +438,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && !(pair && rank != 0)) {
+      // ===================== MMA issuer (pair mode: leader CTA only) =====================
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -389,9 +467,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               bdesc = make_smem_desc_sw128(b_addr + k * 2048, kAtomBytes, 1024);
             else
               bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (pair)
+              umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (cluster == 1)
+          if (pair)
+            umma_commit_2sm_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
+          else if (cluster == 1)
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           else
             umma_commit_mc(&empty_bar[stage], cmask);  // ... in every CTA of the cluster (their TMAs write here too)
@@ -400,7 +483,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (pair)
+          umma_commit_2sm_mc(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
+        else
+          umma_commit(&tfull_bar[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -583,7 +669,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       __syncwarp();
       if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64)
         atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), static_cast<unsigned long long>(clock64() - t_epi0));
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (pair && rank != 0)
+          mbar_arrive_remote(&tempty_bar[acc], 0);   // tell the leader CTA's MMA thread
+        else
+          mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -598,7 +689,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (cluster > 1) cluster_sync_all();   // no CTA exits while a peer may still arrive on / multicast into its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (pair)
+      tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else
+      tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -789,8 +883,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   static int env_cluster = -1;
   if (env_cluster < 0) {
     const char* e = getenv("B200PDM_CLUSTER");
-    env_cluster = e ? atoi(e) : 2;
-    if (env_cluster != 1 && env_cluster != 2 && env_cluster != 4) env_cluster = 2;
+    env_cluster = e ? atoi(e) : 1;
+    if (env_cluster != 1 && env_cluster != 2 && env_cluster != 4) env_cluster = 1;
   }
   int cluster = env_cluster;
   while (cluster > 1) {
@@ -798,7 +892,15 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     if (div_ok && p.tiles_m >= cluster) break;
     cluster >>= 1;
   }
-  p.cluster = cluster;
+  // cta_group::2 pairs: halve the B bytes each SM has to receive per MMA (the L2->SM path is the limiter)
+  static int env_pair = -1;
+  if (env_pair < 0) env_pair = getenv("B200PDM_NO_PAIR") ? 0 : 1;
+  p.pair = 0;
+  if (env_pair && p.tiles_m >= 2 && (b_mn ? ((block_n / 64) % 2 == 0) : (block_n % 16 == 0))) {
+    p.pair = 1;
+    cluster = 2;
+  }
+  p.cluster = p.pair ? 1 : cluster;
   p.tiles_m_super = cdiv(p.tiles_m, cluster);
 
   CUtensorMap map_a, map_b;
@@ -807,12 +909,12 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->N, d->K, Z1, Z2, cluster);
   if (rc) return rc;
 
-  const int stage_bytes = kStageABytes + block_n * 128;
+  const int stage_bytes = kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
   int stages = (193 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  p.idesc = make_idesc_bf16(block_n, a_mn ? 1 : 0, b_mn ? 1 : 0);
+  p.idesc = make_idesc_bf16(block_n, a_mn ? 1 : 0, b_mn ? 1 : 0, p.pair ? 256 : 128);
 
   p.out = d->out;
   p.out_fp32 = d->out_fp32;
@@ -916,10 +1018,16 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     }
     return B200PDM_OK;
   };
-  if (!a_mn && !b_mn) return launch(gemm_kernel<0, 0>);
-  if (!a_mn && b_mn) return launch(gemm_kernel<0, 1>);
-  if (a_mn && !b_mn) return launch(gemm_kernel<1, 0>);
-  return launch(gemm_kernel<1, 1>);
+  if (p.pair) {
+    if (!a_mn && !b_mn) return launch(gemm_kernel<0, 0, true>);
+    if (!a_mn && b_mn) return launch(gemm_kernel<0, 1, true>);
+    if (a_mn && !b_mn) return launch(gemm_kernel<1, 0, true>);
+    return launch(gemm_kernel<1, 1, true>);
+  }
+  if (!a_mn && !b_mn) return launch(gemm_kernel<0, 0, false>);
+  if (!a_mn && b_mn) return launch(gemm_kernel<0, 1, false>);
+  if (a_mn && !b_mn) return launch(gemm_kernel<1, 0, false>);
+  return launch(gemm_kernel<1, 1, false>);
 }
 
 }  // namespace b200
