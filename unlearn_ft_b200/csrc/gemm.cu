@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "../../include/b200pdm.h"
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -729,18 +730,49 @@ static bool pixel_box(int pixels, int Ho, int Wo, int* bw, int* bh, int* bn) {
   return true;
 }
 
-static int pick_block_n(int64_t n, bool mn_major) {
-  const int g = mn_major ? 64 : 16;
-  int64_t n_pad = (n + g - 1) / g * g;
-  if (n_pad <= 256) return static_cast<int>(n_pad);
-  int best = 256;
-  int64_t best_cost = INT64_MAX;
-  for (int bn = 256; bn >= 128; bn -= g) {
-    int64_t tiles = (n + bn - 1) / bn;
-    int64_t cost = tiles * bn;  // padded MMA columns
-    if (cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+static int pair_enabled() {
+  static int env_pair = -1;
+  if (env_pair < 0) env_pair = getenv("B200PDM_NO_PAIR") ? 0 : 1;
+  return env_pair;
+}
+
+// Tile plan: block_n, split-K factor and pair mode chosen with a small cost model (cycles per CTA slot):
+//   per k-block   max(MMA issue = 2*bn cycles, smem fill = bytes / ~36 B per cycle per SM  [measured L2->SM limit])
+//   per tile      k-blocks * that + fixed pipeline overhead, epilogue overlapped unless it dominates
+//   total         waves over the 148 (or 74 pair) slots, + a finalize pass when a bf16 output is split along K
+struct Plan {
+  int bn = 0, splits = 1, pair = 0;
+  double cost = 1e30;
+};
+static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, int kblocks, bool can_split,
+                      bool split_needs_finalize, int fixed_bn) {
+  const int g = b_mn ? 64 : 16;
+  const int n_pad = static_cast<int>((n + g - 1) / g * g);
+  static const int split_cands[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
+  Plan best;
+  for (int bn = g; bn <= 256; bn += g) {
+    if (fixed_bn > 0 && bn != fixed_bn) continue;
+    if (fixed_bn <= 0 && bn > n_pad) break;
+    if (fixed_bn <= 0 && bn < 64 && bn != n_pad) continue;   // tiny tiles only when N itself is tiny
+    const int tiles_n = static_cast<int>((n + bn - 1) / bn) * n_groups;
+    const int pair = (pair_enabled() && tiles_m >= 2 && (b_mn ? ((bn / 64) % 2 == 0) : true)) ? 1 : 0;
+    const int cs = pair ? 2 : 1;
+    const int slots = 148 / cs;
+    const long base_tiles = (long)((tiles_m + cs - 1) / cs) * tiles_n * Z;
+    const double bytes = 16384.0 + (pair ? bn / 2 : bn) * 128.0;
+    const double kcyc = std::max(2.0 * bn, bytes / 36.0);
+    const double epi = 450.0 * ((bn + 31) / 32);
+    for (int s : split_cands) {
+      if (s > 1 && !can_split) break;
+      if (s > 1 && kblocks / s < 8) break;
+      const int kb = (kblocks + s - 1) / s;
+      const long tiles = base_tiles * s;
+      const long waves = (tiles + slots - 1) / slots;
+      double tile_cyc = std::max(kb * kcyc, epi) + 2500.0;
+      if (s > 1) tile_cyc += epi;   // atomics epilogue is slower and less overlapped
+      double cost = waves * tile_cyc;
+      if (s > 1 && split_needs_finalize) cost += 14000.0;
+      if (cost < best.cost) best.bn = bn, best.splits = s, best.pair = pair, best.cost = cost;
     }
   }
   return best;
@@ -809,6 +841,70 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
   return B200PDM_ERR_ARG;
 }
 
+// Library-owned fp32 scratch for split-K partial sums (lazily grown; the only device allocation the library makes).
+static float* scratch_f32(size_t elems, cudaStream_t stream) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (elems > cap) {
+    if (buf) {
+      cudaStreamSynchronize(stream);
+      cudaFree(buf);
+    }
+    size_t want = elems < (8u << 20) ? (8u << 20) : elems;
+    if (cudaMalloc(&buf, want * sizeof(float)) != cudaSuccess) {
+      buf = nullptr, cap = 0;
+      set_err("split-K scratch allocation failed");
+      return nullptr;
+    }
+    cap = want;
+  }
+  if (cudaMemsetAsync(buf, 0, elems * sizeof(float), stream) != cudaSuccess) return nullptr;
+  return buf;
+}
+
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldws, void* __restrict__ out, int out_fp32,
+                                       int64_t ldo, const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                       int64_t ld_rowbias, int rows_per_group, const bf16* __restrict__ residual,
+                                       int64_t ldr, int64_t M, int N) {
+  const int nq = (N + 3) / 4;
+  const int64_t total = M * nq;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / nq;
+    const int n0 = (int)(i - m * nq) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(ws + m * ldws + n0);
+    float f[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + j;
+      if (n < N) {
+        if (bias) f[j] += bias[n];
+        if (rowbias) f[j] += rowbias[(m / rows_per_group) * ld_rowbias + n];
+        if (residual) f[j] += __bfloat162float(residual[m * ldr + n]);
+        if (out_fp32)
+          reinterpret_cast<float*>(out)[m * ldo + n] = f[j];
+        else
+          reinterpret_cast<bf16*>(out)[m * ldo + n] = __float2bfloat16(f[j]);
+      }
+    }
+  }
+}
+
+static int launch_finalize(const b200pdm_gemm_desc* d, const float* ws, int64_t ldws, cudaStream_t stream) {
+  const int64_t total = d->M * ((d->N + 3) / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(ws, ldws, d->out, d->out_fp32, d->ldo, d->bias, d->rowbias,
+                                                         d->ld_rowbias, d->rows_per_group > 0 ? d->rows_per_group : 1,
+                                                         reinterpret_cast<const bf16*>(d->residual), d->ldr, d->M,
+                                                         (int)d->N);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_err("split-K finalize launch failed");
+    return B200PDM_ERR_CUDA;
+  }
+  g_launches += 2;
+  return B200PDM_OK;
+}
+
 // Optional per-shape timing table (B200PDM_GEMM_TRACE=1): every launch is bracketed by events and synchronised, so it
 // serialises the stream -- diagnostics only, never enabled in bench.py.
 struct TraceRow {
@@ -822,6 +918,7 @@ static int trace_on() {
   return on;
 }
 
+static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream);
 static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   if (!d || !d->a.ptr || !d->b.ptr || !d->out) {
     set_err("gemm: null pointer");
@@ -843,13 +940,6 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     p.n_per_group = d->b.channels;
     p.out_group_stride = d->ldo / p.n_groups;  // dW row = [taps][I_ld]
   }
-  int block_n = d->block_n > 0 ? d->block_n : pick_block_n(p.n_per_group, b_mn);
-  if (block_n % 16 || block_n > 256 || block_n < 16 || (b_mn && block_n % 64)) {
-    set_err("gemm: bad block_n");
-    return B200PDM_ERR_ARG;
-  }
-  p.block_n = block_n;
-  p.tiles_n_per_group = cdiv(p.n_per_group, block_n);
   p.M = static_cast<int>(d->M);
   p.tiles_m = cdiv(d->M, kBlockM);
   p.Z = Z1 * Z2;
@@ -869,17 +959,45 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     return B200PDM_ERR_ARG;
   }
   p.kblocks = kblocks;
-  int splits = d->splits > 1 ? d->splits : 1;
+
+  // ---- tile plan (block_n, split-K, pair mode)
+  const bool acc_out = d->out_fp32 && d->accumulate;
+  const bool scratch_ok = !acc_out && p.Z == 1 && p.n_groups == 1 && (int64_t)d->M * d->N * 4 <= (64ll << 20);
+  Plan plan;
+  if (d->splits > 1) {   // caller fixed the split factor
+    plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, false, false, d->block_n);
+    plan.splits = d->splits;
+  } else {
+    plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, acc_out || scratch_ok, !acc_out,
+                     d->block_n);
+  }
+  if (plan.bn <= 0) {
+    set_err("gemm: no valid tile plan (bad block_n?)");
+    return B200PDM_ERR_ARG;
+  }
+  if (plan.splits > 1 && !acc_out) {
+    // split-K of a bf16/fp32 (non-accumulating) output: partial sums go to an fp32 scratch through vector atomics,
+    // then one finalize pass applies bias / time-embedding / residual and converts.
+    const int64_t ldws = (d->N + 3) / 4 * 4;
+    float* ws = scratch_f32((size_t)d->M * ldws, stream);
+    if (!ws) return B200PDM_ERR_CUDA;
+    b200pdm_gemm_desc d2 = *d;
+    d2.out = ws, d2.out_fp32 = 1, d2.ldo = ldws, d2.accumulate = 1, d2.splits = plan.splits, d2.block_n = plan.bn;
+    d2.bias = nullptr, d2.rowbias = nullptr, d2.residual = nullptr;
+    int rc2 = launch_gemm(&d2, stream);
+    if (rc2) return rc2;
+    return launch_finalize(d, ws, ldws, stream);
+  }
+  int block_n = plan.bn;
+  p.block_n = block_n;
+  p.tiles_n_per_group = cdiv(p.n_per_group, block_n);
+  int splits = plan.splits;
   if (splits > kblocks) splits = kblocks;
   p.kb_per_split = cdiv(kblocks, splits);
   splits = cdiv(kblocks, p.kb_per_split);
   p.splits = splits;
-  if (splits > 1 && !(d->out_fp32 && d->accumulate)) {
-    set_err("gemm: split-K needs fp32 accumulate output");
-    return B200PDM_ERR_ARG;
-  }
 
-  // cluster size: share the B tile among `cluster` m-tiles (TMA multicast) to cut L2 -> SM traffic
+  // cluster size: share the B tile among `cluster` m-tiles (TMA multicast); measured no gain on B200 -> default 1
   static int env_cluster = -1;
   if (env_cluster < 0) {
     const char* e = getenv("B200PDM_CLUSTER");
@@ -893,13 +1011,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     cluster >>= 1;
   }
   // cta_group::2 pairs: halve the B bytes each SM has to receive per MMA (the L2->SM path is the limiter)
-  static int env_pair = -1;
-  if (env_pair < 0) env_pair = getenv("B200PDM_NO_PAIR") ? 0 : 1;
-  p.pair = 0;
-  if (env_pair && p.tiles_m >= 2 && (b_mn ? ((block_n / 64) % 2 == 0) : (block_n % 16 == 0))) {
-    p.pair = 1;
-    cluster = 2;
-  }
+  p.pair = plan.pair;
+  if (p.pair) cluster = 2;
   p.cluster = p.pair ? 1 : cluster;
   p.tiles_m_super = cdiv(p.tiles_m, cluster);
 
@@ -1082,16 +1195,6 @@ int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ld
   return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
 }
 
-static int pick_splits(long tiles, int kblocks) {
-  // fill the machine about twice over, keep >= 4 k-blocks per split
-  int sms = num_sms();
-  long want = (2L * sms + tiles - 1) / tiles;
-  long max_by_k = kblocks / 4 > 0 ? kblocks / 4 : 1;
-  long s = want < max_by_k ? want : max_by_k;
-  if (s < 1) s = 1;
-  return static_cast<int>(s);
-}
-
 int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw, int64_t M,
                          int64_t N, int64_t K, b200pdm_stream_t stream) {
   // dw[N,K] += dy[M,N]^T . x[M,K]: reduction over M; A(m'=n, k'=m) = dy[m][n] MN-major, B(n'=k, k'=m) = x[m][k] MN-major.
@@ -1101,9 +1204,6 @@ int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ld
   d.b.mode = B200PDM_OP_MN2D, d.b.ptr = x, d.b.ld = ldx;
   d.M = N, d.N = K, d.K = M, d.Z1 = 1, d.Z2 = 1;
   d.out = dw, d.out_fp32 = 1, d.ldo = lddw, d.alpha = 1.f, d.accumulate = 1;
-  int bn = pick_block_n(K, true);
-  long tiles = (long)cdiv(N, kBlockM) * cdiv(K, bn);
-  d.splits = pick_splits(tiles, cdiv(M, 64));
   return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1166,9 +1266,6 @@ int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx,
   d.b.h_out = h_out, d.b.w_out = w_out, d.b.stride = stride, d.b.taps = taps;
   d.M = c_out, d.N = (int64_t)taps * c_in, d.K = pixels, d.Z1 = 1, d.Z2 = 1;
   d.out = dw, d.out_fp32 = 1, d.ldo = (int64_t)taps * w_ild, d.alpha = 1.f, d.accumulate = 1;
-  int bn = pick_block_n(c_in, true);
-  long tiles = (long)cdiv(c_out, kBlockM) * cdiv(c_in, bn) * taps;
-  d.splits = pick_splits(tiles, cdiv(pixels, 64));
   return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
 }
 
