@@ -14,94 +14,138 @@ extern std::atomic<uint64_t> g_launches;
 void set_err(const char* fmt, const char* a);
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics: grid (B, groups, slices); each block reduces hw/slices pixels of one (b, g) and
-// atomically accumulates (sum, sumsq) into ws[2*(b*G+g)].  A second tiny kernel finalises mean/rstd.
+// GroupNorm.  All heavy passes stream whole pixel rows with 16-byte vectors (8 channels per thread) and use
+// per-(sample, channel) fp32 coefficient tables so that the inner loops are free of integer divisions and scalar
+// parameter loads:
+//   tab[0] = scale = gamma * rstd         tab[1] = shift = beta - mean * scale        (z = x*scale + shift)
+//   tab[2] = R     = rstd                 tab[3] = MR    = mean * rstd                (xhat = x*R - MR)
+// Each table is [B, ldc] with ldc = round8(C); pad lanes hold zeros.
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ ws, int hw, int cpg,
-                                int groups, int slices) {
-  const int b = blockIdx.x, g = blockIdx.y, s = blockIdx.z;
+enum { GN_FWD_STATS = 0, GN_BWD_STATS = 1 };
+
+// Column statistics per (sample, channel).  grid (B, ceil(cvec/32), slices), block (32, 8):
+//   FWD: acc0 += x, acc1 += x^2        BWD: dz = dy * act'(z); acc0 += dz, acc1 += dz * xhat
+template <int MODE>
+__global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ dy, int64_t lddy,
+                                   const float* __restrict__ tab, float* __restrict__ out0, float* __restrict__ out1,
+                                   int B, int hw, int C, int ldc, int silu, int slices) {
+  __shared__ float red[8][32][17];
+  const int b = blockIdx.x;
+  const int cv = blockIdx.y * 32 + threadIdx.x;
+  const int c0 = cv * 8;
+  const int s = blockIdx.z;
   const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
-  const bf16* base = x + ((int64_t)b * hw) * ldx + g * cpg;
-  float sum = 0.f, sq = 0.f;
-  const int n = (p1 - p0) * cpg;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int p = i / cpg, c = i - p * cpg;
-    float v = __bfloat162float(base[(int64_t)(p0 + p) * ldx + c]);
-    sum += v;
-    sq += v * v;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  if (c0 < C) {
+    const int nv = min(8, C - c0);
+    float sc[8], sh[8], rr[8], mr[8];
+    if (MODE == GN_BWD_STATS) {
+      const int64_t tb = (int64_t)b * ldc + c0;
+      const int64_t plane = (int64_t)B * ldc;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = tab[tb + j], sh[j] = tab[plane + tb + j], rr[j] = tab[2 * plane + tb + j], mr[j] = tab[3 * plane + tb + j];
+      }
+    }
+    const int64_t row0 = (int64_t)b * hw;
+#pragma unroll 4
+    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+      float xf[8];
+      const bf16* xp = x + (row0 + p) * ldx + c0;
+      if (nv == 8) {
+        unpack8(*reinterpret_cast<const bf16x8*>(xp), xf);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xf[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
+      }
+      if (MODE == GN_FWD_STATS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0[j] += xf[j], a1[j] += xf[j] * xf[j];
+      } else {
+        float df[8];
+        const bf16* dp = dy + (row0 + p) * lddy + c0;
+        if (nv == 8) {
+          unpack8(*reinterpret_cast<const bf16x8*>(dp), df);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) df[j] = j < nv ? __bfloat162float(dp[j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dz = df[j];
+          if (silu) dz *= silu_grad_f(fmaf(xf[j], sc[j], sh[j]));
+          a0[j] += dz;
+          a1[j] += dz * fmaf(xf[j], rr[j], -mr[j]);
+        }
+      }
+    }
   }
-  __shared__ float red[32];
-  sum = block_sum(sum, red);
-  sq = block_sum(sq, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&ws[2 * (b * groups + g)], sum);
-    atomicAdd(&ws[2 * (b * groups + g) + 1], sq);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = a0[j], red[threadIdx.y][threadIdx.x][8 + j] = a1[j];
+  __syncthreads();
+  // 256 threads reduce 32 vectors x 16 values over the 8 row lanes
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int k = tid; k < 32 * 16; k += 256) {
+    const int vx = k >> 4, jj = k & 15;
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += red[y][vx][jj];
+    const int c = (blockIdx.y * 32 + vx) * 8 + (jj & 7);
+    if (c < C) atomicAdd((jj < 8 ? out0 : out1) + (int64_t)b * ldc + c, t);
   }
 }
 
-// Vectorised statistics when cpg % 2 == 0 and ldx % 2 == 0: one thread handles bf16 pairs.
-__global__ void gn_stats_kernel_v2(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ ws, int hw, int cpg,
-                                   int groups, int slices) {
-  const int b = blockIdx.x, g = blockIdx.y, s = blockIdx.z;
-  const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
-  const bf16* base = x + ((int64_t)b * hw) * ldx + g * cpg;
-  const int hp = cpg >> 1;
-  float sum = 0.f, sq = 0.f;
-  const int n = (p1 - p0) * hp;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int p = i / hp, c = i - p * hp;
-    float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (int64_t)(p0 + p) * ldx + 2 * c));
-    sum += v.x + v.y;
-    sq += v.x * v.x + v.y * v.y;
-  }
-  __shared__ float red[32];
-  sum = block_sum(sum, red);
-  sq = block_sum(sq, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&ws[2 * (b * groups + g)], sum);
-    atomicAdd(&ws[2 * (b * groups + g) + 1], sq);
-  }
+// fwd finalize: one thread per (b, c): group sums from planes 4/5 (sum x, sum x^2) -> the four coefficient tables.
+__global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int B, int C, int cpg, int ldc, float inv_n,
+                                       float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const int g0 = (c / cpg) * cpg;
+  const int64_t plane = (int64_t)B * ldc, base = (int64_t)b * ldc;
+  float s = 0.f, q = 0.f;
+  for (int k = 0; k < cpg; ++k) s += tab[4 * plane + base + g0 + k], q += tab[5 * plane + base + g0 + k];
+  const float mean = s * inv_n;
+  const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  tab[base + c] = sc;
+  tab[plane + base + c] = beta[c] - mean * sc;
+  tab[2 * plane + base + c] = rstd;
+  tab[3 * plane + base + c] = mean * rstd;
 }
 
-// in place: (sum, sumsq) -> (mean, rstd)
-__global__ void gn_finalize_kernel(float* __restrict__ ws, int n, float inv_count, float eps) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float m = ws[2 * i] * inv_count;
-  float var = ws[2 * i + 1] * inv_count - m * m;
-  var = fmaxf(var, 0.f);
-  ws[2 * i] = m;
-  ws[2 * i + 1] = rsqrtf(var + eps);
-}
-
-// Apply: y = act(gamma * (x - mean) * rstd + beta); one thread per 8 channels when C % 8 == 0, scalar tail otherwise.
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ stats,
-                                bf16* __restrict__ y, int64_t ldy, int hw, int C, int cpg,
-                                int groups, int silu, int64_t total_vec, int cvec) {
+// y = act(x * scale + shift)
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ tab,
+                                bf16* __restrict__ y, int64_t ldy, int B, int hw, int C, int ldc, int silu,
+                                int64_t total_vec, int cvec) {
+  const int64_t plane = (int64_t)B * ldc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / cvec;
-    int cv = (int)(i - row * cvec);
-    int b = (int)(row / hw);
-    int c0 = cv * 8;
+    const int64_t row = i / cvec;
+    const int c0 = (int)(i - row * cvec) * 8;
+    const int b = (int)(row / hw);
+    const int nv = min(8, C - c0);
     const bf16* xp = x + row * ldx + c0;
     bf16* yp = y + row * ldy + c0;
     float f[8];
-    int nv = min(8, C - c0);
     if (nv == 8) {
       unpack8(*reinterpret_cast<const bf16x8*>(xp), f);
     } else {
+#pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
     }
+    const float* tp = tab + (int64_t)b * ldc + c0;   // ldc % 8 == 0 -> 32-byte aligned vector loads
+    const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int c = c0 + j;
-      if (j < nv) {
-        int g = c / cpg;
-        float m = __ldg(stats + 2 * (b * groups + g)), r = __ldg(stats + 2 * (b * groups + g) + 1);
-        float v = (f[j] - m) * r * __ldg(gamma + c) + __ldg(beta + c);
-        f[j] = silu ? silu_f(v) : v;
-      }
+      const float v = fmaf(f[j], sc[j], sh[j]);
+      f[j] = silu ? silu_f(v) : v;
     }
     if (nv == 8) {
       *reinterpret_cast<bf16x8*>(yp) = pack8(f);
@@ -111,72 +155,39 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const f
   }
 }
 
-// Backward pass 1: per (b, g) sums  s1 = sum(gamma*dz), s2 = sum(gamma*dz*xhat)  (atomics into ws), and per-channel
-// dgamma += sum(dz*xhat), dbeta += sum(dz) where dz = dy * act'(z).
-// grid (B, groups, slices), block = 256 threads; thread t owns channel (t % cpg_pad) lanes for coalescing-ish access.
-__global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ stats,
-                                     float* __restrict__ ws, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     int hw, int cpg, int groups, int silu, int slices) {
-  extern __shared__ float sh[];  // [2 * cpg] per-channel partials + 32 reduction scratch
-  float* ch_dg = sh;
-  float* ch_db = sh + cpg;
-  float* red = sh + 2 * cpg;
-  const int b = blockIdx.x, g = blockIdx.y, s = blockIdx.z;
-  for (int i = threadIdx.x; i < 2 * cpg; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
-  const float m = stats[2 * (b * groups + g)], r = stats[2 * (b * groups + g) + 1];
-  const int64_t row0 = (int64_t)b * hw;
-  // thread -> (pixel lane, channel): channel = threadIdx.x % cpg for threads < floor(blockDim/cpg)*cpg
-  const int ppb = blockDim.x / cpg;  // pixels processed per block iteration
-  float s1 = 0.f, s2 = 0.f, dg = 0.f, db = 0.f;
-  const int c = threadIdx.x % cpg;
-  const int pl = threadIdx.x / cpg;
-  if (pl < ppb) {
-    const int ch = g * cpg + c;
-    const float ga = gamma[ch], be = beta[ch];
-    for (int p = p0 + pl; p < p1; p += ppb) {
-      float xv = __bfloat162float(x[(row0 + p) * ldx + ch]);
-      float dv = __bfloat162float(dy[(row0 + p) * lddy + ch]);
-      float xh = (xv - m) * r;
-      float dz = dv;
-      if (silu) dz *= silu_grad_f(xh * ga + be);
-      dg += dz * xh;
-      db += dz;
-      s1 += ga * dz;
-      s2 += ga * dz * xh;
-    }
-    atomicAdd(&ch_dg[c], dg);
-    atomicAdd(&ch_db[c], db);
+// bwd finalize: one thread per (b, c).  ws[0] = sum dz, ws[1] = sum dz*xhat per (b, c)  ->
+//   dgamma[c] += ws1, dbeta[c] += ws0 ;  ws[2] <- P = -rstd^2 * s2/n ,  ws[3] <- Q = -rstd*s1/n + mean*rstd^2*s2/n
+__global__ void gn_bwd_finalize_kernel(float* __restrict__ ws, const float* __restrict__ tab,
+                                       const float* __restrict__ gamma, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int B, int C, int cpg, int ldc, float inv_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const int g0 = (c / cpg) * cpg;
+  const int64_t plane = (int64_t)B * ldc, base = (int64_t)b * ldc;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < cpg; ++k) {
+    const float ga = gamma[g0 + k];
+    s1 += ga * ws[base + g0 + k], s2 += ga * ws[plane + base + g0 + k];
   }
-  s1 = block_sum(s1, red);
-  s2 = block_sum(s2, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&ws[2 * (b * groups + g)], s1);
-    atomicAdd(&ws[2 * (b * groups + g) + 1], s2);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
-    atomicAdd(&dgamma[g * cpg + i], ch_dg[i]);
-    atomicAdd(&dbeta[g * cpg + i], ch_db[i]);
-  }
+  atomicAdd(dbeta + c, ws[base + c]);
+  atomicAdd(dgamma + c, ws[plane + base + c]);
+  const float rstd = tab[2 * plane + base + c], mr = tab[3 * plane + base + c];
+  ws[2 * plane + base + c] = -rstd * rstd * s2 * inv_n;
+  ws[3 * plane + base + c] = -rstd * s1 * inv_n + mr * rstd * s2 * inv_n;
 }
 
-// Backward pass 2: dx = rstd * (gamma*dz - s1/n - xhat * s2/n)
+// dx = scale * dz + x * P + Q (+ residual)
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                    const float* __restrict__ stats,
-                                    const float* __restrict__ ws, const bf16* __restrict__ res, int64_t ldr,
-                                    bf16* __restrict__ dx, int64_t lddx, int hw, int C, int cpg, int groups, int silu,
-                                    float inv_n, int64_t total_vec, int cvec) {
+                                    const float* __restrict__ tab, const float* __restrict__ ws,
+                                    const bf16* __restrict__ res, int64_t ldr, bf16* __restrict__ dx, int64_t lddx,
+                                    int B, int hw, int C, int ldc, int silu, int64_t total_vec, int cvec) {
+  const int64_t plane = (int64_t)B * ldc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = i / cvec;
-    int cv = (int)(i - row * cvec);
-    int b = (int)(row / hw);
-    int c0 = cv * 8;
-    int nv = min(8, C - c0);
+    const int64_t row = i / cvec;
+    const int c0 = (int)(i - row * cvec) * 8;
+    const int b = (int)(row / hw);
+    const int nv = min(8, C - c0);
     float xf[8], df[8], o[8];
     const bf16* xp = x + row * ldx + c0;
     const bf16* dp = dy + row * lddy + c0;
@@ -184,26 +195,27 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
       unpack8(*reinterpret_cast<const bf16x8*>(xp), xf);
       unpack8(*reinterpret_cast<const bf16x8*>(dp), df);
     } else {
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
         xf[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
         df[j] = j < nv ? __bfloat162float(dp[j]) : 0.f;
       }
     }
+    const float* tp = tab + (int64_t)b * ldc + c0;
+    const float* wp = ws + (int64_t)b * ldc + c0;
+    const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
+    const float4 p0 = *reinterpret_cast<const float4*>(wp + 2 * plane), p1 = *reinterpret_cast<const float4*>(wp + 2 * plane + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(wp + 3 * plane), q1 = *reinterpret_cast<const float4*>(wp + 3 * plane + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const float P[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    const float Q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      o[j] = 0.f;
-      if (j < nv) {
-        int c = c0 + j;
-        int g = c / cpg;
-        int sg = b * groups + g;
-        float m = __ldg(stats + 2 * sg), r = __ldg(stats + 2 * sg + 1);
-        float ga = __ldg(gamma + c);
-        float xh = (xf[j] - m) * r;
-        float dz = df[j];
-        if (silu) dz *= silu_grad_f(xh * ga + __ldg(beta + c));
-        float s1 = __ldg(ws + 2 * sg) * inv_n, s2 = __ldg(ws + 2 * sg + 1) * inv_n;
-        o[j] = r * (ga * dz - s1 - xh * s2);
-      }
+      float dz = df[j];
+      if (silu) dz *= silu_grad_f(fmaf(xf[j], sc[j], sh[j]));
+      o[j] = fmaf(sc[j], dz, fmaf(xf[j], P[j], Q[j]));
     }
     if (res) {  // fused gradient merge: dx += residual (e.g. the skip/shortcut branch's gradient)
       const bf16* rp = res + row * ldr + c0;
@@ -371,76 +383,77 @@ using namespace b200;
 
 extern "C" {
 
-// stats: fp32 [2 * batch * groups], interleaved (mean, rstd) per (sample, group).
+// stats: fp32 [6][batch][round8(C)]: coefficient tables scale, shift, rstd, mean*rstd (+ 2 planes of scratch sums).
 int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                           float* stats, int batch, int hw, int C, int groups, float eps, int silu,
                           b200pdm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (groups <= 0 || C % groups) {
-    set_err("groupnorm: C %% groups != 0", "");
+  if (groups <= 0 || C % groups || ldx % 8 || ldy % 8) {
+    set_err("groupnorm: C %% groups != 0 or pitches not multiples of 8", "");
     return B200PDM_ERR_ARG;
   }
   const int cpg = C / groups;
-  const int n = batch * groups;
-  if (cudaMemsetAsync(stats, 0, sizeof(float) * 2 * n, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
-  // enough blocks to fill the machine: B*groups*slices >= ~4*148
-  int slices = (4 * 148 + n - 1) / n;
-  if (slices < 1) slices = 1;
-  if (slices > hw / 8) slices = hw / 8 > 0 ? hw / 8 : 1;
-  dim3 grid(batch, groups, slices);
-  const bf16* xb = reinterpret_cast<const bf16*>(x);
-  if ((cpg % 2 == 0) && (ldx % 2 == 0))
-    gn_stats_kernel_v2<<<grid, 256, 0, stream>>>(xb, ldx, stats, hw, cpg, groups, slices);
-  else
-    gn_stats_kernel<<<grid, 256, 0, stream>>>(xb, ldx, stats, hw, cpg, groups, slices);
-  B200_CHECK_LAUNCH();
-  gn_finalize_kernel<<<(n + 127) / 128, 128, 0, stream>>>(stats, n, 1.f / ((float)hw * cpg), eps);
-  B200_CHECK_LAUNCH();
+  const int ldc = (C + 7) / 8 * 8;
+  const int64_t plane = (int64_t)batch * ldc;
+  if (cudaMemsetAsync(stats, 0, sizeof(float) * 6 * plane, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
   const int cvec = (C + 7) / 8;
+  const int cchunks = (cvec + 31) / 32;
+  int slices = (148 * 3 + batch * cchunks - 1) / (batch * cchunks);
+  if (slices > hw / 16) slices = hw / 16 > 0 ? hw / 16 : 1;
+  if (slices < 1) slices = 1;
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  gn_colstats_kernel<GN_FWD_STATS><<<dim3(batch, cchunks, slices), dim3(32, 8), 0, stream>>>(
+      xb, ldx, nullptr, 0, nullptr, stats + 4 * plane, stats + 5 * plane, batch, hw, C, ldc, 0, slices);
+  B200_CHECK_LAUNCH();
+  const int n = batch * C;
+  gn_fwd_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(stats, gamma, beta, batch, C, cpg, ldc,
+                                                             1.f / ((float)hw * cpg), eps);
+  B200_CHECK_LAUNCH();
   const int64_t total_vec = (int64_t)batch * hw * cvec;
   int blocks = (int)((total_vec + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<blocks, 256, 0, stream>>>(xb, ldx, gamma, beta, stats, reinterpret_cast<bf16*>(y), ldy, hw, C, cpg,
-                                             groups, silu, total_vec, cvec);
+  gn_apply_kernel<<<blocks, 256, 0, stream>>>(xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc, silu,
+                                             total_vec, cvec);
   B200_CHECK_LAUNCH();
   g_launches += 4;
   return B200PDM_OK;
 }
 
-// workspace: fp32 [2 * batch * groups].
+// workspace: fp32 [4][batch][round8(C)].
 int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
                           const float* beta, const float* stats, const void* residual, int64_t ldr, void* dx,
                           int64_t lddx, float* dgamma, float* dbeta, float* workspace, int batch, int hw, int C,
                           int groups, int silu, b200pdm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (groups <= 0 || C % groups) return B200PDM_ERR_ARG;
+  if (groups <= 0 || C % groups || ldx % 8 || lddy % 8 || lddx % 8 || (residual && ldr % 8)) return B200PDM_ERR_ARG;
+  (void)beta;
   const int cpg = C / groups;
-  const int n = batch * groups;
-  if (cpg > 256) {
-    set_err("groupnorm_bwd: channels per group > 256 unsupported", "");
-    return B200PDM_ERR_UNSUPPORTED;
-  }
-  if (cudaMemsetAsync(workspace, 0, sizeof(float) * 2 * n, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
-  int slices = (4 * 148 + n - 1) / n;
-  if (slices < 1) slices = 1;
-  if (slices > hw / 8) slices = hw / 8 > 0 ? hw / 8 : 1;
-  dim3 grid(batch, groups, slices);
-  const size_t sh = sizeof(float) * (2 * cpg + 32);
-  gn_bwd_reduce_kernel<<<grid, 256, sh, stream>>>(reinterpret_cast<const bf16*>(dy), lddy,
-                                                  reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, workspace,
-                                                  dgamma, dbeta, hw, cpg, groups, silu, slices);
-  B200_CHECK_LAUNCH();
+  const int ldc = (C + 7) / 8 * 8;
+  const int64_t plane = (int64_t)batch * ldc;
+  if (cudaMemsetAsync(workspace, 0, sizeof(float) * 4 * plane, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
   const int cvec = (C + 7) / 8;
+  const int cchunks = (cvec + 31) / 32;
+  int slices = (148 * 3 + batch * cchunks - 1) / (batch * cchunks);
+  if (slices > hw / 16) slices = hw / 16 > 0 ? hw / 16 : 1;
+  if (slices < 1) slices = 1;
+  const bf16* xb = reinterpret_cast<const bf16*>(x);
+  const bf16* dyb = reinterpret_cast<const bf16*>(dy);
+  gn_colstats_kernel<GN_BWD_STATS><<<dim3(batch, cchunks, slices), dim3(32, 8), 0, stream>>>(
+      xb, ldx, dyb, lddy, stats, workspace, workspace + plane, batch, hw, C, ldc, silu, slices);
+  B200_CHECK_LAUNCH();
+  const int n = batch * C;
+  gn_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(workspace, stats, gamma, dgamma, dbeta, batch, C, cpg, ldc,
+                                                             1.f / ((float)hw * cpg));
+  B200_CHECK_LAUNCH();
   const int64_t total_vec = (int64_t)batch * hw * cvec;
   int blocks = (int)((total_vec + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy), lddy,
-                                                 reinterpret_cast<const bf16*>(x), ldx, gamma, beta, stats, workspace,
+  gn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(dyb, lddy, xb, ldx, stats, workspace,
                                                  reinterpret_cast<const bf16*>(residual), ldr,
-                                                 reinterpret_cast<bf16*>(dx), lddx, hw, C, cpg, groups, silu,
-                                                 1.f / ((float)hw * cpg), total_vec, cvec);
+                                                 reinterpret_cast<bf16*>(dx), lddx, batch, hw, C, ldc, silu, total_vec,
+                                                 cvec);
   B200_CHECK_LAUNCH();
-  g_launches += 3;
+  g_launches += 4;
   return B200PDM_OK;
 }
 

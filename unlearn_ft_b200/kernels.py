@@ -148,7 +148,7 @@ def groupnorm_fwd(x, gamma, beta, B, hw, groups, eps, silu, out=None):
     Cn = x.shape[1]
     if out is None:
         out = alloc2d(B * hw, Cn, x.device)
-    stats = torch.empty(2 * B * groups, device=x.device, dtype=F32)
+    stats = torch.empty(6 * B * round8(Cn), device=x.device, dtype=F32)  # 4 coefficient tables + 2 scratch planes
     check(_lib.lib().b200pdm_groupnorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
                                            out.stride(0), stats.data_ptr(), B, hw, Cn, groups, eps, int(silu),
                                            _stream()), "groupnorm_fwd")
@@ -160,7 +160,7 @@ def groupnorm_bwd(dy, x, gamma, beta, stats, dgamma, dbeta, B, hw, groups, silu,
     Cn = x.shape[1]
     if out is None:
         out = alloc2d(B * hw, Cn, x.device)
-    ws = torch.empty(2 * B * groups, device=x.device, dtype=F32)
+    ws = torch.empty(4 * B * round8(Cn), device=x.device, dtype=F32)
     check(_lib.lib().b200pdm_groupnorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
                                            beta.data_ptr(), stats.data_ptr(), _ptr(residual),
                                            residual.stride(0) if residual is not None else 0, out.data_ptr(),
