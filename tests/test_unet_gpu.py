@@ -191,3 +191,49 @@ def test_reference_trainer_style_loss_with_hooks(gold):
     assert torch.isfinite(total)
     assert float(mine.arena.grad.abs().sum()) > 0
     assert set(fs) == {"d0", "d1", "d2", "d3", "m", "u0", "u1", "u2", "u3"}
+
+
+def test_bilevel_upper_step_matches_oracle(gold):
+    """BilevelUnetFineTuner.upper_step (reference trainer.py:2904-3001): loss = mse(student(x_t,c), 2*eps_T(x_t,0) - eps_T(x_t,c)),
+    second AdamW state set on the same parameters, upper step every `upper_step_freq` lower steps (:2795-2816)."""
+    from oracle import diffusers_restated as D
+    from oracle import pdm_restated as P
+    from oracle.make_golden import SMALL64, deterministic_fill
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel
+    from unlearn_ft_b200.pdm.training import BilevelUnetFineTuner
+    av = gold["small64_r055"]["arch_vector"]
+    mine, orc = build_pair(av, trainable=True)
+    teacher_o = D.UNet2DConditionModel(**{**D.SD21_UNET_CONFIG, "block_out_channels": SMALL64["block_out_channels"],
+                                          "attention_head_dim": SMALL64["heads"],
+                                          "cross_attention_dim": SMALL64["cross_attention_dim"]})
+    deterministic_fill(teacher_o, 5)
+    teacher = UNet2DConditionModel(small_cfg(), seed=None)
+    teacher.load_state_dict(teacher_o.state_dict())
+    teacher_o = teacher_o.eval().cuda()
+    tuner = BilevelUnetFineTuner(mine, teacher, lr=1e-5, upper_lr=5e-5, upper_step_freq=2, warmup_steps=0)
+    batch = make_batch(seed=3)
+    g = torch.Generator().manual_seed(9)
+    batch["empty_prompt_embeds"] = torch.randn(1, 77, SMALL64["cross_attention_dim"], generator=g).expand(2, -1, -1).contiguous().cuda()
+    loss, kd = tuner.upper_step(batch)
+    ref = P.upper_step(orc, teacher_o, D.DDIMSchedulerLite(), batch["latents"], batch["noise"], batch["timesteps"],
+                       batch["prompt_embeds"], batch["empty_prompt_embeds"])
+    print("upper loss", loss.item(), "oracle", ref.item())
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-2
+    loss.backward()
+    ref.backward()
+    params = dict(mine.named_parameters())
+    for k, p in orc.named_parameters():
+        if p.grad.abs().max() > 1e-8:
+            cos = F.cosine_similarity(p.grad.flatten().float(), params[k].grad.flatten().float(), dim=0).item()
+            assert cos > 0.98, (k, cos)
+    mine.arena.grad.zero_()
+    # schedule: lower steps every call, upper step on every 2nd call, separate optimiser states
+    p0 = mine.arena.master.detach().clone()
+    tuner.train_step(batch, upper_batch=batch)
+    assert tuner.optimizer.step_count == 1 and tuner.upper_optimizer.step_count == 0
+    tuner.train_step(batch, upper_batch=batch)
+    assert tuner.optimizer.step_count == 2 and tuner.upper_optimizer.step_count == 1
+    assert float(tuner.upper_optimizer.exp_avg.abs().sum()) > 0
+    assert not torch.equal(tuner.upper_optimizer.exp_avg, tuner.optimizer.exp_avg)
+    assert not torch.equal(p0, mine.arena.master.detach())
+    assert float(mine.arena.grad.abs().sum()) == 0.0

@@ -135,33 +135,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
+      // pass 1: row maximum (4 independent chains; masking only on the ragged last block)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
         tmem_ld_wait();
+        if (valid == kKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx * p.scale_log2);
       const float alpha = exp2f(m - m_new);
       l *= alpha;
       // pass 2: probabilities -> bf16 P tile (K-major, swizzle-128B)
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
         tmem_ld_wait();
         float pf[32];
+        if (valid == kKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-          e = (c * 32 + i < valid) ? e : 0.f;
-          pf[i] = e;
-          l += e;
+          for (int i = 0; i < 32; ++i) {
+            pf[i] = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+            l4[i & 3] += pf[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+            e = (c * 32 + i < valid) ? e : 0.f;
+            pf[i] = e;
+            l4[i & 3] += e;
+          }
         }
         const uint32_t base = p_row + (c >> 1) * kTileBytes;
 #pragma unroll
@@ -177,6 +192,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                        : "memory");
         }
       }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       m = m_new;
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
@@ -456,12 +472,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_32x32(t_dp + lane_base + c * 32, dv_);
         tmem_ld_wait();
         float pf[32], dsf[32];
+        if (q_ok && valid_k == kKV) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float pe = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
-          pe = (q_ok && (c * 32 + j < valid_k)) ? pe : 0.f;
-          pf[j] = pe;
-          dsf[j] = pe * (__uint_as_float(dv_[j]) - dlt) * p.scale;
+          for (int j = 0; j < 32; ++j) {
+            pf[j] = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
+            dsf[j] = pf[j] * ((__uint_as_float(dv_[j]) - dlt) * p.scale);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float pe = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
+            pe = (q_ok && (c * 32 + j < valid_k)) ? pe : 0.f;
+            pf[j] = pe;
+            dsf[j] = pe * (__uint_as_float(dv_[j]) - dlt) * p.scale;
+          }
         }
         st_tile_row32(p_row, c, sw, pf);
         st_tile_row32(ds_row, c, sw, dsf);

@@ -75,9 +75,17 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
     set_err("tensor map base not 16-byte aligned");
     return B200PDM_ERR_ARG;
   }
+  static int promo = -1;
+  if (promo < 0) {
+    const char* e = getenv("B200PDM_L2PROMO");
+    promo = e ? atoi(e) : 256;
+  }
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu %llu %llu box %u %u %u %u)",
              (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
@@ -203,7 +211,7 @@ __device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, 
       ld4<PAIR>(dst + kAtomBytes, map, bar, m_tile * kBlockM + 64, kb * kBlockK, z % op.Z1, z / op.Z1);
       break;
     case B200PDM_OP_CONV_ACT: {
-      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
       int kh = 1, kw = 1;
       if (op.taps == 9) {
         kh = tap / 3;
@@ -242,12 +250,12 @@ __device__ __forceinline__ void load_b_pair(const OpDev& op, const CUtensorMap* 
         tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), kb * kBlockK, z % op.Z1, z / op.Z1);
       break;
     case B200PDM_OP_CONV_W: {
-      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
       tma_load_3d_2sm(dst, map, bar, cb * kBlockK, tap, n0 + rank * rows);
       break;
     }
     case B200PDM_OP_CONV_WT: {
-      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
       for (int j = 0; j < atoms; ++j)
         tma_load_3d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), tap, cb * kBlockK);
       break;
@@ -298,7 +306,7 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
       }
       break;
     case B200PDM_OP_CONV_W: {
-      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
       if (cluster == 1)
         tma_load_3d(dst, map, bar, cb * kBlockK, tap, n0);
       else
@@ -306,7 +314,7 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
       break;
     }
     case B200PDM_OP_CONV_WT: {
-      int tap = kb / op.cblks, cb = kb - tap * op.cblks;
+      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
       if (cluster == 1) {
         for (int j = 0; j < block_n / 64; ++j)
           tma_load_3d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK);
@@ -1025,6 +1033,12 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   const int stage_bytes = kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
   int stages = (193 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
+  static int env_stages = -1;
+  if (env_stages < 0) {
+    const char* e = getenv("B200PDM_STAGES");
+    env_stages = e ? atoi(e) : 0;
+  }
+  if (env_stages > 0 && stages > env_stages) stages = env_stages;
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.idesc = make_idesc_bf16(block_n, a_mn ? 1 : 0, b_mn ? 1 : 0, p.pair ? 256 : 128);
