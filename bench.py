@@ -188,6 +188,39 @@ def gemm_roofline(torch, K, batch, latent):
     return flops / (ms * 1e-3) / 1e12, ms, f"conv3x3 {Ci}->{Co} @ {H}x{W} batch {B} (implicit GEMM M={B*H*W} N={Co} K={9*Ci})"
 
 
+def adamw_roofline(torch, K, student):
+    """Second roofline point (HBM-bound class): the fused AdamW over the student's flat arena, timed alone with CUDA
+    events.  Algorithmic bytes per parameter: 16 B read (p, g, m, v) + 12 B write (p, m, v) + 2 B bf16 shadow + 4 B
+    gradient zeroing = 34 B."""
+    a = student.arena
+    m, v = torch.zeros_like(a.master), torch.zeros_like(a.master)
+    p = a.master.detach().clone()
+    g = torch.zeros_like(p)
+    sh = torch.empty_like(a.shadow)
+    for i in range(2):
+        K.adamw_step(p, g, m, v, sh, 1e-6, 0.9, 0.999, 1e-8, 0.0, i + 1)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for i, (e0, e1) in enumerate(ev):
+        e0.record()
+        K.adamw_step(p, g, m, v, sh, 1e-6, 0.9, 0.999, 1e-8, 0.0, i + 3)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = statistics.median(e0.elapsed_time(e1) for e0, e1 in ev)
+    bytes_ = 34.0 * a.numel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    gbs = bytes_ / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "b200::adamw_kernel (flat multi-tensor AdamW + bf16 shadow + grad zeroing)",
+            "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "ms_per_launch": ms,
+            "bytes_per_launch": bytes_, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs, of measured" if peaks else "fallback 6650 GB/s, of fallback"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -302,6 +335,7 @@ def main():
     except Exception:
         pass
     tf, conv_ms, conv_desc = gemm_roofline(torch, K, B, L)
+    hbm = adamw_roofline(torch, K, student)
     peak_burst = peaks.get("bf16_tflops", 1590.0)
     step_tf = STEP_TFLOP_PER_SAMPLE.get(round(args.ratio, 2), 2.196) * B / (ms_total / args.steps * 1e-3) if ms_total else 0
     line = {
@@ -315,9 +349,14 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "roofline_hbm": hbm,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
-                     "traffic": None, "kernel": "b200::gemm_kernel<0,0> (tcgen05 implicit-GEMM conv)", "shape": conv_desc,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full
+                     # capture profiles/r1_ncu_full_conv960x170_pair.txt (algorithmic bytes: 151.0 MB)
+                     "traffic": 261.96e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 151.0e6,
+                     "kernel": "b200::gemm_kernel<0,0,true> (tcgen05 cta_group::2 implicit-GEMM conv)",
+                     "shape": conv_desc,
                      "ms_per_launch": conv_ms,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), of measured"
                      if peaks else "fallback 1590 TFLOP/s, of fallback",
