@@ -54,6 +54,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// One lane of a converged warp.  Single-thread instructions (TMA, tcgen05.mma/commit) are issued under this predicate from
+// warp-uniform code, so their operands live in uniform registers; a `lane == 0` branch instead makes the compiler wrap
+// every such instruction in an ELECT / R2UR waterfall loop (~20 instructions each).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Bounded wait: a pipeline bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

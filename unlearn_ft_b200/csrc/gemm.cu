@@ -123,6 +123,24 @@ int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
 // ------------------------------------------------------------------------------------------------
 // Device-side parameters
 // ------------------------------------------------------------------------------------------------
+// n / d for 0 <= n < 2^31 without the ~200-cycle integer-division sequence: the single producer / epilogue threads sit on
+// the critical path of every k-block, so their address arithmetic must stay a handful of instructions.
+struct FastDiv {
+  uint32_t mul, shr;
+};
+static FastDiv make_fastdiv(int64_t d64) {
+  uint32_t d = d64 < 1 ? 1u : static_cast<uint32_t>(d64);
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  uint64_t m = ((1ull << 32) * ((1ull << s) - d)) / d + 1;
+  FastDiv f;
+  f.mul = static_cast<uint32_t>(m), f.shr = s;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, FastDiv d) {
+  return static_cast<int>((__umulhi(static_cast<uint32_t>(n), d.mul) + static_cast<uint32_t>(n)) >> d.shr);
+}
+
 struct OpDev {
   int mode;
   int Z1;
@@ -131,6 +149,7 @@ struct OpDev {
   int Wo, HoWo;  // output grid (pixel decomposition)
   int stride;
   int flip;
+  FastDiv fd_Wo, fd_HoWo;
 };
 
 struct GemmDev {
@@ -141,10 +160,12 @@ struct GemmDev {
   int64_t out_group_stride;
   int tiles_m, tiles_n_per_group, Z, splits;
   int kblocks, kb_per_split;
+  int k_taps;        // conv fprop/dgrad: K runs over (channel block, tap), taps innermost; else 1
   int block_n, stages;
   int pair;          // 1: cta_group::2 -- one M=256 MMA per CTA pair, each CTA stages its 128 A rows and HALF of B
   int cluster;       // CTAs per cluster (1, 2, 4): B tile loaded once per cluster and multicast
   int tiles_m_super; // ceil(tiles_m / cluster)
+  FastDiv fd_tiles_per_split, fd_slab, fd_tiles_n, fd_tiles_n_per_group, fd_Z1, fd_taps, fd_rows_per_group;
   uint32_t idesc;
   // epilogue
   void* out;
@@ -159,17 +180,54 @@ struct GemmDev {
   float alpha;
   int accumulate;
   long long* dbg;  // optional per-role wait-cycle counters (diagnostics)
+  int dbg_mode;    // diagnostics only (B200PDM_GEMM_DBGMODE): 1 = quarter of the MMAs, 2 = no A loads, 4 = no B loads
   int epi_tma;     // bf16 output through smem staging + TMA store (coalesced, asynchronous)
   int res_tma;     // residual chunks prefetched with TMA
 };
+
+// Where a tile sits: decoded once per tile by each role.
+struct TileCoord {
+  int split, z1, z2, m_tile, grp, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int tiles_per_split, int tiles_n, int cluster,
+                                                 int rank) {
+  TileCoord c;
+  c.split = p.splits > 1 ? fdiv(t, p.fd_tiles_per_split) : 0;
+  int r = t - c.split * tiles_per_split;
+  int z = 0;
+  if (p.Z > 1) {
+    z = fdiv(r, p.fd_slab);
+    r -= z * (p.tiles_m_super * tiles_n);
+  }
+  c.z2 = p.Z > 1 ? fdiv(z, p.fd_Z1) : 0;
+  c.z1 = z - c.z2 * p.a.Z1;
+  const int m_super = fdiv(r, p.fd_tiles_n);
+  const int n_tile = r - m_super * tiles_n;
+  c.m_tile = m_super * cluster + rank;
+  c.grp = p.n_groups > 1 ? fdiv(n_tile, p.fd_tiles_n_per_group) : 0;
+  c.nt = n_tile - c.grp * p.tiles_n_per_group;
+  return c;
+}
+
+// (kh, kw) of tap 0..8 (row-major 3x3), optionally flipped (dgrad); centre for 1x1.
+__device__ __forceinline__ void tap_offsets(int taps, int tap, int flip, int* kh, int* kw) {
+  int h = 1, w = 1;
+  if (taps == 9) {
+    h = (tap * 11) >> 5;
+    w = tap - 3 * h;
+    if (flip) h = 2 - h, w = 2 - w;
+  }
+  *kh = h, *kw = w;
+}
 
 #define DBG_WAIT(slot, stmt)                                              \
   do {                                                                    \
     if (p.dbg && blockIdx.x == 0) {                                       \
       long long t0__ = clock64();                                         \
       stmt;                                                               \
-      atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (slot)),    \
-                static_cast<unsigned long long>(clock64() - t0__));       \
+      if ((threadIdx.x & 31) == 0 || (slot) == 6)                         \
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (slot)),  \
+                  static_cast<unsigned long long>(clock64() - t0__));     \
     } else {                                                              \
       stmt;                                                               \
     }                                                                     \
@@ -199,34 +257,40 @@ __device__ __forceinline__ void ld3(void* dst, const CUtensorMap* map, uint64_t*
     tma_load_3d(dst, map, bar, c0, c1, c2);
 }
 
+// Per-tile operand cursors: everything that does not change along K is computed once per tile.
+struct ACursor {
+  int c1, c2, c3;   // K2D/MN2D: (row0, z1, z2); CONV_ACT: (w0*stride - 1, h0*stride - 1, n0)
+};
+__device__ __forceinline__ ACursor make_a_cursor(const OpDev& op, const TileCoord& tc) {
+  ACursor c;
+  if (op.mode == B200PDM_OP_CONV_ACT) {
+    const int pix0 = tc.m_tile * kBlockM;
+    const int n0 = fdiv(pix0, op.fd_HoWo);
+    const int rem = pix0 - n0 * op.HoWo;
+    const int h0 = fdiv(rem, op.fd_Wo);
+    const int w0 = rem - h0 * op.Wo;
+    c.c1 = w0 * op.stride - 1, c.c2 = h0 * op.stride - 1, c.c3 = n0;
+  } else {
+    c.c1 = tc.m_tile * kBlockM, c.c2 = tc.z1, c.c3 = tc.z2;
+  }
+  return c;
+}
+
 template <bool PAIR>
-__device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int m_tile,
-                                       int kb, int z) {
+__device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar,
+                                       const ACursor& c, int kb, int cb, int tap) {
   switch (op.mode) {
     case B200PDM_OP_K2D:
-      ld4<PAIR>(dst, map, bar, kb * kBlockK, m_tile * kBlockM, z % op.Z1, z / op.Z1);
+      ld4<PAIR>(dst, map, bar, kb * kBlockK, c.c1, c.c2, c.c3);
       break;
     case B200PDM_OP_MN2D:
-      ld4<PAIR>(dst, map, bar, m_tile * kBlockM, kb * kBlockK, z % op.Z1, z / op.Z1);
-      ld4<PAIR>(dst + kAtomBytes, map, bar, m_tile * kBlockM + 64, kb * kBlockK, z % op.Z1, z / op.Z1);
+      ld4<PAIR>(dst, map, bar, c.c1, kb * kBlockK, c.c2, c.c3);
+      ld4<PAIR>(dst + kAtomBytes, map, bar, c.c1 + 64, kb * kBlockK, c.c2, c.c3);
       break;
     case B200PDM_OP_CONV_ACT: {
-      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
-      int kh = 1, kw = 1;
-      if (op.taps == 9) {
-        kh = tap / 3;
-        kw = tap - kh * 3;
-        if (op.flip) {
-          kh = 2 - kh;
-          kw = 2 - kw;
-        }
-      }
-      int pix0 = m_tile * kBlockM;
-      int n0 = pix0 / op.HoWo;
-      int rem = pix0 - n0 * op.HoWo;
-      int h0 = rem / op.Wo;
-      int w0 = rem - h0 * op.Wo;
-      ld4<PAIR>(dst, map, bar, cb * kBlockK, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, n0);
+      int kh, kw;
+      tap_offsets(op.taps, tap, op.flip, &kh, &kw);
+      ld4<PAIR>(dst, map, bar, cb * kBlockK, c.c1 + kw, c.c2 + kh, c.c3);
       break;
     }
     default:
@@ -234,114 +298,74 @@ __device__ __forceinline__ void load_a(const OpDev& op, const CUtensorMap* map, 
   }
 }
 
-// cta_group::2: CTA `rank` of the pair stages only its half of the B tile (rows / atoms [rank*half, (rank+1)*half)) at
-// the start of its own stage buffer.
-__device__ __forceinline__ void load_b_pair(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int grp,
-                                            int nt, int block_n, int kb, int z, int rank) {
-  const int n0 = nt * block_n;
-  const int rows = block_n / 2;
-  const int atoms = (block_n / 64) / 2;
-  switch (op.mode) {
-    case B200PDM_OP_K2D:
-      tma_load_4d_2sm(dst, map, bar, kb * kBlockK, n0 + rank * rows, z % op.Z1, z / op.Z1);
-      break;
-    case B200PDM_OP_MN2D:
-      for (int j = 0; j < atoms; ++j)
-        tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), kb * kBlockK, z % op.Z1, z / op.Z1);
-      break;
-    case B200PDM_OP_CONV_W: {
-      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
-      tma_load_3d_2sm(dst, map, bar, cb * kBlockK, tap, n0 + rank * rows);
-      break;
-    }
-    case B200PDM_OP_CONV_WT: {
-      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
-      for (int j = 0; j < atoms; ++j)
-        tma_load_3d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), tap, cb * kBlockK);
-      break;
-    }
-    case B200PDM_OP_CONV_ACT_MN: {
-      int kh = 1, kw = 1;
-      if (op.taps == 9) {
-        kh = grp / 3;
-        kw = grp - kh * 3;
-      }
-      int pix0 = kb * kBlockK;
-      int b0 = pix0 / op.HoWo;
-      int rem = pix0 - b0 * op.HoWo;
-      int h0 = rem / op.Wo;
-      int w0 = rem - h0 * op.Wo;
-      for (int j = 0; j < atoms; ++j)
-        tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, n0 + 64 * (rank * atoms + j), w0 * op.stride + kw - 1,
-                        h0 * op.stride + kh - 1, b0);
-      break;
-    }
-    default:
-      break;
-  }
-}
-
-// With cluster > 1 each CTA fetches only its 1/cluster slice of the B tile (rows [rank*block_n/cluster, ...) for
-// K-major tiles, whole 64-wide atoms for MN-major tiles) and multicasts it to every CTA of the cluster.
-__device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int grp,
-                                       int nt, int block_n, int kb, int z, int cluster, int rank) {
-  const int n0 = nt * block_n;
+// B tile of n-tile `nt` (tap group `grp` for wgrad).  pair mode (cta_group::2): CTA `rank` stages only its half of the
+// tile (rows / atoms [rank*half, (rank+1)*half)) at the start of its own stage buffer.  Otherwise, with cluster > 1, each
+// CTA fetches its 1/cluster slice and multicasts it to every CTA of the cluster.
+struct BCursor {
+  int n0, kh, kw;
+};
+template <bool PAIR>
+__device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar,
+                                       const BCursor& c, const TileCoord& tc, int block_n, int kb, int cb, int tap,
+                                       int cluster, int rank) {
+  const int parts = PAIR ? 2 : cluster;
   const uint16_t mask = static_cast<uint16_t>((1u << cluster) - 1);
-  const int rows = block_n / cluster;             // K-major slice
-  const int atoms = (block_n / 64) / cluster;     // MN-major slice (host guarantees divisibility when cluster > 1)
+  const int rows = block_n / parts;            // K-major slice
+  const int atoms = (block_n / 64) / parts;    // MN-major slice (host guarantees divisibility when parts > 1)
+  const int j0 = rank * atoms;
+  // destination of this CTA's slice: pair mode packs it at the start of the stage, multicast keeps tile order
+  uint8_t* kdst = PAIR ? dst : dst + rank * rows * 128;
   switch (op.mode) {
     case B200PDM_OP_K2D:
-      if (cluster == 1)
-        tma_load_4d(dst, map, bar, kb * kBlockK, n0, z % op.Z1, z / op.Z1);
+      if (PAIR)
+        tma_load_4d_2sm(kdst, map, bar, kb * kBlockK, c.n0 + rank * rows, tc.z1, tc.z2);
+      else if (cluster == 1)
+        tma_load_4d(dst, map, bar, kb * kBlockK, c.n0, tc.z1, tc.z2);
       else
-        tma_load_4d_mc(dst + rank * rows * 128, map, bar, kb * kBlockK, n0 + rank * rows, z % op.Z1, z / op.Z1, mask);
+        tma_load_4d_mc(kdst, map, bar, kb * kBlockK, c.n0 + rank * rows, tc.z1, tc.z2, mask);
       break;
     case B200PDM_OP_MN2D:
-      if (cluster == 1) {
-        for (int j = 0; j < block_n / 64; ++j)
-          tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, kb * kBlockK, z % op.Z1, z / op.Z1);
-      } else {
-        for (int j = rank * atoms; j < (rank + 1) * atoms; ++j)
-          tma_load_4d_mc(dst + j * kAtomBytes, map, bar, n0 + 64 * j, kb * kBlockK, z % op.Z1, z / op.Z1, mask);
+      for (int j = 0; j < atoms; ++j) {
+        if (PAIR)
+          tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), kb * kBlockK, tc.z1, tc.z2);
+        else if (cluster == 1)
+          tma_load_4d(dst + j * kAtomBytes, map, bar, c.n0 + 64 * j, kb * kBlockK, tc.z1, tc.z2);
+        else
+          tma_load_4d_mc(dst + (j0 + j) * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), kb * kBlockK, tc.z1, tc.z2, mask);
       }
       break;
-    case B200PDM_OP_CONV_W: {
-      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
-      if (cluster == 1)
-        tma_load_3d(dst, map, bar, cb * kBlockK, tap, n0);
+    case B200PDM_OP_CONV_W:
+      if (PAIR)
+        tma_load_3d_2sm(kdst, map, bar, cb * kBlockK, tap, c.n0 + rank * rows);
+      else if (cluster == 1)
+        tma_load_3d(dst, map, bar, cb * kBlockK, tap, c.n0);
       else
-        tma_load_3d_mc(dst + rank * rows * 128, map, bar, cb * kBlockK, tap, n0 + rank * rows, mask);
+        tma_load_3d_mc(kdst, map, bar, cb * kBlockK, tap, c.n0 + rank * rows, mask);
       break;
-    }
-    case B200PDM_OP_CONV_WT: {
-      int cb = kb / op.taps, tap = kb - cb * op.taps;  // taps innermost: the 9 shifted reads of a channel block are back to back (L2 reuse)
-      if (cluster == 1) {
-        for (int j = 0; j < block_n / 64; ++j)
-          tma_load_3d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK);
-      } else {
-        for (int j = rank * atoms; j < (rank + 1) * atoms; ++j)
-          tma_load_3d_mc(dst + j * kAtomBytes, map, bar, n0 + 64 * j, tap, cb * kBlockK, mask);
+    case B200PDM_OP_CONV_WT:
+      for (int j = 0; j < atoms; ++j) {
+        if (PAIR)
+          tma_load_3d_2sm(dst + j * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), tap, cb * kBlockK);
+        else if (cluster == 1)
+          tma_load_3d(dst + j * kAtomBytes, map, bar, c.n0 + 64 * j, tap, cb * kBlockK);
+        else
+          tma_load_3d_mc(dst + (j0 + j) * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), tap, cb * kBlockK, mask);
       }
       break;
-    }
     case B200PDM_OP_CONV_ACT_MN: {
-      int kh = 1, kw = 1;
-      if (op.taps == 9) {
-        kh = grp / 3;
-        kw = grp - kh * 3;
-      }
-      int pix0 = kb * kBlockK;
-      int b0 = pix0 / op.HoWo;
-      int rem = pix0 - b0 * op.HoWo;
-      int h0 = rem / op.Wo;
-      int w0 = rem - h0 * op.Wo;
-      if (cluster == 1) {
-        for (int j = 0; j < block_n / 64; ++j)
-          tma_load_4d(dst + j * kAtomBytes, map, bar, n0 + 64 * j, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, b0);
-      } else {
-        for (int j = rank * atoms; j < (rank + 1) * atoms; ++j)
-          tma_load_4d_mc(dst + j * kAtomBytes, map, bar, n0 + 64 * j, w0 * op.stride + kw - 1, h0 * op.stride + kh - 1, b0,
-                         mask);
+      const int pix0 = kb * kBlockK;
+      const int b0 = fdiv(pix0, op.fd_HoWo);
+      const int rem = pix0 - b0 * op.HoWo;
+      const int h0 = fdiv(rem, op.fd_Wo);
+      const int w0 = rem - h0 * op.Wo;
+      const int cw = w0 * op.stride + c.kw - 1, ch = h0 * op.stride + c.kh - 1;
+      for (int j = 0; j < atoms; ++j) {
+        if (PAIR)
+          tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), cw, ch, b0);
+        else if (cluster == 1)
+          tma_load_4d(dst + j * kAtomBytes, map, bar, c.n0 + 64 * j, cw, ch, b0);
+        else
+          tma_load_4d_mc(dst + (j0 + j) * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), cw, ch, b0, mask);
       }
       break;
     }
@@ -384,7 +408,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], (pair && (p.dbg_mode & 6) == 6) ? 2 : 1);   // (diagnostic no-load mode: both CTAs arrive)
       mbar_init(&empty_bar[i], mcast);     // every CTA multicasting into this stage must have consumed it
     }
     for (int i = 0; i < 2; ++i) {
@@ -411,34 +435,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const long long t_kernel0 = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===================== TMA producer =====================
+      // On the critical path of every k-block: no divisions, operand cursors hoisted per tile, and the whole warp runs the
+      // loop so that every TMA operand is warp-uniform (one elected lane issues).
       const uint32_t tx_bytes = kStageABytes + stage_b_bytes;
+      const uint32_t a_bytes = (p.dbg_mode & 2) ? 0 : kStageABytes, b_bytes = (p.dbg_mode & 4) ? 0 : stage_b_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int t = first_tile; t < total_tiles; t += tile_step) {
-        int split = t / tiles_per_split;
-        int r = t - split * tiles_per_split;
-        int z = r / (p.tiles_m_super * tiles_n);
-        r -= z * (p.tiles_m_super * tiles_n);
-        int m_tile = (r / tiles_n) * cluster + rank;
-        int n_tile = r % tiles_n;
-        int grp = n_tile / p.tiles_n_per_group;
-        int nt = n_tile - grp * p.tiles_n_per_group;
-        int kb0 = split * p.kb_per_split;
-        int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
+        const ACursor ac = make_a_cursor(p.a, tc);
+        BCursor bc;
+        bc.n0 = tc.nt * p.block_n;
+        tap_offsets(p.b.taps, tc.grp, 0, &bc.kh, &bc.kw);
+        const int kb0 = tc.split * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        int cb = p.k_taps > 1 ? fdiv(kb0, p.fd_taps) : kb0;   // K = (channel block, tap), taps innermost
+        int tap = kb0 - cb * p.k_taps;
         for (int kb = kb0; kb < kb1; ++kb) {
           DBG_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
-          if (pair) {
-            // both CTAs' loads complete_tx on the LEADER's full barrier, which expects the bytes of the whole pair
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
-            load_a<true>(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
-            load_b_pair(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z, rank);
-          } else {
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
-            load_a<false>(p.a, &tma_a, sA + stage * kStageABytes, &full_bar[stage], m_tile, kb, z);
-            load_b(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], grp, nt, p.block_n, kb, z, mcast, rank);
+          uint8_t* a_dst = sA + stage * kStageABytes;
+          uint8_t* b_dst = sB + stage * stage_b_bytes;
+          if (elect_one()) {
+            if (p.dbg_mode & 6) {   // diagnostics: drop one or both operand streams (results are garbage)
+              if (!pair || rank == 0) mbar_expect_tx(&full_bar[stage], (pair ? 2 : 1) * (a_bytes + b_bytes));
+              else if ((p.dbg_mode & 6) == 6) mbar_arrive_remote(&full_bar[stage], 0);   // keeps the peer in lock step
+              if (a_bytes) load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac, kb, cb, tap);
+              if (b_bytes) load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank);
+            } else {
+              // pair: both CTAs' loads complete_tx on the LEADER's full barrier, which expects the bytes of the whole pair
+              if (!pair || rank == 0) mbar_expect_tx(&full_bar[stage], (pair ? 2 : 1) * tx_bytes);
+              DBG_WAIT(6, load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac, kb, cb, tap);
+                       load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank));
+            }
           }
+          if (++tap == p.k_taps) tap = 0, ++cb;
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -447,55 +479,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && !(pair && rank != 0)) {
+    if (!(pair && rank != 0)) {
       // ===================== MMA issuer (pair mode: leader CTA only) =====================
+      // Warp-uniform loop, one elected lane issues the MMAs and their commits (see elect_one()).
+      const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFF) >> 4, b_lo0 = (smem_u32(sB) & 0x3FFFF) >> 4;
+      const uint32_t a_kstep = A_MN ? (2048 >> 4) : (32 >> 4), b_kstep = B_MN ? (2048 >> 4) : (32 >> 4);
+      const uint64_t a_hi = make_smem_desc_sw128(0, A_MN ? kAtomBytes : 16, 1024);
+      const uint64_t b_hi = make_smem_desc_sw128(0, B_MN ? kAtomBytes : 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = first_tile; t < total_tiles; t += tile_step) {
-        int split = t / tiles_per_split;
-        int kb0 = split * p.kb_per_split;
-        int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        const int split = p.splits > 1 ? fdiv(t, p.fd_tiles_per_split) : 0;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         DBG_WAIT(2, mbar_wait(&tempty_bar[acc], acc_phase ^ 1));
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
           DBG_WAIT(1, mbar_wait(&full_bar[stage], phase));
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * kStageABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * stage_b_bytes);
+          const long long t_iss0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
+          const uint32_t a_lo = a_lo0 + stage * (kStageABytes >> 4), b_lo = b_lo0 + stage * (stage_b_bytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            uint64_t adesc, bdesc;
-            if (A_MN)
-              adesc = make_smem_desc_sw128(a_addr + k * 2048, kAtomBytes, 1024);
-            else
-              adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            if (B_MN)
-              bdesc = make_smem_desc_sw128(b_addr + k * 2048, kAtomBytes, 1024);
-            else
-              bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if ((p.dbg_mode & 1) && k > 0) break;   // diagnostics: a quarter of the MMA work
+              const uint64_t adesc = a_hi | (a_lo + k * a_kstep), bdesc = b_hi | (b_lo + k * b_kstep);
+              if (pair)
+                umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
             if (pair)
-              umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_commit_2sm_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
+            else if (cluster == 1)
+              umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
             else
-              umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_commit_mc(&empty_bar[stage], cmask);  // ... in every CTA of the cluster (their TMAs write here too)
+            if (kb == kb1 - 1) {
+              if (pair)
+                umma_commit_2sm_mc(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
+              else
+                umma_commit(&tfull_bar[acc]);  // accumulator complete
+            }
           }
-          if (pair)
-            umma_commit_2sm_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
-          else if (cluster == 1)
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          else
-            umma_commit_mc(&empty_bar[stage], cmask);  // ... in every CTA of the cluster (their TMAs write here too)
+          if (p.dbg && blockIdx.x == 0 && lane == 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 7), static_cast<unsigned long long>(clock64() - t_iss0));
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (pair)
-          umma_commit_2sm_mc(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
-        else
-          umma_commit(&tfull_bar[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -511,15 +547,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step) {
-      int split = t / tiles_per_split;
-      int r = t - split * tiles_per_split;
-      int z = r / (p.tiles_m_super * tiles_n);
-      r -= z * (p.tiles_m_super * tiles_n);
-      int m_tile = (r / tiles_n) * cluster + rank;
-      int n_tile = r % tiles_n;
-      int grp = n_tile / p.tiles_n_per_group;
-      int nt = n_tile - grp * p.tiles_n_per_group;
-      const int z1 = z % p.a.Z1, z2 = z / p.a.Z1;
+      const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
+      const int m_tile = tc.m_tile, grp = tc.grp, nt = tc.nt, z1 = tc.z1, z2 = tc.z2;
       const int row = m_tile * kBlockM + erow;
       const bool row_ok = row < p.M;
       const int col_base = nt * p.block_n;  // within group
@@ -549,7 +578,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bf16* res_row =
           p.residual ? p.residual + z1 * p.rbs1 + z2 * p.rbs2 + static_cast<int64_t>(row) * p.ldr + col_base : nullptr;
       const float* rb_row =
-          p.rowbias ? p.rowbias + static_cast<int64_t>(row / p.rows_per_group) * p.ld_rowbias + col_base : nullptr;
+          p.rowbias ? p.rowbias + static_cast<int64_t>(fdiv(row, p.fd_rows_per_group)) * p.ld_rowbias + col_base : nullptr;
       const float* bias = p.bias ? p.bias + col_base : nullptr;
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -820,6 +849,8 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
       }
       dev->Wo = op.w_out;
       dev->HoWo = op.h_out * op.w_out;
+      dev->fd_Wo = make_fastdiv(dev->Wo);
+      dev->fd_HoWo = make_fastdiv(dev->HoWo);
       dev->cblks = (op.channels + 63) / 64;
       dims[0] = op.channels, dims[1] = op.w_in, dims[2] = op.h_in, dims[3] = op.batch;
       str[0] = 1, str[1] = op.ld, str[2] = (uint64_t)op.w_in * op.ld, str[3] = (uint64_t)op.h_in * op.w_in * op.ld;
@@ -1030,6 +1061,22 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->N, d->K, Z1, Z2, cluster);
   if (rc) return rc;
 
+  {
+    const int tiles_n = p.tiles_n_per_group * p.n_groups;
+    p.k_taps = (d->a.mode == B200PDM_OP_CONV_ACT && p.a.taps > 1) ? p.a.taps : 1;
+    if ((d->b.mode == B200PDM_OP_CONV_W || d->b.mode == B200PDM_OP_CONV_WT) && p.b.taps != p.k_taps) {
+      set_err("gemm: operand tap counts disagree");
+      return B200PDM_ERR_ARG;
+    }
+    p.fd_tiles_per_split = make_fastdiv((int64_t)p.tiles_m_super * tiles_n * p.Z);
+    p.fd_slab = make_fastdiv((int64_t)p.tiles_m_super * tiles_n);
+    p.fd_tiles_n = make_fastdiv(tiles_n);
+    p.fd_tiles_n_per_group = make_fastdiv(p.tiles_n_per_group);
+    p.fd_Z1 = make_fastdiv(p.a.Z1);
+    p.fd_taps = make_fastdiv(p.k_taps);
+    p.fd_rows_per_group = make_fastdiv(d->rows_per_group > 0 ? d->rows_per_group : 1);
+  }
+
   const int stage_bytes = kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
   int stages = (193 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -1066,6 +1113,10 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), stream);
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
+  {
+    const char* e = getenv("B200PDM_GEMM_DBGMODE");   // diagnostics, re-read every launch so a script can toggle it
+    p.dbg_mode = e ? atoi(e) : 0;
+  }
 
   const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + 16 + 128 + 4 * kEpiBufBytes;
   // epilogue through TMA store (+ TMA residual prefetch) whenever the output is a plain bf16 matrix
@@ -1090,6 +1141,10 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   const long total_tiles = (long)p.tiles_m_super * p.tiles_n_per_group * p.n_groups * p.Z * p.splits;  // per cluster
   const int max_clusters = num_sms() / cluster;
   int grid = static_cast<int>(total_tiles < max_clusters ? total_tiles : max_clusters) * cluster;
+  {
+    const char* e = getenv("B200PDM_GRID");   // diagnostics: cap the number of CTAs
+    if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e) / cluster * cluster;
+  }
 
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1135,8 +1190,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
         int tiles_cta0 = (int)((total_tiles + grid / cluster - 1) / (grid / cluster));
         fprintf(stderr, "[gemm dbg] %s | cta0: total=%lld prod_wait_empty=%lld mma_wait_full=%lld mma_wait_tempty=%lld "
-                "epi_wait_tfull=%lld epi_busy=%lld (~%d tiles, %d kblocks)\n", key, h[4], h[0], h[1], h[2], h[3], h[5],
-                tiles_cta0, p.kb_per_split);
+                "epi_wait_tfull=%lld epi_busy=%lld tma_issue=%lld mma_issue=%lld (~%d tiles, %d kblocks)\n", key, h[4], h[0],
+                h[1], h[2], h[3], h[5], h[6], h[7], tiles_cta0, p.kb_per_split);
       }
       TraceRow& r = g_trace[key];
       r.count++, r.ms += ms;
