@@ -96,7 +96,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
   return B200PDM_OK;
 }
 
-// Unswizzled 2-D bf16 map over an [rows, cols] matrix (pitch ld) with a [128 rows x 32 cols] box: epilogue TMA store
+// 64B-swizzled 2-D bf16 map over an [rows, cols] matrix (pitch ld) with a [128 rows x 32 cols] box: epilogue TMA store
 // of output chunks and TMA load of residual chunks (out-of-range rows / columns are clipped / zero-filled).
 static int make_map_epilogue(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();
@@ -106,7 +106,7 @@ static int make_map_epilogue(CUtensorMap* map, const void* ptr, int64_t rows, in
   cuuint32_t bx[2] = {32, 128}, es[2] = {1, 1};
   if ((gstr[0] % 16) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return B200PDM_ERR_ARG;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_err("cuTensorMapEncodeTiled (epilogue map) failed");
@@ -164,7 +164,8 @@ struct GemmDev {
   int block_n, stages;
   int pair;          // 1: cta_group::2 -- one M=256 MMA per CTA pair, each CTA stages its 128 A rows and HALF of B
   int cluster;       // CTAs per cluster (1, 2, 4): B tile loaded once per cluster and multicast
-  int tiles_m_super; // ceil(tiles_m / cluster)
+  int m_sub;         // 128-row sub-tiles per CTA and tile (2 = "tall" tile: two accumulators share every B stage)
+  int tiles_m_super; // ceil(tiles_m / (cluster * m_sub))
   FastDiv fd_tiles_per_split, fd_slab, fd_tiles_n, fd_tiles_n_per_group, fd_Z1, fd_taps, fd_rows_per_group;
   uint32_t idesc;
   // epilogue
@@ -182,6 +183,7 @@ struct GemmDev {
   long long* dbg;  // optional per-role wait-cycle counters (diagnostics)
   int dbg_mode;    // diagnostics only (B200PDM_GEMM_DBGMODE): 1 = quarter of the MMAs, 2 = no A loads, 4 = no B loads
   int epi_tma;     // bf16 output through smem staging + TMA store (coalesced, asynchronous)
+  int epi_groups;  // epilogue warpgroups: group g takes every epi_groups-th 32-column chunk of a tile
   int res_tma;     // residual chunks prefetched with TMA
 };
 
@@ -203,7 +205,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ti
   c.z1 = z - c.z2 * p.a.Z1;
   const int m_super = fdiv(r, p.fd_tiles_n);
   const int n_tile = r - m_super * tiles_n;
-  c.m_tile = m_super * cluster + rank;
+  c.m_tile = m_super * cluster * p.m_sub + rank;   // sub-tile s of the CTA: + s * cluster
   c.grp = p.n_groups > 1 ? fdiv(n_tile, p.fd_tiles_n_per_group) : 0;
   c.nt = n_tile - c.grp * p.tiles_n_per_group;
   return c;
@@ -239,7 +241,8 @@ constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kAtomBytes = 64 * 64 * 2;              // one [64 k][64 mn] MN-major atom = 8 KiB
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
-constexpr int kThreads = 192;
+constexpr int kMaxEpiGroups = 2;                      // epilogue warpgroups (4 warps each); 2 for epilogue-bound shapes
+constexpr int kMaxThreads = 64 + 128 * kMaxEpiGroups;
 constexpr int kEpiBufBytes = 128 * 32 * 2;  // one [128 rows x 32 cols] bf16 staging chunk
 
 template <bool PAIR>
@@ -261,17 +264,17 @@ __device__ __forceinline__ void ld3(void* dst, const CUtensorMap* map, uint64_t*
 struct ACursor {
   int c1, c2, c3;   // K2D/MN2D: (row0, z1, z2); CONV_ACT: (w0*stride - 1, h0*stride - 1, n0)
 };
-__device__ __forceinline__ ACursor make_a_cursor(const OpDev& op, const TileCoord& tc) {
+__device__ __forceinline__ ACursor make_a_cursor(const OpDev& op, const TileCoord& tc, int m_tile) {
   ACursor c;
   if (op.mode == B200PDM_OP_CONV_ACT) {
-    const int pix0 = tc.m_tile * kBlockM;
+    const int pix0 = m_tile * kBlockM;
     const int n0 = fdiv(pix0, op.fd_HoWo);
     const int rem = pix0 - n0 * op.HoWo;
     const int h0 = fdiv(rem, op.fd_Wo);
     const int w0 = rem - h0 * op.Wo;
     c.c1 = w0 * op.stride - 1, c.c2 = h0 * op.stride - 1, c.c3 = n0;
   } else {
-    c.c1 = tc.m_tile * kBlockM, c.c2 = tc.z1, c.c3 = tc.z2;
+    c.c1 = m_tile * kBlockM, c.c2 = tc.z1, c.c3 = tc.z2;
   }
   return c;
 }
@@ -375,22 +378,24 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
 }
 
 template <int A_MN, int B_MN, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_b_bytes = (PAIR ? p.block_n / 2 : p.block_n) * 128;
+  const int stage_a_bytes = p.m_sub * kStageABytes;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + p.stages * kStageABytes;
+  uint8_t* sB = smem + p.stages * stage_a_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.stages * stage_b_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint64_t* res_full = tempty_bar + 4;                          // [2]
-  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tempty_bar + 6) + 127) & ~uintptr_t(127));
-  uint8_t* sRes = sOut + 2 * kEpiBufBytes;                      // 2 x [128 rows][32 bf16] each
+  uint64_t* res_full = tempty_bar + 4;                          // [epi_groups][2]
+  // staging chunks [128 rows][32 bf16], 64B-swizzled (512-byte pattern): per epilogue warpgroup 2 output + 2 residual
+  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(res_full + 2 * kMaxEpiGroups) + 1023) & ~uintptr_t(1023));
+  uint8_t* sRes = sOut + 2 * p.epi_groups * kEpiBufBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.tiles_n_per_group * p.n_groups;
@@ -413,9 +418,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], pair ? 8 : 4);   // pair: the leader's MMA waits for both CTAs' epilogue warps
-      mbar_init(&res_full[i], 1);
+      mbar_init(&tempty_bar[i], (pair ? 8 : 4) * p.epi_groups);   // pair: the leader's MMA waits for both CTAs' epilogue warps
     }
+    for (int i = 0; i < 2 * kMaxEpiGroups; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -439,13 +444,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       // ===================== TMA producer =====================
       // On the critical path of every k-block: no divisions, operand cursors hoisted per tile, and the whole warp runs the
       // loop so that every TMA operand is warp-uniform (one elected lane issues).
-      const uint32_t tx_bytes = kStageABytes + stage_b_bytes;
-      const uint32_t a_bytes = (p.dbg_mode & 2) ? 0 : kStageABytes, b_bytes = (p.dbg_mode & 4) ? 0 : stage_b_bytes;
+      const uint32_t tx_bytes = stage_a_bytes + stage_b_bytes;
+      const uint32_t a_bytes = (p.dbg_mode & 2) ? 0 : stage_a_bytes, b_bytes = (p.dbg_mode & 4) ? 0 : stage_b_bytes;
       int stage = 0;
       uint32_t phase = 0;
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
-        const ACursor ac = make_a_cursor(p.a, tc);
+        const ACursor ac0 = make_a_cursor(p.a, tc, tc.m_tile);
+        const ACursor ac1 = make_a_cursor(p.a, tc, tc.m_tile + cluster);   // second sub-tile of a tall tile
         BCursor bc;
         bc.n0 = tc.nt * p.block_n;
         tap_offsets(p.b.taps, tc.grp, 0, &bc.kh, &bc.kw);
@@ -455,18 +461,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         int tap = kb0 - cb * p.k_taps;
         for (int kb = kb0; kb < kb1; ++kb) {
           DBG_WAIT(0, mbar_wait(&empty_bar[stage], phase ^ 1));
-          uint8_t* a_dst = sA + stage * kStageABytes;
+          uint8_t* a_dst = sA + stage * stage_a_bytes;
           uint8_t* b_dst = sB + stage * stage_b_bytes;
           if (elect_one()) {
             if (p.dbg_mode & 6) {   // diagnostics: drop one or both operand streams (results are garbage)
               if (!pair || rank == 0) mbar_expect_tx(&full_bar[stage], (pair ? 2 : 1) * (a_bytes + b_bytes));
               else if ((p.dbg_mode & 6) == 6) mbar_arrive_remote(&full_bar[stage], 0);   // keeps the peer in lock step
-              if (a_bytes) load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac, kb, cb, tap);
+              if (a_bytes) {
+                load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac0, kb, cb, tap);
+                if (p.m_sub == 2) load_a<PAIR>(p.a, &tma_a, a_dst + kStageABytes, &full_bar[stage], ac1, kb, cb, tap);
+              }
               if (b_bytes) load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank);
             } else {
               // pair: both CTAs' loads complete_tx on the LEADER's full barrier, which expects the bytes of the whole pair
               if (!pair || rank == 0) mbar_expect_tx(&full_bar[stage], (pair ? 2 : 1) * tx_bytes);
-              DBG_WAIT(6, load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac, kb, cb, tap);
+              DBG_WAIT(6, load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac0, kb, cb, tap);
+                       if (p.m_sub == 2) load_a<PAIR>(p.a, &tma_a, a_dst + kStageABytes, &full_bar[stage], ac1, kb, cb, tap);
                        load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank));
             }
           }
@@ -488,41 +498,48 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint64_t b_hi = make_smem_desc_sw128(0, B_MN ? kAtomBytes : 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      uint32_t unit = 0;   // accumulator units issued so far: unit u lives in TMEM slot u & 1, barrier phase (u >> 1) & 1
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const int split = p.splits > 1 ? fdiv(t, p.fd_tiles_per_split) : 0;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
-        DBG_WAIT(2, mbar_wait(&tempty_bar[acc], acc_phase ^ 1));
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
           DBG_WAIT(1, mbar_wait(&full_bar[stage], phase));
           tc_fence_after();
           const long long t_iss0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
-          const uint32_t a_lo = a_lo0 + stage * (kStageABytes >> 4), b_lo = b_lo0 + stage * (stage_b_bytes >> 4);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              if ((p.dbg_mode & 1) && k > 0) break;   // diagnostics: a quarter of the MMA work
-              const uint64_t adesc = a_hi | (a_lo + k * a_kstep), bdesc = b_hi | (b_lo + k * b_kstep);
-              if (pair)
-                umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else
-                umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          const uint32_t b_lo = b_lo0 + stage * (stage_b_bytes >> 4);
+          for (int sub = 0; sub < p.m_sub; ++sub) {
+            const uint32_t u = unit + sub, acc = u & 1;
+            if (kb == kb0) {   // the epilogue must have drained this accumulator (two units ago)
+              DBG_WAIT(2, mbar_wait(&tempty_bar[acc], ((u >> 1) & 1) ^ 1));
+              tc_fence_after();
             }
-            if (pair)
-              umma_commit_2sm_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
-            else if (cluster == 1)
-              umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-            else
-              umma_commit_mc(&empty_bar[stage], cmask);  // ... in every CTA of the cluster (their TMAs write here too)
-            if (kb == kb1 - 1) {
-              if (pair)
-                umma_commit_2sm_mc(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
-              else
-                umma_commit(&tfull_bar[acc]);  // accumulator complete
+            const uint32_t tmem_d = tmem_base + acc * kAccStride;
+            const uint32_t a_lo = a_lo0 + (stage * stage_a_bytes + sub * kStageABytes) / 16;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if ((p.dbg_mode & 1) && k > 0) break;   // diagnostics: a quarter of the MMA work
+                const uint64_t adesc = a_hi | (a_lo + k * a_kstep), bdesc = b_hi | (b_lo + k * b_kstep);
+                if (pair)
+                  umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                else
+                  umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              }
+              if (sub == p.m_sub - 1) {
+                if (pair)
+                  umma_commit_2sm_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
+                else if (cluster == 1)
+                  umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                else
+                  umma_commit_mc(&empty_bar[stage], cmask);  // ... in every CTA of the cluster (their TMAs write here too)
+              }
+              if (kb == kb1 - 1) {
+                if (pair)
+                  umma_commit_2sm_mc(&tfull_bar[acc], 3);  // accumulator halves complete in both CTAs
+                else
+                  umma_commit(&tfull_bar[acc]);  // accumulator complete
+              }
             }
           }
           if (p.dbg && blockIdx.x == 0 && lane == 0)
@@ -532,23 +549,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             phase ^= 1;
           }
         }
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
+        unit += p.m_sub;
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue warps (2 .. 2 + 4*epi_groups) =====================
+    // A warp may only read the TMEM lane quarter (warp id % 4); each warpgroup covers all four quarters = the 128 rows
+    // of the tile, one row per thread, and takes every epi_groups-th 32-column chunk.
+    if (warp - 2 < 4 * p.epi_groups) {
+    const int wg = (warp - 2) >> 2;
+    const int q = warp & 3;
     const int erow = q * 32 + lane;            // row of the tile this thread owns (== TMEM lane)
-    const bool leader = threadIdx.x == 64;     // first epilogue thread: issues TMA stores / residual prefetches
-    uint32_t chunk_ctr = 0;                    // staged chunks so far (buffer parity + residual barrier phase)
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;   // issues this group's TMA stores / residual prefetches
+    const bool dbg_thread = p.dbg && blockIdx.x == 0 && threadIdx.x == 64;
+    const uint32_t bar_id = 1 + wg;
+    uint8_t* const my_out = sOut + wg * 2 * kEpiBufBytes;
+    uint8_t* const my_res = sRes + wg * 2 * kEpiBufBytes;
+    uint64_t* const my_res_full = res_full + wg * 2;
+    const int swz = (erow >> 1) & 3;           // 64B swizzle: 16-byte slot index ^= bits [7,9) of the byte offset
+    uint32_t chunk_ctr = 0;                    // chunks this group has staged so far (buffer parity + barrier phase)
+    uint32_t unit = 0;                         // accumulator units drained so far (slot = unit & 1, phase = (unit >> 1) & 1)
     for (int t = first_tile; t < total_tiles; t += tile_step) {
       const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
-      const int m_tile = tc.m_tile, grp = tc.grp, nt = tc.nt, z1 = tc.z1, z2 = tc.z2;
+      for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
+      const int acc = unit & 1;
+      const uint32_t acc_phase = (unit >> 1) & 1;
+      const int m_tile = tc.m_tile + sub * cluster, grp = tc.grp, nt = tc.nt, z1 = tc.z1, z2 = tc.z2;
       const int row = m_tile * kBlockM + erow;
       const bool row_ok = row < p.M;
       const int col_base = nt * p.block_n;  // within group
@@ -556,22 +582,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int n_cols = min(p.block_n, n_valid);               // valid columns of this tile
       const int n_staged = p.epi_tma ? (min(n_cols + 31, p.block_n) / 32) : 0;  // full 32-wide chunks via TMA store
 
-      // residual prefetch for the first two staged chunks (before the accumulator is even ready)
+      // residual prefetch for this group's first two staged chunks (before the accumulator is even ready)
       if (p.res_tma && leader) {
-        for (int c = 0; c < min(2, n_staged); ++c) {
-          const uint32_t b = (chunk_ctr + c) & 1;
-          mbar_expect_tx(&res_full[b], kEpiBufBytes);
-          tma_load_2d(sRes + b * kEpiBufBytes, &tma_res, &res_full[b], col_base + c * 32, m_tile * kBlockM);
+        for (int i = 0; i < 2; ++i) {
+          const int c = wg + i * p.epi_groups;
+          if (c >= n_staged) break;
+          const uint32_t b = (chunk_ctr + i) & 1;
+          mbar_expect_tx(&my_res_full[b], kEpiBufBytes);
+          tma_load_2d(my_res + b * kEpiBufBytes, &tma_res, &my_res_full[b], col_base + c * 32, m_tile * kBlockM);
         }
       }
 
-      if (threadIdx.x == 64) {
+      if (dbg_thread) {
         DBG_WAIT(3, mbar_wait(&tfull_bar[acc], acc_phase));
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);
       }
       tc_fence_after();
-      const long long t_epi0 = (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) ? clock64() : 0;
+      const long long t_epi0 = dbg_thread ? clock64() : 0;
 
       const int64_t out_off =
           z1 * p.obs1 + z2 * p.obs2 + static_cast<int64_t>(row) * p.ldo + grp * p.out_group_stride + col_base;
@@ -582,7 +610,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const float* bias = p.bias ? p.bias + col_base : nullptr;
       const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (int c0 = 0; c0 < n_cols; c0 += 32) {
+      for (int c0 = wg * 32; c0 < n_cols; c0 += 32 * p.epi_groups) {
         uint32_t v[32];
         if (p.block_n - c0 >= 32) {
           tmem_ld_32x32(taddr + c0, v);
@@ -613,46 +641,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (staged) {
           const uint32_t b = chunk_ctr & 1;
           if (p.res_tma) {
-            mbar_wait(&res_full[b], (chunk_ctr >> 1) & 1);
-            const uint4* rp = reinterpret_cast<const uint4*>(sRes + b * kEpiBufBytes + erow * 64);
+            mbar_wait(&my_res_full[b], (chunk_ctr >> 1) & 1);
+            const uint8_t* rp = my_res + b * kEpiBufBytes + erow * 64;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const int gg = g;   // (a 4-way bank conflict on 4 accesses per chunk is cheaper than dynamic indexing)
-              uint4 u = rp[gg];
+              uint4 u = *reinterpret_cast<const uint4*>(rp + ((g ^ swz) << 4));
               bf16x8 rv = *reinterpret_cast<bf16x8*>(&u);
               float rf[8];
               unpack8(rv, rf);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[gg * 8 + j] += rf[j];
+              for (int j = 0; j < 8; ++j) f[g * 8 + j] += rf[j];
             }
           } else if (res_row && row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
           }
-          uint4* op = reinterpret_cast<uint4*>(sOut + b * kEpiBufBytes + erow * 64);
+          uint4 pk[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int gg = g;
             float t8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t8[j] = f[gg * 8 + j];
-            bf16x8 pk = pack8(t8);
-            op[gg] = *reinterpret_cast<uint4*>(&pk);
+            for (int j = 0; j < 8; ++j) t8[j] = f[g * 8 + j];
+            bf16x8 h8 = pack8(t8);
+            pk[g] = *reinterpret_cast<uint4*>(&h8);
           }
+          // buffer b was last read by the store issued two chunks ago: at most the previous store may still be pending
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          uint8_t* op = my_out + b * kEpiBufBytes + erow * 64;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(op + ((g ^ swz) << 4)) = pk[g];
           fence_proxy_async();
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // earlier stores left smem
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (leader) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                              reinterpret_cast<uint64_t>(&tma_out)),
-                         "r"(smem_u32(sOut + b * kEpiBufBytes)), "r"(col_base + c0), "r"(m_tile * kBlockM)
+                         "r"(smem_u32(my_out + b * kEpiBufBytes)), "r"(col_base + c0), "r"(m_tile * kBlockM)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            const int cn = (c0 >> 5) + 2;   // residual chunk that will reuse this buffer
+            const int cn = (c0 >> 5) + 2 * p.epi_groups;   // residual chunk that will reuse this buffer
             if (p.res_tma && cn < n_staged) {
-              mbar_expect_tx(&res_full[b], kEpiBufBytes);
-              tma_load_2d(sRes + b * kEpiBufBytes, &tma_res, &res_full[b], col_base + cn * 32, m_tile * kBlockM);
+              mbar_expect_tx(&my_res_full[b], kEpiBufBytes);
+              tma_load_2d(my_res + b * kEpiBufBytes, &tma_res, &my_res_full[b], col_base + cn * 32, m_tile * kBlockM);
             }
           }
           ++chunk_ctr;
@@ -705,7 +736,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64)
+      if (dbg_thread)
         atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), static_cast<unsigned long long>(clock64() - t_epi0));
       if (lane == 0) {
         if (pair && rank != 0)
@@ -713,12 +744,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         else
           mbar_arrive(&tempty_bar[acc]);
       }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output stores are complete
+    }
   }
 
   tc_fence_before();
@@ -773,16 +802,23 @@ static int pair_enabled() {
   return env_pair;
 }
 
-// Tile plan: block_n, split-K factor and pair mode chosen with a small cost model (cycles per CTA slot):
-//   per k-block   max(MMA issue = 2*bn cycles, smem fill = bytes / ~36 B per cycle per SM  [measured L2->SM limit])
-//   per tile      k-blocks * that + fixed pipeline overhead, epilogue overlapped unless it dominates
+// Tile plan: block_n, tall tiles, split-K factor and pair mode chosen with a small cost model (cycles per CTA slot).
+//   per k-block   max(MMA = 2*bn cycles per 128-row sub-tile, smem fill = bytes / ~40 B per cycle per SM  [measured
+//                 L2->SM delivery limit; a tall tile shares each B stage between two sub-tiles])
+//   per tile      k-blocks * that; the epilogue of a normal tile overlaps the next tile's main loop (second TMEM
+//                 accumulator), a tall tile uses both accumulators, so its drain is exposed
 //   total         waves over the 148 (or 74 pair) slots, + a finalize pass when a bf16 output is split along K
 struct Plan {
-  int bn = 0, splits = 1, pair = 0;
+  int bn = 0, splits = 1, pair = 0, m_sub = 1;
   double cost = 1e30;
 };
 static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, int kblocks, bool can_split,
-                      bool split_needs_finalize, int fixed_bn) {
+                      bool split_needs_finalize, int fixed_bn, int fixed_splits = 0) {
+  static int env_msub = -1;
+  if (env_msub < 0) {
+    const char* e = getenv("B200PDM_MSUB");
+    env_msub = e ? atoi(e) : 0;
+  }
   const int g = b_mn ? 64 : 16;
   const int n_pad = static_cast<int>((n + g - 1) / g * g);
   static const int split_cands[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
@@ -795,21 +831,30 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
     const int pair = (pair_enabled() && tiles_m >= 2 && (b_mn ? ((bn / 64) % 2 == 0) : true)) ? 1 : 0;
     const int cs = pair ? 2 : 1;
     const int slots = 148 / cs;
-    const long base_tiles = (long)((tiles_m + cs - 1) / cs) * tiles_n * Z;
-    const double bytes = 16384.0 + (pair ? bn / 2 : bn) * 128.0;
-    const double kcyc = std::max(2.0 * bn, bytes / 36.0);
-    const double epi = 450.0 * ((bn + 31) / 32);
-    for (int s : split_cands) {
-      if (s > 1 && !can_split) break;
-      if (s > 1 && kblocks / s < 8) break;
-      const int kb = (kblocks + s - 1) / s;
-      const long tiles = base_tiles * s;
-      const long waves = (tiles + slots - 1) / slots;
-      double tile_cyc = std::max(kb * kcyc, epi) + 2500.0;
-      if (s > 1) tile_cyc += epi;   // atomics epilogue is slower and less overlapped
-      double cost = waves * tile_cyc;
-      if (s > 1 && split_needs_finalize) cost += 14000.0;
-      if (cost < best.cost) best.bn = bn, best.splits = s, best.pair = pair, best.cost = cost;
+    const double epi_unit = 400.0 * ((bn + 31) / 32) / 2.0;   // two epilogue warpgroups
+    for (int m_sub = 1; m_sub <= 2; ++m_sub) {
+      if (env_msub > 0 && m_sub != env_msub) continue;
+      if (m_sub == 2 && tiles_m < 2 * cs) break;
+      const long base_tiles = (long)((tiles_m + cs * m_sub - 1) / (cs * m_sub)) * tiles_n * Z;
+      const double bytes = 16384.0 * m_sub + (pair ? bn / 2 : bn) * 128.0;
+      const double kcyc = std::max(2.0 * bn * m_sub, bytes / 40.0) + 40.0;
+      for (int s : split_cands) {
+        if (fixed_splits > 0) {
+          if (s != 1) break;
+          s = fixed_splits;
+        } else {
+          if (s > 1 && !can_split) break;
+          if (s > 1 && kblocks / s < 8) break;
+        }
+        const int kb = (kblocks + s - 1) / s;
+        const long tiles = base_tiles * s;
+        const long waves = (tiles + slots - 1) / slots;
+        double tile_cyc = (m_sub == 1 ? std::max(kb * kcyc, epi_unit) : kb * kcyc + 2.0 * epi_unit) + 800.0;
+        if (s > 1) tile_cyc += epi_unit * m_sub;   // atomics epilogue is slower and less overlapped
+        double cost = waves * tile_cyc + (m_sub == 1 ? epi_unit : 0.0);
+        if (s > 1 && split_needs_finalize) cost += 14000.0;
+        if (cost < best.cost) best.bn = bn, best.splits = s, best.pair = pair, best.m_sub = m_sub, best.cost = cost;
+      }
     }
   }
   return best;
@@ -1004,8 +1049,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   const bool scratch_ok = !acc_out && p.Z == 1 && p.n_groups == 1 && (int64_t)d->M * d->N * 4 <= (64ll << 20);
   Plan plan;
   if (d->splits > 1) {   // caller fixed the split factor
-    plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, false, false, d->block_n);
-    plan.splits = d->splits;
+    plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, false, false, d->block_n, d->splits);
   } else {
     plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, acc_out || scratch_ok, !acc_out,
                      d->block_n);
@@ -1053,7 +1097,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   p.pair = plan.pair;
   if (p.pair) cluster = 2;
   p.cluster = p.pair ? 1 : cluster;
-  p.tiles_m_super = cdiv(p.tiles_m, cluster);
+  p.m_sub = plan.m_sub;
+  p.tiles_m_super = cdiv(p.tiles_m, cluster * p.m_sub);
 
   CUtensorMap map_a, map_b;
   int rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2);
@@ -1077,8 +1122,19 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     p.fd_rows_per_group = make_fastdiv(d->rows_per_group > 0 ? d->rows_per_group : 1);
   }
 
-  const int stage_bytes = kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
-  int stages = (193 * 1024) / stage_bytes;
+  {
+    static int env_eg = -1;
+    if (env_eg < 0) {
+      const char* e = getenv("B200PDM_EPI_GROUPS");
+      env_eg = e ? atoi(e) : 0;
+    }
+    p.epi_groups = 2;   // measured: never slower than one group, up to 1.4x faster on small-K shapes
+    if (env_eg == 1 || env_eg == 2) p.epi_groups = env_eg;
+  }
+  const int epi_bytes = 4 * p.epi_groups * kEpiBufBytes;
+  const int stage_bytes = p.m_sub * kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
+  const int fixed_bytes = 1024 + (2 * 8 + 6 + 2 * kMaxEpiGroups) * 8 + 16 + 1024 + epi_bytes;
+  int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   static int env_stages = -1;
   if (env_stages < 0) {
@@ -1113,12 +1169,13 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), stream);
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
+  const size_t smem = (size_t)fixed_bytes + (size_t)stages * stage_bytes;
+  const int threads = 64 + 128 * p.epi_groups;
   {
     const char* e = getenv("B200PDM_GEMM_DBGMODE");   // diagnostics, re-read every launch so a script can toggle it
     p.dbg_mode = e ? atoi(e) : 0;
   }
 
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 6) * 8 + 16 + 128 + 4 * kEpiBufBytes;
   // epilogue through TMA store (+ TMA residual prefetch) whenever the output is a plain bf16 matrix
   CUtensorMap map_out, map_res;
   memset(&map_out, 0, sizeof(map_out));
@@ -1158,11 +1215,11 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       cudaEventRecord(t0, stream);
     }
     if (cluster == 1) {
-      kern<<<grid, kThreads, smem, stream>>>(map_a, map_b, map_out, map_res, p);
+      kern<<<grid, threads, smem, stream>>>(map_a, map_b, map_out, map_res, p);
     } else {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+      cfg.gridDim = dim3(grid), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
@@ -1182,9 +1239,9 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       cudaEventElapsedTime(&ms, t0, t1);
       char key[256];
       const double kk = (double)kblocks * 64;
-      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d split=%d tiles=%ld grid=%d stages=%d cl=%d", d->a.mode,
-               d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.splits, total_tiles, grid, stages,
-               cluster);
+      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d msub=%d split=%d tiles=%ld grid=%d stages=%d cl=%d",
+               d->a.mode, d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.m_sub, p.splits,
+               total_tiles, grid, stages, cluster);
       if (p.dbg) {
         long long h[8];
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
