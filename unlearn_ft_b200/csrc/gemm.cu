@@ -96,25 +96,6 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
   return B200PDM_OK;
 }
 
-// 64B-swizzled 2-D bf16 map over an [rows, cols] matrix (pitch ld) with a [128 rows x 32 cols] box: epilogue TMA store
-// of output chunks and TMA load of residual chunks (out-of-range rows / columns are clipped / zero-filled).
-static int make_map_epilogue(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return B200PDM_ERR_DRIVER;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t bx[2] = {32, 128}, es[2] = {1, 1};
-  if ((gstr[0] % 16) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return B200PDM_ERR_ARG;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_err("cuTensorMapEncodeTiled (epilogue map) failed");
-    return B200PDM_ERR_DRIVER;
-  }
-  return B200PDM_OK;
-}
-
 int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
                     const uint32_t* box) {
   return make_map(map, ptr, rank, dims, strides_el, box, nullptr);
@@ -182,9 +163,7 @@ struct GemmDev {
   int accumulate;
   long long* dbg;  // optional per-role wait-cycle counters (diagnostics)
   int dbg_mode;    // diagnostics only (B200PDM_GEMM_DBGMODE): 1 = quarter of the MMAs, 2 = no A loads, 4 = no B loads
-  int epi_tma;     // bf16 output through smem staging + TMA store (coalesced, asynchronous)
   int epi_groups;  // epilogue warpgroups: group g takes every epi_groups-th 32-column chunk of a tile
-  int res_tma;     // residual chunks prefetched with TMA
 };
 
 // Where a tile sits: decoded once per tile by each role.
@@ -243,7 +222,6 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kMaxEpiGroups = 2;                      // epilogue warpgroups (4 warps each); 2 for epilogue-bound shapes
 constexpr int kMaxThreads = 64 + 128 * kMaxEpiGroups;
-constexpr int kEpiBufBytes = 128 * 32 * 2;  // one [128 rows x 32 cols] bf16 staging chunk
 
 template <bool PAIR>
 __device__ __forceinline__ void ld4(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -379,8 +357,7 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
 
 template <int A_MN, int B_MN, bool PAIR>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_b_bytes = (PAIR ? p.block_n / 2 : p.block_n) * 128;
@@ -392,10 +369,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint64_t* res_full = tempty_bar + 4;                          // [epi_groups][2]
-  // staging chunks [128 rows][32 bf16], 64B-swizzled (512-byte pattern): per epilogue warpgroup 2 output + 2 residual
-  uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(res_full + 2 * kMaxEpiGroups) + 1023) & ~uintptr_t(1023));
-  uint8_t* sRes = sOut + 2 * p.epi_groups * kEpiBufBytes;
+  // per epilogue warp: 1 KiB slice holding (bias + time-embedding row bias) of the tile's columns, read back as broadcasts
+  uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tempty_bar + 4) + 127) & ~uintptr_t(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.tiles_n_per_group * p.n_groups;
@@ -420,7 +395,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], (pair ? 8 : 4) * p.epi_groups);   // pair: the leader's MMA waits for both CTAs' epilogue warps
     }
-    for (int i = 0; i < 2 * kMaxEpiGroups; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -555,198 +529,209 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else {
     // ===================== epilogue warps (2 .. 2 + 4*epi_groups) =====================
     // A warp may only read the TMEM lane quarter (warp id % 4); each warpgroup covers all four quarters = the 128 rows
-    // of the tile, one row per thread, and takes every epi_groups-th 32-column chunk.
-    if (warp - 2 < 4 * p.epi_groups) {
-    const int wg = (warp - 2) >> 2;
-    const int q = warp & 3;
-    const int erow = q * 32 + lane;            // row of the tile this thread owns (== TMEM lane)
-    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;   // issues this group's TMA stores / residual prefetches
-    const bool dbg_thread = p.dbg && blockIdx.x == 0 && threadIdx.x == 64;
-    const uint32_t bar_id = 1 + wg;
-    uint8_t* const my_out = sOut + wg * 2 * kEpiBufBytes;
-    uint8_t* const my_res = sRes + wg * 2 * kEpiBufBytes;
-    uint64_t* const my_res_full = res_full + wg * 2;
-    const int swz = (erow >> 1) & 3;           // 64B swizzle: 16-byte slot index ^= bits [7,9) of the byte offset
-    uint32_t chunk_ctr = 0;                    // chunks this group has staged so far (buffer parity + barrier phase)
-    uint32_t unit = 0;                         // accumulator units drained so far (slot = unit & 1, phase = (unit >> 1) & 1)
-    for (int t = first_tile; t < total_tiles; t += tile_step) {
-      const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
-      for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
-      const int acc = unit & 1;
-      const uint32_t acc_phase = (unit >> 1) & 1;
-      const int m_tile = tc.m_tile + sub * cluster, grp = tc.grp, nt = tc.nt, z1 = tc.z1, z2 = tc.z2;
-      const int row = m_tile * kBlockM + erow;
-      const bool row_ok = row < p.M;
-      const int col_base = nt * p.block_n;  // within group
-      const int n_valid = p.n_per_group - col_base;
-      const int n_cols = min(p.block_n, n_valid);               // valid columns of this tile
-      const int n_staged = p.epi_tma ? (min(n_cols + 31, p.block_n) / 32) : 0;  // full 32-wide chunks via TMA store
-
-      // residual prefetch for this group's first two staged chunks (before the accumulator is even ready)
-      if (p.res_tma && leader) {
-        for (int i = 0; i < 2; ++i) {
-          const int c = wg + i * p.epi_groups;
-          if (c >= n_staged) break;
-          const uint32_t b = (chunk_ctr + i) & 1;
-          mbar_expect_tx(&my_res_full[b], kEpiBufBytes);
-          tma_load_2d(my_res + b * kEpiBufBytes, &tma_res, &my_res_full[b], col_base + c * 32, m_tile * kBlockM);
-        }
-      }
-
-      if (dbg_thread) {
-        DBG_WAIT(3, mbar_wait(&tfull_bar[acc], acc_phase));
-      } else {
-        mbar_wait(&tfull_bar[acc], acc_phase);
-      }
-      tc_fence_after();
-      const long long t_epi0 = dbg_thread ? clock64() : 0;
-
-      const int64_t out_off =
-          z1 * p.obs1 + z2 * p.obs2 + static_cast<int64_t>(row) * p.ldo + grp * p.out_group_stride + col_base;
-      const bf16* res_row =
-          p.residual ? p.residual + z1 * p.rbs1 + z2 * p.rbs2 + static_cast<int64_t>(row) * p.ldr + col_base : nullptr;
-      const float* rb_row =
-          p.rowbias ? p.rowbias + static_cast<int64_t>(fdiv(row, p.fd_rows_per_group)) * p.ld_rowbias + col_base : nullptr;
-      const float* bias = p.bias ? p.bias + col_base : nullptr;
-      const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
-
-      for (int c0 = wg * 32; c0 < n_cols; c0 += 32 * p.epi_groups) {
-        uint32_t v[32];
-        if (p.block_n - c0 >= 32) {
-          tmem_ld_32x32(taddr + c0, v);
-        } else {  // block_n % 32 == 16 tail
-          uint32_t h[16];
-          tmem_ld_32x16(taddr + c0, h);
+    // of a sub-tile and takes every epi_groups-th 32-column chunk.  Each lane owns one output row: it pulls 32 fp32
+    // columns out of TMEM, applies alpha / bias / time-embedding row bias / residual and writes its 64 bytes of bf16 as
+    // two 256-bit stores (whole 32-byte sectors; the neighbouring chunk, handled by the other warpgroup at the same time,
+    // completes the 128-byte line in L2).  Deliberately no shared memory: TMA fills + UMMA operand reads already use
+    // ~all of the smem bandwidth, and every staged variant (TMA store, warp transpose) measured ~1000 cycles per chunk
+    // waiting for smem behind them.
+    {
+      const int wg = (warp - 2) >> 2;
+      const int q = warp & 3;
+      const bool dbg_thread = p.dbg && blockIdx.x == 0 && threadIdx.x == 64;
+      const int out_el = p.out_fp32 ? 4 : 2;
+      auto aligned_to = [&](int bytes) {   // every chunk start of every row is `bytes`-aligned
+        return ((reinterpret_cast<uintptr_t>(p.out) % bytes) == 0) && ((p.ldo * out_el) % bytes == 0) &&
+               ((p.obs1 * out_el) % bytes == 0) && ((p.obs2 * out_el) % bytes == 0) &&
+               ((p.out_group_stride * out_el) % bytes == 0) && ((p.block_n * out_el) % bytes == 0);
+      };
+      const bool out_v32 = aligned_to(32), out_v16 = aligned_to(16);
+      const bool res_v32 = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 31) == 0) && (p.ldr % 16 == 0) &&
+                           (p.rbs1 % 16 == 0) && (p.rbs2 % 16 == 0) && (p.block_n % 16 == 0);
+      const bool rb_vec = p.rowbias && ((reinterpret_cast<uintptr_t>(p.rowbias) & 15) == 0) && (p.ld_rowbias % 4 == 0);
+      // Column offsets shared by all 32 rows of the warp (bias, and the row bias when a warp never straddles two row
+      // groups) are summed once per unit into the warp's smem slice; per-lane loads of one address are far slower.
+      const bool rb_uniform = p.rowbias && (p.rows_per_group % 32 == 0);
+      const bool use_cb = p.bias || rb_uniform;
+      const uint32_t cb_s = smem_u32(sEpi + (warp - 2) * 1024);
+      uint32_t unit = 0;   // accumulator units drained so far (slot = unit & 1, phase = (unit >> 1) & 1)
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
+        const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
+        const int col_base = tc.nt * p.block_n;                // within the N group
+        const int n_cols = min(p.block_n, p.n_per_group - col_base);   // valid columns of this tile
+        for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
+          const int acc = unit & 1;
+          const uint32_t acc_phase = (unit >> 1) & 1;
+          const int m_tile = tc.m_tile + sub * cluster;
+          const int row = m_tile * kBlockM + q * 32 + lane;      // own row (TMEM lane)
+          const bool row_ok = row < p.M;
+          const int64_t out_off =
+              tc.z1 * p.obs1 + tc.z2 * p.obs2 + tc.grp * p.out_group_stride + static_cast<int64_t>(row) * p.ldo + col_base;
+          const bf16* res_row = (p.residual && row_ok)
+                                    ? p.residual + tc.z1 * p.rbs1 + tc.z2 * p.rbs2 + static_cast<int64_t>(row) * p.ldr + col_base
+                                    : nullptr;
+          const float* rb_row = (p.rowbias && !rb_uniform && row_ok)
+                                    ? p.rowbias + static_cast<int64_t>(fdiv(row, p.fd_rows_per_group)) * p.ld_rowbias + col_base
+                                    : nullptr;
+          if (use_cb) {
+            const int row_w = m_tile * kBlockM + q * 32;   // first row of the warp
+            const float* rbw = (rb_uniform && row_w < p.M)
+                                   ? p.rowbias + static_cast<int64_t>(fdiv(row_w, p.fd_rows_per_group)) * p.ld_rowbias + col_base
+                                   : nullptr;
+            float b8[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = h[j];
-#pragma unroll
-          for (int j = 16; j < 32; ++j) v[j] = 0;
-        }
-        tmem_ld_wait();
-        const int nv = min(min(32, p.block_n - c0), n_valid - c0);  // valid columns in this chunk
-        const bool staged = (c0 >> 5) < n_staged;                   // else: direct (masked) stores
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        if (bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) f[j] += __ldg(bias + c0 + j);
-        }
-        if (rb_row && row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) f[j] += __ldg(rb_row + c0 + j);
-        }
-        if (staged) {
-          const uint32_t b = chunk_ctr & 1;
-          if (p.res_tma) {
-            mbar_wait(&my_res_full[b], (chunk_ctr >> 1) & 1);
-            const uint8_t* rp = my_res + b * kEpiBufBytes + erow * 64;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 u = *reinterpret_cast<const uint4*>(rp + ((g ^ swz) << 4));
-              bf16x8 rv = *reinterpret_cast<bf16x8*>(&u);
-              float rf[8];
-              unpack8(rv, rf);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[g * 8 + j] += rf[j];
+            for (int j = 0; j < 8; ++j) {
+              const int c = lane * 8 + j;
+              float x = 0.f;
+              if (c < n_cols) {
+                if (p.bias) x = __ldg(p.bias + col_base + c);
+                if (rbw) x += __ldg(rbw + c);
+              }
+              b8[j] = x;
             }
-          } else if (res_row && row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
+            __syncwarp();   // previous unit's readers are done
+            sts128(cb_s + lane * 32, __float_as_uint(b8[0]), __float_as_uint(b8[1]), __float_as_uint(b8[2]), __float_as_uint(b8[3]));
+            sts128(cb_s + lane * 32 + 16, __float_as_uint(b8[4]), __float_as_uint(b8[5]), __float_as_uint(b8[6]), __float_as_uint(b8[7]));
+            __syncwarp();
           }
-          uint4 pk[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float t8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t8[j] = f[g * 8 + j];
-            bf16x8 h8 = pack8(t8);
-            pk[g] = *reinterpret_cast<uint4*>(&h8);
+
+          if (dbg_thread) {
+            DBG_WAIT(3, mbar_wait(&tfull_bar[acc], acc_phase));
+          } else {
+            mbar_wait(&tfull_bar[acc], acc_phase);
           }
-          // buffer b was last read by the store issued two chunks ago: at most the previous store may still be pending
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          uint8_t* op = my_out + b * kEpiBufBytes + erow * 64;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(op + ((g ^ swz) << 4)) = pk[g];
-          fence_proxy_async();
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (leader) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                             reinterpret_cast<uint64_t>(&tma_out)),
-                         "r"(smem_u32(my_out + b * kEpiBufBytes)), "r"(col_base + c0), "r"(m_tile * kBlockM)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            const int cn = (c0 >> 5) + 2 * p.epi_groups;   // residual chunk that will reuse this buffer
-            if (p.res_tma && cn < n_staged) {
-              mbar_expect_tx(&my_res_full[b], kEpiBufBytes);
-              tma_load_2d(my_res + b * kEpiBufBytes, &tma_res, &my_res_full[b], col_base + cn * 32, m_tile * kBlockM);
+          tc_fence_after();
+          const long long t_epi0 = dbg_thread ? clock64() : 0;
+          const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+          for (int c0 = wg * 32; c0 < n_cols; c0 += 32 * p.epi_groups) {
+            const int nv = min(32, n_cols - c0);                  // valid columns in this chunk
+            if (p.dbg_mode & 128) continue;
+            // ---- residual does not depend on the accumulator: issue its loads first
+            uint32_t resv[2][8];
+            const bool res_fast = res_row && res_v32 && nv == 32;
+            if (res_fast) {
+              ldg256(res_row + c0, resv[0]);
+              ldg256(res_row + c0 + 16, resv[1]);
             }
-          }
-          ++chunk_ctr;
-        } else if (row_ok && nv > 0) {
-          if (res_row) {
+            // ---- TMEM -> registers (lane == row).  (Issuing the next chunk's load early was measured: no gain.)
+            uint32_t v[32];
+            if (p.block_n - c0 >= 32) {
+              tmem_ld_32x32(taddr + c0, v);
+            } else {  // block_n % 32 == 16 tail
+              tmem_ld_32x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
-          }
-          if (p.out_fp32) {
-            float* o = reinterpret_cast<float*>(p.out) + out_off + c0;
-            if (p.accumulate) {
-              if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              for (int jj = 16; jj < 32; ++jj) v[jj] = 0;
+            }
+            tmem_ld_wait();
+            float f[32];
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + g * 4), "f"(f[g * 4]),
-                               "f"(f[g * 4 + 1]), "f"(f[g * 4 + 2]), "f"(f[g * 4 + 3])
-                               : "memory");
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+            if (use_cb) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = lds128f(cb_s + (c0 + g * 4) * 4);
+                f[4 * g] += b4.x, f[4 * g + 1] += b4.y, f[4 * g + 2] += b4.z, f[4 * g + 3] += b4.w;
+              }
+            }
+            if (rb_row) {
+              if (rb_vec && nv == 32) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb_row + c0) + g);
+                  f[4 * g] += b4.x, f[4 * g + 1] += b4.y, f[4 * g + 2] += b4.z, f[4 * g + 3] += b4.w;
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (j < nv) atomicAdd(o + j, f[j]);
+                  if (j < nv) f[j] += __ldg(rb_row + c0 + j);
               }
-            } else if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            }
+            if (res_fast) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-            } else {
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t w = resv[j >> 3][j & 7];
+                f[2 * j] += __uint_as_float(w << 16);
+                f[2 * j + 1] += __uint_as_float(w & 0xffff0000u);
+              }
+            } else if (res_row) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < nv) o[j] = f[j];
+                if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
             }
-          } else {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + c0;
-            if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            if (!row_ok || (p.dbg_mode & 8)) continue;
+
+            if (!p.out_fp32) {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + c0;
+              if (nv == 32 && out_v16) {
+                uint32_t pk[16];
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float t8[8];
+                for (int j = 0; j < 16; ++j) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                  pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                if (out_v32) {
+                  const uint32_t lo[8] = {pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]};
+                  const uint32_t hi[8] = {pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]};
+                  stg256(o, lo);
+                  stg256(o + 16, hi);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t8[j] = f[g * 8 + j];
-                *reinterpret_cast<bf16x8*>(o + g * 8) = pack8(t8);
+                  for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) o[j] = __float2bfloat16(f[j]);
               }
             } else {
+              float* o = reinterpret_cast<float*>(p.out) + out_off + c0;
+              if (nv == 32 && out_v16) {
+                if (p.accumulate) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nv) o[j] = __float2bfloat16(f[j]);
+                  for (int g = 0; g < 8; ++g)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + g * 4), "f"(f[g * 4]),
+                                 "f"(f[g * 4 + 1]), "f"(f[g * 4 + 2]), "f"(f[g * 4 + 3])
+                                 : "memory");
+                } else if (out_v32) {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) {
+                    const uint32_t w8[8] = {__float_as_uint(f[8 * g]),     __float_as_uint(f[8 * g + 1]), __float_as_uint(f[8 * g + 2]),
+                                            __float_as_uint(f[8 * g + 3]), __float_as_uint(f[8 * g + 4]), __float_as_uint(f[8 * g + 5]),
+                                            __float_as_uint(f[8 * g + 6]), __float_as_uint(f[8 * g + 7])};
+                    stg256(o + g * 8, w8);
+                  }
+                } else {
+#pragma unroll
+                  for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (j < nv) {
+                    if (p.accumulate)
+                      atomicAdd(o + j, f[j]);
+                    else
+                      o[j] = f[j];
+                  }
+                }
+              }
             }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (dbg_thread)
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), static_cast<unsigned long long>(clock64() - t_epi0));
+          if (lane == 0) {
+            if (pair && rank != 0)
+              mbar_arrive_remote(&tempty_bar[acc], 0);   // tell the leader CTA's MMA thread
+            else
+              mbar_arrive(&tempty_bar[acc]);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (dbg_thread)
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), static_cast<unsigned long long>(clock64() - t_epi0));
-      if (lane == 0) {
-        if (pair && rank != 0)
-          mbar_arrive_remote(&tempty_bar[acc], 0);   // tell the leader CTA's MMA thread
-        else
-          mbar_arrive(&tempty_bar[acc]);
-      }
-      }
-    }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output stores are complete
     }
   }
 
@@ -849,7 +834,7 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
         const int kb = (kblocks + s - 1) / s;
         const long tiles = base_tiles * s;
         const long waves = (tiles + slots - 1) / slots;
-        double tile_cyc = (m_sub == 1 ? std::max(kb * kcyc, epi_unit) : kb * kcyc + 2.0 * epi_unit) + 800.0;
+        double tile_cyc = (m_sub == 1 ? std::max(kb * kcyc, epi_unit) : kb * kcyc + 4.0 * epi_unit) + 800.0;
         if (s > 1) tile_cyc += epi_unit * m_sub;   // atomics epilogue is slower and less overlapped
         double cost = waves * tile_cyc + (m_sub == 1 ? epi_unit : 0.0);
         if (s > 1 && split_needs_finalize) cost += 14000.0;
@@ -1131,9 +1116,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     p.epi_groups = 2;   // measured: never slower than one group, up to 1.4x faster on small-K shapes
     if (env_eg == 1 || env_eg == 2) p.epi_groups = env_eg;
   }
-  const int epi_bytes = 4 * p.epi_groups * kEpiBufBytes;
   const int stage_bytes = p.m_sub * kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
-  const int fixed_bytes = 1024 + (2 * 8 + 6 + 2 * kMaxEpiGroups) * 8 + 16 + 1024 + epi_bytes;
+  const int fixed_bytes = 1024 + (2 * 8 + 6) * 8 + 64 + 128 + 4 * p.epi_groups * 1024;
   int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
   if (stages > 8) stages = 8;
   static int env_stages = -1;
@@ -1176,25 +1160,6 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     p.dbg_mode = e ? atoi(e) : 0;
   }
 
-  // epilogue through TMA store (+ TMA residual prefetch) whenever the output is a plain bf16 matrix
-  CUtensorMap map_out, map_res;
-  memset(&map_out, 0, sizeof(map_out));
-  memset(&map_res, 0, sizeof(map_res));
-  p.epi_tma = (!d->out_fp32 && !d->accumulate && p.Z == 1 && p.n_groups == 1 && (d->ldo % 8 == 0) &&
-               ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0)) ? 1 : 0;
-  static int env_epi = -1;
-  if (env_epi < 0) env_epi = getenv("B200PDM_NO_EPI_TMA") ? 0 : 1;
-  if (!env_epi) p.epi_tma = 0;
-  p.res_tma = 0;
-  if (p.epi_tma) {
-    rc = make_map_epilogue(&map_out, d->out, d->M, p.n_per_group, d->ldo);
-    if (rc) return rc;
-    if (d->residual && (d->ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0)) {
-      rc = make_map_epilogue(&map_res, d->residual, d->M, p.n_per_group, d->ldr);
-      if (rc) return rc;
-      p.res_tma = 1;
-    }
-  }
   const long total_tiles = (long)p.tiles_m_super * p.tiles_n_per_group * p.n_groups * p.Z * p.splits;  // per cluster
   const int max_clusters = num_sms() / cluster;
   int grid = static_cast<int>(total_tiles < max_clusters ? total_tiles : max_clusters) * cluster;
@@ -1215,7 +1180,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       cudaEventRecord(t0, stream);
     }
     if (cluster == 1) {
-      kern<<<grid, threads, smem, stream>>>(map_a, map_b, map_out, map_res, p);
+      kern<<<grid, threads, smem, stream>>>(map_a, map_b, p);
     } else {
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
@@ -1224,7 +1189,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr, cfg.numAttrs = 1;
-      cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_out, map_res, p);
+      cudaLaunchKernelEx(&cfg, kern, map_a, map_b, p);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) {
