@@ -27,8 +27,9 @@ def _worker(rank, world, port, out):
     model = SimpleNamespace(arena=SimpleNamespace(grad=grad.clone(), numel=1000))
     red = GradReducer(model)
     assert red.world == world
-    red.reduce_range(0, 300)          # bucketed, as issued per U-Net block
-    red.reduce_range(300, 1000)
+    red.reduce_range(600, 1000)       # bucketed, as issued per U-Net block from its backward (last block first)
+    red.reduce_range(100, 300)
+    red.reduce_all()                  # the complement: [0,100) and [300,600), each exactly once
     red.wait()
     out[rank] = model.arena.grad.clone()
     dist.destroy_process_group()
@@ -51,3 +52,29 @@ def test_world1_is_noop():
     red = GradReducer(SimpleNamespace(arena=SimpleNamespace(grad=g.clone(), numel=10)))
     red.reduce_all(), red.wait()
     assert torch.equal(red.arena.grad, g)
+
+
+def test_block_buckets_partition_the_arena():
+    """Per-block buckets (fired from each block's backward) are disjoint, contiguous arena slices; together with the
+    complement handled by reduce_all() every gradient element is exchanged exactly once."""
+    from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModelPruned
+    from unlearn_ft_b200.pdm.models.unet.unet_2d_conditional import SD21_CONFIG, structure_from_config
+    from unlearn_ft_b200.pdm.training.trainer import GradReducer
+    torch.manual_seed(0)
+    av = HyperStructure.get_random_arch_vector(0.55, structure_from_config(SD21_CONFIG))
+    model = UNet2DConditionModelPruned(arch_vector=av, device="meta", seed=None)
+    buckets = GradReducer.block_buckets(model)
+    names = {attr for (_, attr) in buckets}
+    assert names == {"_grad_ready", "_grad_ready_head", "_grad_ready_stem"}
+    assert len(buckets) == 4 + 1 + 4 + 2                      # down x4, mid, up x4, head, stem
+    spans = sorted(buckets.values())
+    for (l0, h0), (l1, h1) in zip(spans, spans[1:]):
+        assert h0 <= l1                                        # disjoint
+    covered = sum(h - l for l, h in spans)
+    assert covered >= 0.999 * model.arena.numel                # (alignment padding aside) the blocks own everything
+    for (mod, attr), (lo, hi) in buckets.items():              # every parameter of a block lies inside its bucket
+        if attr != "_grad_ready":
+            continue
+        for sub in mod.modules():
+            for a, (o, n) in getattr(sub, "_arena_off", {}).items():
+                assert lo <= o and o + n <= hi

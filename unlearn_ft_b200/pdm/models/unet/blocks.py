@@ -34,10 +34,11 @@ class _BlockFn(torch.autograd.Function):
     activation input requires grad (the network input does not)."""
 
     @staticmethod
-    def forward(ctx, runner, need_bwd, anchor, *tensors):
+    def forward(ctx, runner, need_bwd, anchor, owner, *tensors):
         outs, bwd = runner(need_bwd, *tensors)
         ctx.bwd = bwd
         ctx.n_in = len(tensors)
+        ctx.owner = owner
         return tuple(outs)
 
     @staticmethod
@@ -46,16 +47,22 @@ class _BlockFn(torch.autograd.Function):
             raise RuntimeError("backward through a block that ran without gradient bookkeeping")
         in_grads = ctx.bwd(*grads)
         ctx.bwd = None  # release saved activations
+        # this block's parameter gradients are final now: let the data-parallel reducer start on them while the rest of
+        # the backward pass runs (GradReducer installs the callbacks; None on a single GPU)
+        cb = None if ctx.owner is None else getattr(ctx.owner[0], ctx.owner[1], None)
+        if cb is not None:
+            cb()
         in_grads = tuple(in_grads) + (None,) * (ctx.n_in - len(in_grads))
-        return (None, None, None) + in_grads
+        return (None, None, None, None) + in_grads
 
 
-def run_block(runner, anchor, *tensors):
+def run_block(runner, anchor, *tensors, owner=None):
+    """`owner` = (module, attribute name) of an optional zero-argument callback fired after the block's backward."""
     need_bwd = torch.is_grad_enabled() and anchor is not None and anchor.requires_grad
     if not need_bwd:
         outs, _ = runner(False, *tensors)
         return tuple(outs)
-    return _BlockFn.apply(runner, True, anchor, *tensors)
+    return _BlockFn.apply(runner, True, anchor, owner, *tensors)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -407,7 +414,7 @@ class CrossAttnDownBlock2DWidthHalfDepthGated(_UNetBlock):
 
             return res4, bwd
 
-        outs = run_block(runner, self._anchor, hidden_states, temb, encoder_hidden_states)
+        outs = run_block(runner, self._anchor, hidden_states, temb, encoder_hidden_states, owner=(self, "_grad_ready"))
         return outs[-1], tuple(outs)
 
 
@@ -459,7 +466,7 @@ class UNetMidBlock2DCrossAttnWidthGated(_UNetBlock):
 
             return out, bwd
 
-        return run_block(runner, self._anchor, hidden_states, temb, encoder_hidden_states)[0]
+        return run_block(runner, self._anchor, hidden_states, temb, encoder_hidden_states, owner=(self, "_grad_ready"))[0]
 
 
 class CrossAttnUpBlock2DWidthHalfDepthGated(_UNetBlock):
@@ -523,7 +530,7 @@ class CrossAttnUpBlock2DWidthHalfDepthGated(_UNetBlock):
 
             return out, bwd
 
-        return run_block(runner, self._anchor, hidden_states, temb, encoder_hidden_states, *skips)[0]
+        return run_block(runner, self._anchor, hidden_states, temb, encoder_hidden_states, *skips, owner=(self, "_grad_ready"))[0]
 
 
 class UpBlock2DWidthHalfDepthGated(CrossAttnUpBlock2DWidthHalfDepthGated):

@@ -345,7 +345,7 @@ class UNet2DConditionModelGated(nn.Module):
 
             return outs, bwd
 
-        return run_block(runner, self._anchor, sample, timesteps)
+        return run_block(runner, self._anchor, sample, timesteps, owner=(self, "_grad_ready_stem"))
 
     @staticmethod
     @torch.no_grad()
@@ -373,7 +373,7 @@ class UNet2DConditionModelGated(nn.Module):
 
             return out, bwd
 
-        return run_block(runner, self._anchor, x4)[0]
+        return run_block(runner, self._anchor, x4, owner=(self, "_grad_ready_head"))[0]
 
     def forward(self, sample, timestep, encoder_hidden_states, return_dict: bool = True, **kwargs):
         """Reference :1417-1728 for the SD-2.1 configuration."""

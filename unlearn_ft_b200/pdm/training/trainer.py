@@ -16,6 +16,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -177,20 +179,57 @@ class ConstantWithWarmup:
 
 class GradReducer:
     """Data-parallel gradient averaging over NCCL (the reference wraps the student in torch DDP via accelerate,
-    trainer.py:122-129,2257-2260).  The flat fp32 gradient buffer is all-reduced in per-U-Net-block buckets on a
-    side stream; `reduce_range` is called from each block's backward so communication overlaps the remaining
-    backward compute.  With world_size == 1 everything is a no-op."""
+    trainer.py:122-129,2257-2260).  The flat fp32 gradient arena is all-reduced in per-U-Net-block buckets on a side
+    stream: every top-level block fires `reduce_range` for its own slice of the arena as soon as its backward has
+    finished, so communication overlaps the remaining backward compute; `reduce_all` (after backward) covers whatever
+    no block claimed.  With world_size == 1 everything is a no-op."""
 
-    def __init__(self, model, group=None):
+    def __init__(self, model, group=None, overlap=True):
         self.arena = model.arena
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.stream = torch.cuda.Stream() if (self.world > 1 and torch.cuda.is_available()) else None
         self.pending = []
+        self.done = []          # (start, end) slices already handed to NCCL since the last wait()
+        self.buckets = self.block_buckets(model)
+        if self.world > 1 and overlap and not os.environ.get("B200PDM_NO_OVERLAP"):   # (env: A/B measurement only)
+            self.install(model)
+
+    @staticmethod
+    def block_buckets(model):
+        """{(module, callback attribute): (start, end)} -- contiguous arena slices of the top-level blocks."""
+        spans = {}
+        for mod, mod_name, attr, shape, kind, off, n in getattr(model.arena, "entries", ()):
+            head = mod_name.split(".")
+            key = ".".join(head[:2]) if head[0] in ("down_blocks", "up_blocks") else head[0]
+            lo, hi = spans.get(key, (off, off + n))
+            spans[key] = (min(lo, off), max(hi, off + n))
+        out = {}
+        for key, (lo, hi) in spans.items():
+            if any(k != key and not (h <= lo or l >= hi) for k, (l, h) in spans.items()):
+                continue                                     # not contiguous in the arena: leave it to reduce_all()
+            if key.startswith(("down_blocks", "up_blocks")):
+                kind, idx = key.split(".")
+                out[(getattr(model, kind)[int(idx)], "_grad_ready")] = (lo, hi)
+            elif key == "mid_block":
+                out[(model.mid_block, "_grad_ready")] = (lo, hi)
+        # head (conv_norm_out, conv_out) finishes first, stem (conv_in, time_embedding) last
+        for names, attr in ((("conv_norm_out", "conv_out"), "_grad_ready_head"), (("conv_in", "time_embedding"), "_grad_ready_stem")):
+            have = [spans[n] for n in names if n in spans]
+            if have:
+                lo, hi = min(l for l, _ in have), max(h for _, h in have)
+                if not any(k not in names and not (h <= lo or l >= hi) for k, (l, h) in spans.items()):
+                    out[(model, attr)] = (lo, hi)
+        return out
+
+    def install(self, model):
+        for (mod, attr), (lo, hi) in self.buckets.items():
+            object.__setattr__(mod, attr, (lambda lo=lo, hi=hi: self.reduce_range(lo, hi)))
 
     def reduce_range(self, start: int, end: int):
         if self.world == 1 or end <= start:
             return
+        self.done.append((start, end))
         buf = self.arena.grad[start:end]
         if self.stream is None:                              # CPU/gloo test path
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
@@ -204,12 +243,20 @@ class GradReducer:
         self.pending.append(work)
 
     def reduce_all(self):
-        self.reduce_range(0, self.arena.numel)
+        """Everything not reduced yet since the last wait()."""
+        pos = 0
+        for lo, hi in sorted(self.done):
+            if lo > pos:
+                self.reduce_range(pos, lo)
+            pos = max(pos, hi)
+        if pos < self.arena.numel:
+            self.reduce_range(pos, self.arena.numel)
 
     def wait(self):
         for w in self.pending:
             w.wait()
         self.pending.clear()
+        self.done.clear()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
 
