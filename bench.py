@@ -353,8 +353,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full
-                     # capture profiles/r1_ncu_full_conv960x170_pair.txt (algorithmic bytes: 151.0 MB)
-                     "traffic": 261.96e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 151.0e6,
+                     # capture profiles/r1_ncu_full_conv960x170_v9.txt (algorithmic bytes: 151.0 MB; the 22 MB output mostly stays in L2)
+                     "traffic": 138.97e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 151.0e6,
                      "kernel": "b200::gemm_kernel<0,0,true> (tcgen05 cta_group::2 implicit-GEMM conv)",
                      "shape": conv_desc,
                      "ms_per_launch": conv_ms,
