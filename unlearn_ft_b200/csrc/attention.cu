@@ -13,6 +13,7 @@
 #include "../../include/b200pdm.h"
 
 #include <atomic>
+#include <stdlib.h>
 #include <string.h>
 
 namespace b200 {
@@ -20,6 +21,8 @@ extern std::atomic<uint64_t> g_launches;
 void set_err(const char* fmt, const char* a);
 int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
                     const uint32_t* box);
+int make_map_f32_3d(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld,
+                    uint32_t box_rows);
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
 constexpr int kTileBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B tile
@@ -31,6 +34,7 @@ struct AttnFwdParams {
   bf16* out;
   int64_t ldo;
   float* lse;  // [B, H, Lq] log2-domain log-sum-exp (may be null)
+  long long* dbg;  // optional phase timers of CTA 0 / warp 2 (diagnostics)
 };
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -234,6 +238,278 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Forward, version 2: one CTA = one (sample, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor
+// core; one CTA per SM.
+//   warp 0            : TMA producer  - both Q tiles once, then K/V blocks of 128 keys through a 3-stage smem ring
+//   warp 1            : MMA issuer    - per key block and query tile t:  O_t += P_t V (accumulating in TMEM), then
+//                                       immediately S_t = Q_t K_next^T, so that tile t's softmax overlaps the other
+//                                       tile's MMAs
+//   warps 2..5 / 6..9 : softmax of query tile 0 / 1 - one row per thread; the 128 scores of a row are pulled out of
+//                       TMEM at once, exponentiated against a LAZILY updated running maximum (the O accumulator in
+//                       TMEM is rescaled only when a row maximum grew by more than 2^8, which after the first blocks
+//                       is rare), written as bf16 P into a swizzle-128B tile for the second MMA
+// Both roles issue from warp-uniform code through elect.sync.  O leaves TMEM once, at the end.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kFwd2Threads = 320;
+constexpr int kKVStages = 3;
+constexpr float kRescaleThreshold = 8.f;   // log2 domain
+
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                   // 2 tiles
+  uint8_t* sKV = smem + 2 * kTileBytes;                 // kKVStages x (K tile, V tile)
+  uint8_t* sP = sKV + kKVStages * 2 * kTileBytes;       // 2 query tiles x 2 [128 x 64] sub-tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                 // [3]
+  uint64_t* kv_empty = kv_full + kKVStages;     // [3]
+  uint64_t* s_full = kv_empty + kKVStages;      // [2]
+  uint64_t* p_full = s_full + 2;                // [2]
+  uint64_t* pv_done = p_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * kQ;
+  const int n_qt = min(2, (p.Lq - q0 + kQ - 1) / kQ);   // query tiles with at least one valid row
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("b200pdm attention: dynamic smem not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKVStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;   // S_t: columns [128 t, 128 t + 128);  O_t: columns [256 + 64 t, 256 + 64 t + 64)
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(q_full, n_qt * kTileBytes);
+      for (int t = 0; t < n_qt; ++t) tma_load_4d(sQ + t * kTileBytes, &tm_q, q_full, 0, q0 + t * kQ, h, b);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < p.nkv; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&kv_full[stage], 2 * kTileBytes);
+        tma_load_4d(sKV + stage * 2 * kTileBytes, &tm_k, &kv_full[stage], 0, j * kKV, h, b);
+        tma_load_4d(sKV + stage * 2 * kTileBytes + kTileBytes, &tm_v, &kv_full[stage], 0, j * kKV, h, b);
+      }
+      if (++stage == kKVStages) stage = 0, phase ^= 1;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = make_idesc_bf16(kKV, 0, 0);  // S: N = 128 keys, A/B K-major
+    const uint32_t idesc_o = make_idesc_bf16(kD, 0, 1);   // PV: N = 64, B (= V) MN-major
+    const uint64_t dk = make_smem_desc_sw128(0, 16, 1024);       // K-major operand template
+    const uint64_t dv = make_smem_desc_sw128(0, 8192, 1024);     // MN-major (V) template
+    const uint32_t q_lo = (smem_u32(sQ) & 0x3FFFF) >> 4, kv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4,
+                   p_lo = (smem_u32(sP) & 0x3FFFF) >> 4;
+    auto issue_s = [&](int t, int stage) {   // S_t = Q_t K^T
+      const uint32_t a = q_lo + t * (kTileBytes >> 4), bq = kv_lo + stage * (2 * kTileBytes >> 4);
+#pragma unroll
+      for (int k = 0; k < kD / 16; ++k) umma_bf16(tmem + t * 128, dk | (a + k * 2), dk | (bq + k * 2), idesc_s, k > 0);
+      umma_commit(&s_full[t]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one())
+      for (int t = 0; t < n_qt; ++t) issue_s(t, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < p.nkv; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == kKVStages) nstage = 0, nphase ^= 1;
+      if (j + 1 < p.nkv) {
+        mbar_wait(&kv_full[nstage], nphase);
+        tc_fence_after();
+      }
+      for (int t = 0; t < n_qt; ++t) {
+        mbar_wait(&p_full[t], j & 1);   // P_t(j) is in smem, S_t(j) has been read out of TMEM
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a = p_lo + t * (2 * kTileBytes >> 4), bv = kv_lo + (stage * 2 * kTileBytes + kTileBytes) / 16;
+#pragma unroll
+          for (int k = 0; k < kKV / 16; ++k)
+            umma_bf16(tmem + 256 + t * 64, dk | (a + (k >> 2) * (kTileBytes >> 4) + (k & 3) * 2), dv | (bv + k * 128), idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&pv_done[t]);
+          if (j + 1 < p.nkv) issue_s(t, nstage);
+        }
+      }
+      if (elect_one()) umma_commit(&kv_empty[stage]);   // both tiles' PV(j) (and S(j), long before) have read this stage
+      stage = nstage, phase = nphase;
+    }
+  } else if (((warp - 2) >> 2) < n_qt) {
+    // ===================== softmax warpgroups =====================
+    const int t = (warp - 2) >> 2;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tmem_s = tmem + t * 128 + lane_base, tmem_o = tmem + 256 + t * 64 + lane_base;
+    const uint32_t p_row = smem_u32(sP) + t * 2 * kTileBytes + r * 128;
+    const int sw = r & 7;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < p.nkv; ++j) {
+      const int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
+      const bool prof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 64 || threadIdx.x == 192);
+      const int pslot = (threadIdx.x == 64) ? 0 : 8;
+      long long tp0 = prof ? clock64() : 0;
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      long long tp1 = prof ? clock64() : 0;
+      // pass 1: row maximum of the block (two rounds of 64 columns; masking only on the ragged last block)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(tmem_s + hh * 64, va);
+        tmem_ld_32x32(tmem_s + hh * 64 + 32, vb);
+        tmem_ld_wait();
+        if (valid == kKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (hh * 64 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(va[i]));
+            if (hh * 64 + 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(vb[i]));
+          }
+        }
+      }
+      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+      if (j == 0) {
+        m = m_tile;
+      } else {
+        // lazy rescaling: keep the stale maximum unless this row's maximum grew by more than 2^8
+        const bool grow = m_tile - m > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? exp2f(m - m_tile) : 1.f;
+          if (grow) m = m_tile;
+          l *= alpha;
+          mbar_wait(&pv_done[t], (j - 1) & 1);   // O_t holds every PV up to block j-1
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tmem_o + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      long long tp2 = prof ? clock64() : 0;
+      if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);   // PV(j-1) has finished reading this tile's P buffer
+      long long tp3 = prof ? clock64() : 0;
+      // pass 2: probabilities -> bf16 P tile (K-major, swizzle-128B); the next chunk's TMEM load is in flight meanwhile
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t vbuf[2][32];
+      tmem_ld_32x32(tmem_s, vbuf[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        if (c < 3) tmem_ld_32x32(tmem_s + (c + 1) * 32, vbuf[(c + 1) & 1]);
+        const uint32_t(&vv)[32] = vbuf[c & 1];
+        float pf[32];
+        if (valid == kKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            pf[i] = exp2f(fmaf(__uint_as_float(vv[i]), p.scale_log2, -m));
+            l4[i & 3] += pf[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = exp2f(fmaf(__uint_as_float(vv[i]), p.scale_log2, -m));
+            e = (c * 32 + i < valid) ? e : 0.f;
+            pf[i] = e;
+            l4[i & 3] += e;
+          }
+        }
+        const uint32_t base = p_row + (c >> 1) * kTileBytes;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(pf[g * 8 + 0], pf[g * 8 + 1]);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(pf[g * 8 + 2], pf[g * 8 + 3]);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(pf[g * 8 + 4], pf[g * 8 + 5]);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(pf[g * 8 + 6], pf[g * 8 + 7]);
+          const int chunk = ((c & 1) * 4 + g) ^ sw;
+          sts128(base + chunk * 16, *reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
+                 *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
+        }
+      }
+      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (prof) {
+        const long long tp4 = clock64();
+        p.dbg[pslot + 0] += tp1 - tp0, p.dbg[pslot + 1] += tp2 - tp1, p.dbg[pslot + 2] += tp3 - tp2, p.dbg[pslot + 3] += tp4 - tp3;
+      }
+    }
+    mbar_wait(&pv_done[t], (p.nkv - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + t * kQ + r;
+    const float inv = 1.f / l;
+    bf16* dst = p.out + (static_cast<int64_t>(b) * p.Lq + q) * p.ldo + h * kD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(tmem_o + c * 32, o);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float t8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = __uint_as_float(o[g * 8 + i]) * inv;
+          *reinterpret_cast<bf16x8*>(dst + c * 32 + g * 8) = pack8(t8);
+        }
+      }
+    }
+    if (q < p.Lq && p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = m + log2f(l);
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 static int make_qkv_map(CUtensorMap* map, const void* ptr, int64_t ld, int B, int H, int L) {
   // dims (d, token, head, batch)
   uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)H, (uint64_t)B};
@@ -266,20 +542,49 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
   p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nkv = (lk + kKV - 1) / kKV;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(out), p.ldo = ldo, p.lse = lse;
-  const size_t smem = 7 * kTileBytes + 256;
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_err("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return B200PDM_ERR_CUDA;
+  static long long* dbg_buf = nullptr;
+  static int dbg_on = -1;
+  if (dbg_on < 0) dbg_on = getenv("B200PDM_ATTN_DBG") ? 1 : 0;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
   }
-  dim3 grid((lq + kQ - 1) / kQ, heads, batch);
-  attn_fwd_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mk, mv, p);
+  p.dbg = dbg_on ? dbg_buf : nullptr;
+  static int use_v1 = -1;
+  if (use_v1 < 0) use_v1 = getenv("B200PDM_ATTN_V1") ? 1 : 0;   // A/B measurement only
+  cudaError_t e;
+  if (use_v1) {
+    const size_t smem = 7 * kTileBytes + 256;
+    e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_err("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return B200PDM_ERR_CUDA;
+    }
+    dim3 grid((lq + kQ - 1) / kQ, heads, batch);
+    attn_fwd_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mk, mv, p);
+  } else {
+    const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256;
+    e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_err("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return B200PDM_ERR_CUDA;
+    }
+    dim3 grid((lq + 2 * kQ - 1) / (2 * kQ), heads, batch);
+    attn_fwd2_kernel<<<grid, kFwd2Threads, smem, stream>>>(mq, mk, mv, p);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err("attention_fwd launch: %s", cudaGetErrorString(e));
     return B200PDM_ERR_CUDA;
   }
   g_launches++;
+  if (dbg_on) {
+    long long hbuf[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[attn dbg] Lq=%d Lk=%d nkv=%d | wg0: wait_s=%lld pass1=%lld wait_pv=%lld pass2=%lld | wg1: wait_s=%lld pass1=%lld "
+            "wait_pv=%lld pass2=%lld\n", lq, lk, p.nkv, hbuf[0], hbuf[1], hbuf[2], hbuf[3], hbuf[8], hbuf[9], hbuf[10], hbuf[11]);
+  }
   return B200PDM_OK;
 }
 
@@ -298,6 +603,7 @@ struct AttnBwdParams {
   int B, H, Lq, Lk, nq;
   float scale, scale_log2;
   const float* lse;    // [B, H, Lq] (log2 domain)
+  long long* dbg;      // optional phase timers (diagnostics)
   const float* delta;  // [B, H, Lq]
   float* dq_acc;       // fp32 [B*Lq, ld_dq], head h at columns [64h, 64h+64)
   int64_t ld_dq;
@@ -338,10 +644,12 @@ __device__ __forceinline__ void st_tile_row32(uint32_t row_base, int c, int sw, 
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+constexpr int kBwdThreads = 320;   // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter, 64 key columns each)
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + kTileBytes;
@@ -349,7 +657,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sdO = smem + 4 * kTileBytes;   // [2]
   uint8_t* sP = smem + 6 * kTileBytes;    // two sub-tiles
   uint8_t* sdS = smem + 8 * kTileBytes;   // two sub-tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * kTileBytes);
+  uint8_t* sDQ = smem + 10 * kTileBytes;  // fp32 dQ tile as two [128 rows x 32 cols] swizzle-128B sub-tiles (bulk reduce source)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * kTileBytes);
   uint64_t* kv_full = bars;
   uint64_t* qdo_full = bars + 1;   // [2]
   uint64_t* qdo_empty = bars + 3;  // [2]
@@ -376,9 +685,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
+    mbar_init(dq_empty, 8);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -429,14 +738,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         umma_commit(s_full);
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dV += P^T dO   (A: M' = keys over the two sub-tiles (LBO), K' = query rows)
-          umma_bf16(t_dv, make_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
-                    make_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK += dS^T Q
-          umma_bf16(t_dk, make_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
-                    make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
         if (i > 0) {
           mbar_wait(dq_empty, (i - 1) & 1);
           tc_fence_after();
@@ -445,13 +746,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int k = 0; k < 8; ++k)   // dQ_i = dS K  (A K-major over the two sub-tiles, B = K tile read MN-major)
           umma_bf16(t_dq, make_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), id_km64, k > 0);
-        umma_commit(dq_full);
+        umma_commit(dq_full);   // first, so that the softmax threads drain dQ while dV / dK (and the next S, dP) run
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV += P^T dO   (A: M' = keys over the two sub-tiles (LBO), K' = query rows)
+          umma_bf16(t_dv, make_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
+                    make_smem_desc_sw128(do_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK += dS^T Q
+          umma_bf16(t_dk, make_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
+                    make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
         umma_commit(&qdo_empty[s]);
       }
       umma_commit(acc_full);
     }
   } else {
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;   // which 64 of the 128 key columns (and which 32 of the 64 dQ columns) this warp handles
     const int r = qd * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t p_row = smem_u32(sP) + r * 128, ds_row = smem_u32(sdS) + r * 128;
@@ -463,28 +773,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool q_ok = q < p.Lq;
       const float lse = q_ok ? p.lse[bh * p.Lq + q] : 0.f;
       const float dlt = q_ok ? p.delta[bh * p.Lq + q] : 0.f;
+      const bool prof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+      const long long tp0 = prof ? clock64() : 0;
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      const long long tp1 = prof ? clock64() : 0;
+      uint32_t sv[2][32], dv_[2][32];
+      tmem_ld_32x32(t_s + lane_base + half * 64, sv[0]);
+      tmem_ld_32x32(t_dp + lane_base + half * 64, dv_[0]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], dv_[32];
-        tmem_ld_32x32(t_s + lane_base + c * 32, sv);
-        tmem_ld_32x32(t_dp + lane_base + c * 32, dv_);
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         tmem_ld_wait();
+        if (cc == 0) {   // the second chunk's loads are in flight while the first is processed
+          tmem_ld_32x32(t_s + lane_base + (c + 1) * 32, sv[1]);
+          tmem_ld_32x32(t_dp + lane_base + (c + 1) * 32, dv_[1]);
+        }
+        const uint32_t(&s_)[32] = sv[cc];
+        const uint32_t(&d_)[32] = dv_[cc];
         float pf[32], dsf[32];
         if (q_ok && valid_k == kKV) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            pf[j] = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
-            dsf[j] = pf[j] * ((__uint_as_float(dv_[j]) - dlt) * p.scale);
+            pf[j] = exp2f(fmaf(__uint_as_float(s_[j]), p.scale_log2, -lse));
+            dsf[j] = pf[j] * ((__uint_as_float(d_[j]) - dlt) * p.scale);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float pe = exp2f(fmaf(__uint_as_float(sv[j]), p.scale_log2, -lse));
+            float pe = exp2f(fmaf(__uint_as_float(s_[j]), p.scale_log2, -lse));
             pe = (q_ok && (c * 32 + j < valid_k)) ? pe : 0.f;
             pf[j] = pe;
-            dsf[j] = pe * (__uint_as_float(dv_[j]) - dlt) * p.scale;
+            dsf[j] = pe * (__uint_as_float(d_[j]) - dlt) * p.scale;
           }
         }
         st_tile_row32(p_row, c, sw, pf);
@@ -494,33 +814,47 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      const long long tp2 = prof ? clock64() : 0;
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_dq + lane_base + c * 32, v);
+      const long long tp3 = prof ? clock64() : 0;
+      // dQ tile: TMEM -> fp32 smem tile -> ONE bulk tensor reduce-add per 32-column half (instead of 2048 vector atomics)
+      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile left smem
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        uint32_t v0[32];
+        tmem_ld_32x32(t_dq + lane_base + half * 32, v0);
         tmem_ld_wait();
-        if (q_ok) {
-          float* dst = p.dq_acc + ((int64_t)b * p.Lq + q) * p.ld_dq + h * kD + c * 32;
+        const uint32_t row0 = smem_u32(sDQ) + half * kTileBytes + r * 128;
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
-                         "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
-                         "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
-                         : "memory");
-        }
+        for (int g = 0; g < 8; ++g) sts128(row0 + ((g ^ sw) << 4), v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3]);
       }
+      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);
+      if (lane == 0) mbar_arrive(dq_empty);   // the TMEM accumulator may be overwritten by the next dQ
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tm_dq)),
+                       "r"(smem_u32(sDQ + c * kTileBytes)), "r"(h * kD + c * 32), "r"(i * kQ), "r"(b)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (prof) {
+        const long long tp4 = clock64();
+        p.dbg[0] += tp1 - tp0, p.dbg[1] += tp2 - tp1, p.dbg[2] += tp3 - tp2, p.dbg[3] += tp4 - tp3;
+      }
     }
+    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reduces have been performed
     // accumulated dV / dK for key row k0 + r
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int key = k0 + r;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
+    {
+      const int which = half;   // first warp group writes dV, second dK
       bf16* dst = (which == 0 ? p.dv : p.dk) + ((int64_t)b * p.Lk + key) * (which == 0 ? p.ld_dv : p.ld_dk) + h * kD;
       const uint32_t t = (which == 0 ? t_dv : t_dk) + lane_base;
 #pragma unroll
@@ -596,15 +930,26 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
   p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nq = (lq + kQ - 1) / kQ;
   p.scale = scale, p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse, p.delta = delta, p.dq_acc = dq_acc, p.ld_dq = ld_acc;
+  static long long* bdbg = nullptr;
+  static int bdbg_on = -1;
+  if (bdbg_on < 0) bdbg_on = getenv("B200PDM_ATTN_DBG") ? 1 : 0;
+  if (bdbg_on) {
+    if (!bdbg) cudaMalloc(&bdbg, 16 * sizeof(long long));
+    cudaMemsetAsync(bdbg, 0, 16 * sizeof(long long), stream);
+  }
+  p.dbg = bdbg_on ? bdbg : nullptr;
   p.dk = reinterpret_cast<bf16*>(dk), p.ld_dk = lddk, p.dv = reinterpret_cast<bf16*>(dv), p.ld_dv = lddv;
-  const size_t smem = 10 * kTileBytes + 256;
+  CUtensorMap mdq;
+  rc = make_map_f32_3d(&mdq, dq_acc, (uint64_t)ld_acc, (uint64_t)lq, (uint64_t)batch, (uint64_t)ld_acc, kQ);
+  if (rc) return rc;
+  const size_t smem = 12 * kTileBytes + 256;
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_err("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return B200PDM_ERR_CUDA;
   }
   dim3 grid((lk + kKV - 1) / kKV, heads, batch);
-  attn_bwd_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mk, mv, mdo, p);
+  attn_bwd_kernel<<<grid, kBwdThreads, smem, stream>>>(mq, mk, mv, mdo, mdq, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err("attention_bwd launch: %s", cudaGetErrorString(e));
@@ -619,5 +964,12 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
   e = cudaGetLastError();
   if (e != cudaSuccess) return B200PDM_ERR_CUDA;
   g_launches += 4;
+  if (bdbg_on) {
+    long long hbuf[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(hbuf, bdbg, sizeof(hbuf), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[attn bwd dbg] Lq=%d Lk=%d nq=%d | wait_s=%lld softmax=%lld wait_dq=%lld drain_dq=%lld\n", lq, lk, p.nq, hbuf[0],
+            hbuf[1], hbuf[2], hbuf[3]);
+  }
   return B200PDM_OK;
 }

@@ -96,6 +96,26 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
   return B200PDM_OK;
 }
 
+// fp32 [batch][rows][cols] view (row pitch ld, batch pitch rows*ld elements), [box_rows x 32 col] boxes, 128B swizzle:
+// target of the attention backward's bulk tensor reduce-add of dQ tiles.
+int make_map_f32_3d(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld,
+                    uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return B200PDM_ERR_DRIVER;
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstr[2] = {ld * 4, rows * ld * 4};
+  cuuint32_t bx[3] = {32, box_rows, 1}, es[3] = {1, 1, 1};
+  if ((gstr[0] % 16) || (reinterpret_cast<uintptr_t>(ptr) & 15)) return B200PDM_ERR_ARG;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err("cuTensorMapEncodeTiled (fp32 reduce map) failed");
+    return B200PDM_ERR_DRIVER;
+  }
+  return B200PDM_OK;
+}
+
 int make_map_public(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
                     const uint32_t* box) {
   return make_map(map, ptr, rank, dims, strides_el, box, nullptr);
