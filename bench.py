@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--ratio", type=float, default=0.55)
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="single GPU: time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--cpu-steps", type=int, default=1)
     return ap.parse_args()
 
@@ -281,16 +282,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up
+    # warm-up (eager), and the number of kernels one step launches
     for i in range(max(args.warmup, 3)):
+        n_before = _lib.launch_count()
         tuner.train_step(dev_batches[i % len(dev_batches)])
+        launches_per_step = _lib.launch_count() - n_before
+    barrier()
+    # Single GPU: the whole step (forward x2, backward, AdamW: ~2300 launches) is replayed from ONE CUDA graph, so the host
+    # costs microseconds per step and a per-step result read-back cannot starve the GPU.  Multi-GPU keeps the eager path
+    # (NCCL all-reduce overlapped with backward).  --no-graph measures the eager path on one GPU as well.
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:
+        try:
+            tuner.capture_cuda_graph(dev_batches[0])
+            for i in range(2):
+                tuner.train_step(dev_batches[i % len(dev_batches)])
+        except Exception as e:                                     # report it instead of silently changing the metric
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); using the eager step", file=sys.stderr)
+            tuner._graph = None
+            use_graph = False
     barrier()
 
     # ---- timed: device-resident inputs (activations + parameters >> L2, so no L2 flush is needed between steps)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -299,7 +315,7 @@ def main():
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    launches = _lib.launch_count() - n0
+    launches = launches_per_step * args.steps      # (graph replays do not pass through the C entry points' counter)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms)
@@ -345,7 +361,9 @@ def main():
         "config": {"workload": workload, "global_batch": world * B, "parallelism": f"dp{world}",
                    "student_params": student.num_parameters(), "teacher_params": teacher.num_parameters(),
                    "l2": "no flush: per-step working set (1.4 B params x 2-4 B + activations) >> 126 MB L2",
-                   "last_loss": last},
+                   "last_loss": last,
+                   "step_launch": "one CUDA graph replay per step (capture of step+backward+AdamW)" if use_graph
+                   else "eager: one launch per kernel"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -230,6 +230,12 @@ int b200pdm_feature_loss(const void* s, const void* t, void* ds, float* sums, in
 int b200pdm_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
                        float beta2, float eps, float weight_decay, int64_t step, float grad_scale, int zero_grad,
                        b200pdm_stream_t stream);
+/* Same update with the step-dependent scalars read from device memory: dyn = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}
+ * (fp32[3]).  The launch itself is then step-independent and can live in a replayed CUDA graph of the whole training
+ * step (trainer.py:2316-2329); the host refreshes `dyn` before each replay.                                        */
+int b200pdm_adamw_step_dyn(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* dyn,
+                           float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad,
+                           b200pdm_stream_t stream);
 /* shadow = bf16(p) (after load_state_dict / a foreign optimizer touched the masters). */
 int b200pdm_refresh_shadow(const float* p, void* shadow_bf16, int64_t n, b200pdm_stream_t stream);
 

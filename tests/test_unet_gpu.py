@@ -237,3 +237,38 @@ def test_bilevel_upper_step_matches_oracle(gold):
     assert not torch.equal(tuner.upper_optimizer.exp_avg, tuner.optimizer.exp_avg)
     assert not torch.equal(p0, mine.arena.master.detach())
     assert float(mine.arena.grad.abs().sum()) == 0.0
+
+
+def test_cuda_graph_step_matches_eager(gold):
+    """The replayed CUDA graph of step -> backward -> AdamW follows the same trajectory as the eager loop (trainer.py:2316-2329)
+    and capturing it leaves the training state untouched."""
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel
+    from unlearn_ft_b200.pdm.training import UnetFineTuner
+    av = gold["small64_r055"]["arch_vector"]
+    batches = [make_batch(seed=s) for s in range(3)]
+    runs = []
+    for graphed in (False, True):
+        mine, _ = build_pair(av, trainable=True)
+        teacher = UNet2DConditionModel(small_cfg(), seed=7)
+        tuner = UnetFineTuner(mine, teacher, lr=1e-3, warmup_steps=2)
+        if graphed:
+            before = mine.arena.master.detach().clone()
+            tuner.capture_cuda_graph(batches[0])
+            assert torch.equal(mine.arena.master.detach(), before)             # capture did not train
+            assert float(tuner.optimizer.exp_avg.abs().sum()) == 0.0
+            assert float(mine.arena.grad.abs().sum()) == 0.0
+        losses = []
+        for b in batches:
+            out = tuner.train_step(b)
+            losses.append([float(v.detach()) for v in out])
+        runs.append((losses, mine.arena.master.detach().clone(), tuner.optimizer.step_count, tuner.global_step))
+    (l0, p0, n0, g0), (l1, p1, n1, g1) = runs
+    assert n0 == n1 == 3 and g0 == g1 == 3
+    for a, b in zip(l0, l1):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-3 * max(abs(x), 1e-6), (l0, l1)             # fp32 atomics order is the only difference
+    # Adam turns atomics-order noise on near-zero gradients into lr-sized differences: compare the update as a whole
+    init, _ = build_pair(av, trainable=True)
+    d0, d1 = (p0 - init.arena.master.detach()).flatten(), (p1 - init.arena.master.detach()).flatten()
+    assert F.cosine_similarity(d0, d1, dim=0).item() > 0.98
+    assert rel(p1, p0) < 5e-3

@@ -1189,10 +1189,15 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   }
 
   auto launch = [&](auto kern) -> int {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_err("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return B200PDM_ERR_CUDA;
+    static std::map<const void*, bool> attr_set;   // once per kernel instantiation (not per launch: graph capture)
+    cudaError_t e = cudaSuccess;
+    if (!attr_set[reinterpret_cast<const void*>(kern)]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        set_err("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return B200PDM_ERR_CUDA;
+      }
+      attr_set[reinterpret_cast<const void*>(kern)] = true;
     }
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (trace_on()) {

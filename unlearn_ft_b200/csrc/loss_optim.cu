@@ -95,7 +95,11 @@ __global__ void feature_loss_kernel(const bf16* __restrict__ s, const bf16* __re
 // Flat AdamW: one thread handles 4 consecutive parameters (float4 I/O), bf16 shadow written as 8 bytes.
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              bf16* __restrict__ shadow, int64_t n, float lr, float beta1, float beta2, float eps,
-                             float wd, float bc1, float bc2_sqrt, float grad_scale, int zero_grad) {
+                             float wd, float bc1, float bc2_sqrt, float grad_scale, int zero_grad,
+                             const float* __restrict__ dyn) {
+  if (dyn) {   // step-dependent scalars from device memory: the launch can sit in a replayed CUDA graph
+    lr = dyn[0], bc1 = dyn[1], bc2_sqrt = dyn[2];
+  }
   const int64_t nvec = n >> 2;
   const float step_size = lr / bc1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -203,7 +207,24 @@ int b200pdm_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, lr, beta1, beta2, eps,
-                                               weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grad);
+                                               weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grad, nullptr);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+
+int b200pdm_adamw_step_dyn(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, const float* dyn,
+                           float beta1, float beta2, float eps, float weight_decay, float grad_scale, int zero_grad,
+                           b200pdm_stream_t stream) {
+  if (!p || !g || !m || !v || !dyn || n <= 0) return B200PDM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return B200PDM_ERR_ARG;
+  int64_t blocks = ((n >> 2) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, 0.f, beta1, beta2, eps,
+                                               weight_decay, 1.f, 1.f, grad_scale, zero_grad, dyn);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

@@ -384,6 +384,13 @@ def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, grad_scale=1
           "adamw_step")
 
 
+def adamw_step_dyn(p, g, m, v, shadow, dyn, beta1, beta2, eps, wd, grad_scale=1.0, zero_grad=True):
+    """AdamW with {lr, bias corrections} read from the device tensor `dyn` (fp32[3]); CUDA-graph replayable."""
+    check(_lib.lib().b200pdm_adamw_step_dyn(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), p.numel(),
+                                            dyn.data_ptr(), beta1, beta2, eps, wd, grad_scale, int(zero_grad), _stream()),
+          "adamw_step_dyn")
+
+
 def refresh_shadow(p, shadow):
     check(_lib.lib().b200pdm_refresh_shadow(p.data_ptr(), shadow.data_ptr(), p.numel(), _stream()), "refresh_shadow")
 

@@ -382,6 +382,14 @@ class UNet2DConditionModelGated(nn.Module):
         if self.arena.trainable and self.conv_in.weight.grad is None:
             self.arena.reattach_grads()                     # a foreign zero_grad(set_to_none=True) detached them
         self.arena.ensure_shadow()
+        if self.arena.trainable and torch.is_grad_enabled():
+            # Per-forward graph anchor: a fresh leaf makes autograd record the block functions even though no activation
+            # input requires grad.  (A long-lived leaf would pin its AccumulateGrad node to whatever stream first used it,
+            # and the engine's end-of-backward sync with that stream breaks CUDA-graph capture of the training step.)
+            anchor = torch.empty(1, device=sample.device, requires_grad=True)
+            for blk in list(self.down_blocks) + [self.mid_block] + list(self.up_blocks):
+                blk._anchor = anchor
+            self._anchor = anchor
         timesteps = timestep
         if not torch.is_tensor(timesteps):
             timesteps = torch.tensor([timesteps], dtype=torch.int64, device=sample.device)
