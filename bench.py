@@ -288,10 +288,10 @@ def main():
         tuner.train_step(dev_batches[i % len(dev_batches)])
         launches_per_step = _lib.launch_count() - n_before
     barrier()
-    # Single GPU: the whole step (forward x2, backward, AdamW: ~2300 launches) is replayed from ONE CUDA graph, so the host
-    # costs microseconds per step and a per-step result read-back cannot starve the GPU.  Multi-GPU keeps the eager path
-    # (NCCL all-reduce overlapped with backward).  --no-graph measures the eager path on one GPU as well.
-    use_graph = world == 1 and not args.no_graph
+    # The whole step (forward x2, backward with its overlapped per-block NCCL all-reduces, AdamW: ~2300 launches) is replayed
+    # from ONE CUDA graph, so the host costs microseconds per step and a per-step result read-back cannot starve the GPU.
+    # --no-graph measures the eager path.
+    use_graph = not args.no_graph
     if use_graph:
         try:
             tuner.capture_cuda_graph(dev_batches[0])
@@ -337,9 +337,22 @@ def main():
     ms_e2e = float(ms2)
     clocks = sampler.stop() if rank == 0 else None
 
-    if rank != 0:
+    def shutdown():
+        """Drop the captured graph (it references the NCCL communicator), then tear the process group down; a teardown that
+        does not return within 20 s is abandoned (the result line has been printed by then)."""
+        tuner.release_cuda_graph()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            import threading
+            t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+            t.start()
+            t.join(20)
+            if t.is_alive():
+                sys.stdout.flush()
+                os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
 
     samples = world * B * args.steps
@@ -388,9 +401,8 @@ def main():
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e!r}"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown()
 
 
 if __name__ == "__main__":

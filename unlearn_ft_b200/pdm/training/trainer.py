@@ -335,7 +335,9 @@ class UnetFineTuner:
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def _graph_body(self):
         loss, diff, kd, blk = self.step(self._static_in)
-        loss.backward()
+        loss.backward()                          # (world > 1: each block's backward forks its all-reduce onto the side stream)
+        self.reducer.reduce_all()
+        self.reducer.wait()                      # joins the side stream back, also inside a capture
         self.optimizer.step_dyn(self._dyn)
         return loss.detach(), diff, kd, blk
 
@@ -344,11 +346,10 @@ class UnetFineTuner:
         batch into the graph's static input buffers, refresh three device scalars (lr, bias corrections) and replay.
         The host then spends microseconds instead of ~35 ms per step, so per-step result read-backs no longer starve the
         GPU.  Shapes are frozen to those of `example_batch`; training state is left untouched by the capture itself
-        (warm-up runs use lr = 0 and the optimizer moments are restored).  Single-GPU only: with world_size > 1 the eager
-        path (overlapped NCCL all-reduce) stays in use.  The tensors returned by `train_step` are graph-owned and are
+        (warm-up runs use lr = 0 and the optimizer moments are restored).  With world_size > 1 the per-block NCCL
+        all-reduces (forked onto the reducer's side stream from each block's backward, joined before AdamW) are captured
+        as part of the same graph; every rank must capture.  The tensors returned by `train_step` are graph-owned and are
         overwritten by the next step."""
-        if self.reducer.world > 1:
-            raise NotImplementedError("CUDA-graph replay of the training step is single-GPU only")
         dev = self.device
         self._static_in = {k: v.to(dev, copy=True) for k, v in example_batch.items()}
         self._dyn = torch.zeros(3, device=dev, dtype=torch.float32)
@@ -368,6 +369,11 @@ class UnetFineTuner:
         self.optimizer.exp_avg_sq.copy_(v0)
         self._graph = graph
         return graph
+
+    def release_cuda_graph(self):
+        """Back to the eager step; frees the graph and its private memory pool."""
+        self._graph = None
+        self._static_out = None
 
     def _replay(self, batch):
         for k, buf in self._static_in.items():
