@@ -240,68 +240,87 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, C % 8 == 0 (C in {320, 640, 1280}); row cached in registers.
 // ------------------------------------------------------------------------------------------------
-template <int MAXV>  // max 16-byte vectors per lane: C <= MAXV*8*32
+template <int MAXV, int R>
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                               const float* __restrict__ beta, bf16* __restrict__ y, int64_t ldy,
                               float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int C, float eps) {
+  // One warp normalises R consecutive rows; all of their loads are issued before any arithmetic and the rows stay PACKED
+  // (bf16) in registers between the passes: short rows (640 bytes at C = 320) need many warps x rows in flight per SM to
+  // reach HBM bandwidth, so the register footprint decides the throughput.
   const int lane = threadIdx.x & 31;
-  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t row0 = (blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int nvec = C >> 3;
-  float v[MAXV][8];
-  float sum = 0.f;
+  bf16x8 raw[R][MAXV];
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    int vi = lane + k * 32;
-    if (vi < nvec) {
-      unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + vi * 8), v[k]);
+  for (int rr = 0; rr < R; ++rr) {
+    const int64_t row = row0 + rr;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum += v[k][j];
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec && row < rows) raw[rr][k] = *reinterpret_cast<const bf16x8*>(x + row * ldx + vi * 8);
     }
   }
-  sum = warp_sum(sum);
-  const float m = sum / C;
-  float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    int vi = lane + k * 32;
-    if (vi < nvec) {
+  for (int rr = 0; rr < R; ++rr) {
+    const int64_t row = row0 + rr;
+    if (row >= rows) break;
+    float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float d = v[k][j] - m;
-        sq += d * d;
+    for (int k = 0; k < MAXV; ++k) {
+      if (lane + k * 32 < nvec) {
+        float v[8];
+        unpack8(raw[rr][k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[j];
       }
     }
-  }
-  sq = warp_sum(sq);
-  const float r = rsqrtf(sq / C + eps);
-  if (lane == 0) {
-    if (mean) mean[row] = m;
-    if (rstd) rstd[row] = r;
-  }
+    sum = warp_sum(sum);
+    const float m = sum / C;
+    float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    int vi = lane + k * 32;
-    if (vi < nvec) {
-      float o[8];
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(beta + vi * 8), b1 = *reinterpret_cast<const float4*>(beta + vi * 8 + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int k = 0; k < MAXV; ++k) {
+      if (lane + k * 32 < nvec) {
+        float v[8];
+        unpack8(raw[rr][k], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - m) * r * gg[j] + bb[j];
-      *reinterpret_cast<bf16x8*>(y + row * ldy + vi * 8) = pack8(o);
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[j] - m;
+          sq += d * d;
+        }
+      }
+    }
+    sq = warp_sum(sq);
+    const float r = rsqrtf(sq / C + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = m;
+      if (rstd) rstd[row] = r;
+    }
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int vi = lane + k * 32;
+      if (vi < nvec) {
+        float v[8], o[8];
+        unpack8(raw[rr][k], v);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[j] - m) * r * gg[j] + bb[j];
+        *reinterpret_cast<bf16x8*>(y + row * ldy + vi * 8) = pack8(o);
+      }
     }
   }
 }
 
 // LN backward: dx per row (one warp per row); dgamma/dbeta partials accumulated per block in smem then atomics.
-template <int MAXV>
-__global__ void ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
-                              const float* __restrict__ gamma, const float* __restrict__ mean,
-                              const float* __restrict__ rstd, const bf16* __restrict__ res, int64_t ldr,
-                              bf16* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
-                              float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block) {
+template <int MAXV, int R>
+__global__ void __launch_bounds__(256, (MAXV <= 2 ? 2 : 1))
+ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
+              const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const bf16* __restrict__ res, int64_t ldr, bf16* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block) {
   extern __shared__ float sh[];  // dgamma[C], dbeta[C]
   float* sdg = sh;
   float* sdb = sh + C;
@@ -316,46 +335,72 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const b
     for (int j = 0; j < 8; ++j) adg[k][j] = 0.f, adb[k][j] = 0.f;
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_block;
   const int64_t row_end = min(rows, row_begin + rows_per_block);
-  for (int64_t row = row_begin + warp; row < row_end; row += nwarps) {
-    const float m = mean[row], r = rstd[row];
-    float xh[MAXV][8], gd[MAXV][8];
-    float s1 = 0.f, s2 = 0.f;
+  // R rows per warp iteration, all loads first: more bytes in flight per SM (short rows are latency-bound otherwise)
+  for (int64_t rowb = row_begin + warp * R; rowb < row_end; rowb += nwarps * R) {
+    bf16x8 xr[R][MAXV], dr[R][MAXV], rr_[R][MAXV];
+    float mm[R], rs[R];
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      int vi = lane + k * 32;
-      if (vi < nvec) {
-        float xv[8], dv[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(x + row * ldx + vi * 8), xv);
-        unpack8(*reinterpret_cast<const bf16x8*>(dy + row * lddy + vi * 8), dv);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + vi * 8), g1 = *reinterpret_cast<const float4*>(gamma + vi * 8 + 4);
-        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    for (int q = 0; q < R; ++q) {
+      const int64_t row = rowb + q;
+      const bool ok = row < row_end;
+      mm[q] = ok ? mean[row] : 0.f;
+      rs[q] = ok ? rstd[row] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[k][j] = (xv[j] - m) * r;
-          gd[k][j] = gg[j] * dv[j];
-          s1 += gd[k][j];
-          s2 += gd[k][j] * xh[k][j];
-          adg[k][j] += dv[j] * xh[k][j];
-          adb[k][j] += dv[j];
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (ok && vi < nvec) {
+          xr[q][k] = *reinterpret_cast<const bf16x8*>(x + row * ldx + vi * 8);
+          dr[q][k] = *reinterpret_cast<const bf16x8*>(dy + row * lddy + vi * 8);
+          if (res) rr_[q][k] = *reinterpret_cast<const bf16x8*>(res + row * ldr + vi * 8);
         }
       }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      int vi = lane + k * 32;
-      if (vi < nvec) {
-        float o[8];
+    for (int q = 0; q < R; ++q) {
+      const int64_t row = rowb + q;
+      if (row >= row_end) break;
+      const float m = mm[q], r = rs[q];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = r * (gd[k][j] - s1 - xh[k][j] * s2);
-        if (res) {
-          float rf[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(res + row * ldr + vi * 8), rf);
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) {
+          float xv[8], dv[8];
+          unpack8(xr[q][k], xv);
+          unpack8(dr[q][k], dv);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += rf[j];
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - m) * r, gd = gg[j] * dv[j];
+            s1 += gd;
+            s2 += gd * xh;
+            adg[k][j] += dv[j] * xh;
+            adb[k][j] += dv[j];
+          }
         }
-        *reinterpret_cast<bf16x8*>(dx + row * lddx + vi * 8) = pack8(o);
+      }
+      s1 = warp_sum(s1) / C;
+      s2 = warp_sum(s2) / C;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int vi = lane + k * 32;
+        if (vi < nvec) {
+          float xv[8], dv[8], o[8];
+          unpack8(xr[q][k], xv);
+          unpack8(dr[q][k], dv);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = r * (gg[j] * dv[j] - s1 - (xv[j] - m) * r * s2);
+          if (res) {
+            float rf[8];
+            unpack8(rr_[q][k], rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += rf[j];
+          }
+          *reinterpret_cast<bf16x8*>(dx + row * lddx + vi * 8) = pack8(o);
+        }
       }
     }
   }
@@ -465,15 +510,17 @@ int b200pdm_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
     return B200PDM_ERR_UNSUPPORTED;
   }
   const int wpb = 8;
-  const int blocks = (int)((rows + wpb - 1) / wpb);
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   bf16* yb = reinterpret_cast<bf16*>(y);
+  auto nblocks = [&](int r) { return (int)((rows + (int64_t)wpb * r - 1) / ((int64_t)wpb * r)); };
   if (C <= 8 * 32 * 2)
-    ln_fwd_kernel<2><<<blocks, wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    ln_fwd_kernel<2, 4><<<nblocks(4), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+  else if (C <= 8 * 32 * 3)
+    ln_fwd_kernel<3, 2><<<nblocks(2), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   else if (C <= 8 * 32 * 5)
-    ln_fwd_kernel<5><<<blocks, wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    ln_fwd_kernel<5, 1><<<nblocks(1), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   else
-    ln_fwd_kernel<8><<<blocks, wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    ln_fwd_kernel<8, 1><<<nblocks(1), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -487,7 +534,7 @@ int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
     set_err("layernorm_bwd: C must be a multiple of 8 and <= 1280", "");
     return B200PDM_ERR_UNSUPPORTED;
   }
-  int blocks = 148 * 2;
+  int blocks = 148 * (C <= 512 ? 2 : 1) * 2;   // two waves of the resident blocks
   int rows_per_block = (int)((rows + blocks - 1) / blocks);
   if (rows_per_block < 8) rows_per_block = 8;
   blocks = (int)((rows + rows_per_block - 1) / rows_per_block);
@@ -498,11 +545,14 @@ int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   const bf16* rb = reinterpret_cast<const bf16*>(residual);
   if (residual && ldr % 8) return B200PDM_ERR_UNSUPPORTED;
   if (C <= 8 * 32 * 2)
-    ln_bwd_kernel<2><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
-                                                 dbeta, rows, C, rows_per_block);
+    ln_bwd_kernel<2, 2><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+                                                    dbeta, rows, C, rows_per_block);
+  else if (C <= 8 * 32 * 3)
+    ln_bwd_kernel<3, 1><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+                                                    dbeta, rows, C, rows_per_block);
   else
-    ln_bwd_kernel<5><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
-                                                 dbeta, rows, C, rows_per_block);
+    ln_bwd_kernel<5, 1><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+                                                    dbeta, rows, C, rows_per_block);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
