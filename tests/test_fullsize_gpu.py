@@ -210,4 +210,8 @@ def test_fullsize_batch_rows_are_independent(full_models):
         full = teacher(b16["latents"], b16["timesteps"], b16["prompt_embeds"]).sample
         sub = {k: v[5:7].contiguous() for k, v in b16.items()}
         part = teacher(sub["latents"], sub["timesteps"], sub["prompt_embeds"]).sample
-    assert rel_err(full[5:7], part) < 1e-2
+    # different batch sizes take different tile / split-K plans (fp32 atomics order, bf16 rounding points): the same 2e-2
+    # budget as any two bf16 evaluations of this 30-layer network, far below the O(1) error of a cross-sample leak
+    err = rel_err(full[5:7], part)
+    print("batch-16 vs batch-2 rows: max-abs relative difference", err)
+    assert err < 2e-2
