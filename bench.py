@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="single GPU: time the eager step instead of the CUDA-graph replay")
+    ap.add_argument("--sampling", action="store_true",
+                    help="BASELINE config 5 instead of the default config 2: forward-only CFG sampling loop (U-Net only), "
+                         "--images per GPU, 50 DDIM steps, guidance 7.5; a 'step' is one complete 50-step sampling call")
+    ap.add_argument("--images", type=int, default=32, help="--sampling: images per GPU (U-Net batch = 2x)")
     ap.add_argument("--cpu-steps", type=int, default=1)
     return ap.parse_args()
 
@@ -222,11 +226,98 @@ def adamw_roofline(torch, K, student):
             "peak_source": "MEASURED_PEAKS.json hbm_gbs, of measured" if peaks else "fallback 6650 GB/s, of fallback"}
 
 
+def sampling_bench(args, rank, world, local_rank):
+    """BASELINE config 5: images/s of the guided denoising loop, U-Net only.  Ranks are independent
+    replicas (each samples its own images; no collective on this path)."""
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from unlearn_ft_b200 import _lib
+    from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModelPruned
+    from unlearn_ft_b200.pdm.models.unet.unet_2d_conditional import SD21_CONFIG, structure_from_config
+    from unlearn_ft_b200.pdm.pipelines import CFGSampler
+
+    torch.manual_seed(43)
+    av = HyperStructure.get_random_arch_vector(args.ratio, structure_from_config(SD21_CONFIG))
+    unet = UNet2DConditionModelPruned(arch_vector=av, trainable=False, seed=43)
+    n, L, steps_inf = args.images, args.latent, 50
+    sampler = CFGSampler(unet, num_inference_steps=steps_inf, guidance_scale=7.5, use_cuda_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(2000 + rank)
+    host = [(torch.randn(n, 4, L, L, generator=g).pin_memory(), torch.randn(n, 77, 1024, generator=g).bfloat16().pin_memory(),
+             torch.randn(1, 77, 1024, generator=g).bfloat16().expand(n, -1, -1).contiguous().pin_memory()) for _ in range(2)]
+    dev = [tuple(t.cuda() for t in hb) for hb in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n0 = _lib.launch_count()
+    sampler.use_cuda_graph, keep = False, sampler.use_cuda_graph
+    sampler.steps, full = 1, sampler.steps
+    sampler.sample(*dev[0])                                       # one eager step: kernels per denoising step
+    launches_per_call = (_lib.launch_count() - n0) * full
+    sampler.steps, sampler.use_cuda_graph = full, keep
+    for i in range(max(1, min(args.warmup, 2))):
+        sampler.sample(*dev[i % 2])
+    barrier()
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        sampler.sample(*dev[i % 2])
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        lat, pos, neg = host[i % 2]
+        out = sampler.sample(lat.cuda(non_blocking=True), pos.cuda(non_blocking=True), neg.cuda(non_blocking=True))
+        res = out.cpu()                                           # final latents back to the host (what the VAE would take)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    clocks = clk.stop() if rank == 0 else None
+    if rank == 0:
+        images = world * n * args.steps
+        fl = 0.464e12 * 2 * steps_inf if abs(args.ratio - 0.55) < 1e-6 else None      # SURVEY App. C: per image
+        line = {"metric": "sampled images/sec (U-Net only, 50-step CFG DDIM, 512px)", "value": images / (float(ms) * 1e-3),
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"BASELINE config 5: APTP r={args.ratio} pruned SD-2.1 U-Net, forward only, {n} images/GPU "
+                                       f"(U-Net batch {2 * n}), 50 DDIM steps, guidance 7.5, {L}x{L} latent; VAE / text encoder "
+                                       "excluded", "parallelism": f"replicas x{world}",
+                           "step_launch": "one CUDA graph replay per denoising step" if sampler.use_cuda_graph else "eager",
+                           "l2": "no flush: weights + activations of a batch-64 forward >> 126 MB L2"},
+                "e2e": {"value": images / (float(ms2) * 1e-3), "unit": "images/s",
+                        "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]),
+                        "d2h_bytes_per_step": n * 4 * L * L * 4},
+                "gpu_launches": int(launches_per_call * args.steps), "clocks": clocks,
+                "algorithmic_tflops": None if fl is None else fl * images / (float(ms) * 1e-3) / 1e12}
+        print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.sampling and args.impl != "reference":
+        return sampling_bench(args, rank, world, local_rank)
     workload = (f"APTP r={args.ratio} pruned SD-2.1 U-Net (random arch vector, random init) + frozen SD-2.1 teacher, "
                 f"DDPM+output-KD+feature-KD step, batch {args.batch}/GPU, {args.latent}x{args.latent} latent, bf16")
 

@@ -239,6 +239,17 @@ int b200pdm_adamw_step_dyn(float* p, float* g, float* m, float* v, void* shadow_
 /* shadow = bf16(p) (after load_state_dict / a foreign optimizer touched the masters). */
 int b200pdm_refresh_shadow(const float* p, void* shadow_bf16, int64_t n, b200pdm_stream_t stream);
 
+/* Sampling: one denoising step of the classifier-free-guidance loop, pdm/pipelines/pruning_pipelines.py:957-978
+ * = chunk(2) + guidance combine (:972-974) + diffusers DDIMScheduler.step (eta 0, v_prediction, "leading" timesteps,
+ * set_alpha_to_one False) (:981), fused.  model_out = U-Net output [2n, chw] fp32 (unconditional half first, :931);
+ * latents [n, chw] is updated in place and copied into both halves of latent_in [2n, chw] (the next U-Net input, :961).
+ * state = int32[2] {step index, internal counter} (zero it before a loop), t_dev = int64[2n] U-Net timestep tensor that
+ * is advanced to timesteps[step + 1]: all step-dependent values live on the device, so the launches of one step can be
+ * replayed from a CUDA graph.                                                                                          */
+int b200pdm_cfg_ddim_step(const float* model_out, float* latents, float* latent_in, const float* alphas_cumprod,
+                          const int64_t* timesteps, int* state, int64_t* t_dev, int n, int64_t chw, int num_steps,
+                          int train_timesteps, float guidance_scale, b200pdm_stream_t stream);
+
 /* Forward diffusion (diffusers DDIMScheduler.add_noise / get_velocity at trainer.py:2430,2443):
  * noisy = sa[t_b] x0 + sb[t_b] eps ; target = sa[t_b] eps - sb[t_b] x0 ; fp32.                             */
 int b200pdm_diffusion_prep(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,

@@ -865,3 +865,31 @@ class DDIMSchedulerLite:
     def get_velocity(self, sample, noise, timesteps):
         a, s = self._coeffs(sample, timesteps)
         return a * noise - s * sample
+
+    # ---- sampling side (diffusers 0.30.3 DDIMScheduler with the SD-2.1 scheduler_config.json: clip_sample False,
+    #      set_alpha_to_one False, steps_offset 1, timestep_spacing "leading", v_prediction; restated, unpinned)
+    def set_timesteps(self, num_inference_steps, device=None):
+        T = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        step_ratio = T // num_inference_steps
+        ts = (torch.arange(0, num_inference_steps) * step_ratio).round().flip(0).to(torch.int64) + 1     # steps_offset = 1
+        self.timesteps = ts.to(device) if device is not None else ts
+        self.init_noise_sigma = 1.0
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0):
+        """DDIMScheduler.step for eta = 0 (the pipeline default, pruning_pipelines.py:876): returns prev_sample."""
+        assert eta == 0.0
+        t = int(timestep)
+        prev_t = t - self.config.num_train_timesteps // self.num_inference_steps
+        acp = self.alphas_cumprod.to(sample.device)
+        a_t = acp[t]
+        a_prev = acp[prev_t] if prev_t >= 0 else acp[0]                       # final_alpha_cumprod (set_alpha_to_one False)
+        b_t = 1 - a_t
+        assert self.config.prediction_type == "v_prediction"
+        pred_x0 = a_t ** 0.5 * sample - b_t ** 0.5 * model_output
+        pred_eps = a_t ** 0.5 * model_output + b_t ** 0.5 * sample
+        direction = (1 - a_prev) ** 0.5 * pred_eps                            # sigma_t = 0
+        return a_prev ** 0.5 * pred_x0 + direction

@@ -83,6 +83,7 @@ _SIGS = {
     "b200pdm_pred_loss": [c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, f32, f32, c_p],
     "b200pdm_feature_loss": [c_p, c_p, c_p, c_p, i64, f32, f32, c_p],
     "b200pdm_adamw_step": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i64, f32, i32, c_p],
+    "b200pdm_cfg_ddim_step": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, i32, i32, f32, c_p],
     "b200pdm_adamw_step_dyn": [c_p, c_p, c_p, c_p, c_p, i64, c_p, f32, f32, f32, f32, f32, i32, c_p],
     "b200pdm_refresh_shadow": [c_p, c_p, i64, c_p],
     "b200pdm_diffusion_prep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, c_p],

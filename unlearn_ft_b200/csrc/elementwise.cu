@@ -286,6 +286,51 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, bf16* _
   }
 }
 
+// ---------------------------------------------------------------- sampling: CFG combine + DDIM step (eta = 0, v-prediction)
+// One launch per denoising step: guided = u + g (c - u); x0 = sqrt(a_t) x - sqrt(1 - a_t) v; eps = sqrt(a_t) v + sqrt(1 - a_t) x;
+// x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps.  The step counter, the next U-Net timestep tensor and the duplicated latent
+// batch live in device memory so that the identical launch sequence of one step can be replayed from a CUDA graph 50 times.
+__global__ void cfg_ddim_step_kernel(const float* __restrict__ model_out, float* __restrict__ latents, float* __restrict__ latent_in,
+                                     const float* __restrict__ alphas_cumprod, const int64_t* __restrict__ timesteps,
+                                     int* __restrict__ step_idx, int64_t* __restrict__ t_dev, int n, int64_t chw, int num_steps,
+                                     int train_T, float guidance, unsigned int* __restrict__ done_ctr) {
+  const int idx = *step_idx;
+  const int64_t t = timesteps[idx];
+  const int64_t t_prev = t - train_T / num_steps;
+  const float a_t = alphas_cumprod[t];
+  const float a_prev = t_prev >= 0 ? alphas_cumprod[t_prev] : alphas_cumprod[0];   // set_alpha_to_one = False
+  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), pa = sqrtf(a_prev), pb = sqrtf(1.f - a_prev);
+  const int64_t total = (int64_t)n * chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = model_out[i], c = model_out[total + i];
+    const float v = u + guidance * (c - u);
+    const float x = latents[i];
+    const float x0 = sa * x - sb * v;
+    const float eps = sa * v + sb * x;
+    const float xp = pa * x0 + pb * eps;
+    latents[i] = xp;
+    latent_in[i] = xp;            // uncond half
+    latent_in[total + i] = xp;    // text half
+  }
+  // last block to finish advances the step state (nobody reads step_idx / t_dev any more in this launch)
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    const int next = idx + 1;
+    const int64_t tn = timesteps[next < num_steps ? next : num_steps - 1];
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) t_dev[i] = tn;
+    if (threadIdx.x == 0) {
+      *step_idx = next;
+      *done_ctr = 0;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- forward diffusion prep
 __global__ void diffusion_prep_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                       const int64_t* __restrict__ t, const float* __restrict__ sa,
@@ -459,6 +504,19 @@ int b200pdm_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int batc
 int b200pdm_timestep_embedding(const int64_t* t, void* out, int64_t ldo, int batch, int dim, b200pdm_stream_t stream) {
   if (dim % 2) return B200PDM_ERR_ARG;
   timestep_embedding_kernel<<<grid_for((int64_t)batch * dim / 2, 128), 128, 0, STREAM>>>(t, BF(out), ldo, batch, dim);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_cfg_ddim_step(const float* model_out, float* latents, float* latent_in, const float* alphas_cumprod,
+                          const int64_t* timesteps, int* state, int64_t* t_dev, int n, int64_t chw, int num_steps,
+                          int train_timesteps, float guidance_scale, b200pdm_stream_t stream) {
+  if (!model_out || !latents || !latent_in || !alphas_cumprod || !timesteps || !state || !t_dev || n <= 0 || chw <= 0 ||
+      num_steps <= 0 || train_timesteps < num_steps)
+    return B200PDM_ERR_ARG;
+  cfg_ddim_step_kernel<<<grid_for((int64_t)n * chw, 256), 256, 0, STREAM>>>(
+      model_out, latents, latent_in, alphas_cumprod, timesteps, state, t_dev, n, chw, num_steps, train_timesteps, guidance_scale,
+      reinterpret_cast<unsigned int*>(state + 1));
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

@@ -395,6 +395,15 @@ def refresh_shadow(p, shadow):
     check(_lib.lib().b200pdm_refresh_shadow(p.data_ptr(), shadow.data_ptr(), p.numel(), _stream()), "refresh_shadow")
 
 
+def cfg_ddim_step(model_out, latents, latent_in, alphas_cumprod, timesteps, state, t_dev, num_steps, train_timesteps, guidance):
+    """Fused CFG combine + DDIM step (see include/b200pdm.h); all tensors fp32 / int64 / int32 on the device, in place."""
+    n = latents.shape[0]
+    chw = latents.numel() // n
+    check(_lib.lib().b200pdm_cfg_ddim_step(model_out.data_ptr(), latents.data_ptr(), latent_in.data_ptr(),
+                                           alphas_cumprod.data_ptr(), timesteps.data_ptr(), state.data_ptr(), t_dev.data_ptr(),
+                                           n, chw, num_steps, train_timesteps, float(guidance), _stream()), "cfg_ddim_step")
+
+
 def diffusion_prep(x0, noise, t, sqrt_acp, sqrt_1macp):
     B = x0.shape[0]
     noisy, vt = torch.empty_like(x0), torch.empty_like(x0)
