@@ -25,6 +25,13 @@ int make_map_f32_3d(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
                     uint32_t box_rows);
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
+// Share of the exponentials moved from MUFU.EX2 to the FMA pipe (exp2_fma): elements with (i & mask) == mask; 3 -> 25 %,
+// 1 -> 50 %, 64 -> none.  Measured on B200 (L = 4096): 0 % 689 us fwd / 1757 us bwd, 25 % 691 / 1765, 50 % 719 / 1815 -- the
+// softmax warps are issue-bound, not MUFU-bound (the polynomial costs 9 issue slots per element), so it stays off.
+#ifndef B200PDM_EXP_FMA_MASK
+#define B200PDM_EXP_FMA_MASK 64
+#endif
+constexpr int kExpFmaMask = B200PDM_EXP_FMA_MASK;
 constexpr int kTileBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B tile
 constexpr int kAttnThreads = 192;
 
@@ -445,7 +452,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (valid == kKV) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            pf[i] = exp2f(fmaf(__uint_as_float(vv[i]), p.scale_log2, -m));
+            const float xs = fmaf(__uint_as_float(vv[i]), p.scale_log2, -m);
+            pf[i] = ((i & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs) : exp2f(xs);   // a fixed share on the FMA pipe
             l4[i & 3] += pf[i];
           }
         } else {
@@ -795,7 +803,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (q_ok && valid_k == kKV) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            pf[j] = exp2f(fmaf(__uint_as_float(s_[j]), p.scale_log2, -lse));
+            const float xs = fmaf(__uint_as_float(s_[j]), p.scale_log2, -lse);
+            pf[j] = ((j & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs) : exp2f(xs);   // a fixed share on the FMA pipe
             dsf[j] = pf[j] * ((__uint_as_float(d_[j]) - dlt) * p.scale);
           }
         } else {

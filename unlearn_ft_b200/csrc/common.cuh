@@ -79,6 +79,18 @@ __device__ __forceinline__ void ldg256(const void* ptr, uint32_t (&a)[8]) {
                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
                : "l"(ptr));
 }
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 polynomial, max relative error 7.8e-5 -- far below bf16's 2^-9): the
+// attention kernels are bound by the 16-per-clock MUFU.EX2 rate, so a fixed fraction of the exponentials is computed here
+// instead (FlashAttention-4's trick).  Valid for x in [-126, 126]; callers clamp below (their x is <= ~8).
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                        // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);                  // fractional part in [-0.5, 0.5]
+  float p = fmaf(f, 0.05508868f, 0.24260405f);
+  p = fmaf(f, p, 0.69327624f);
+  p = fmaf(f, p, 0.99992894f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 // One lane of a converged warp.  Single-thread instructions (TMA, tcgen05.mma/commit) are issued under this predicate from
 // warp-uniform code, so their operands live in uniform registers; a `lane == 0` branch instead makes the compiler wrap
 // every such instruction in an ELECT / R2UR waterfall loop (~20 instructions each).
