@@ -441,6 +441,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       long long tp3 = prof ? clock64() : 0;
       // pass 2: probabilities -> bf16 P tile (K-major, swizzle-128B); the next chunk's TMEM load is in flight meanwhile
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m, -m);
       uint32_t vbuf[2][32];
       tmem_ld_32x32(tmem_s, vbuf[0]);
 #pragma unroll
@@ -451,10 +453,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float pf[32];
         if (valid == kKV) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float xs = fmaf(__uint_as_float(vv[i]), p.scale_log2, -m);
-            pf[i] = ((i & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs) : exp2f(xs);   // a fixed share on the FMA pipe
-            l4[i & 3] += pf[i];
+          for (int i = 0; i < 16; ++i) {   // packed pairs: one FFMA2 + one FADD2 per two scores
+            const float2 xs = ffma2(make_float2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1])), sc2, nm2);
+            pf[2 * i] = ((2 * i & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs.x) : exp2f(xs.x);
+            pf[2 * i + 1] = (((2 * i + 1) & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs.y) : exp2f(xs.y);
+            ls2[i & 1] = fadd2(ls2[i & 1], make_float2(pf[2 * i], pf[2 * i + 1]));
           }
         } else {
 #pragma unroll
@@ -477,7 +480,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                  *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
         }
       }
-      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      l += ((l4[0] + l4[1]) + (l4[2] + l4[3])) + ((ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y));
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
@@ -786,6 +789,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       const long long tp1 = prof ? clock64() : 0;
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(-lse, -lse);
+      const float2 nd2 = make_float2(-dlt, -dlt), ss2 = make_float2(p.scale, p.scale);
       uint32_t sv[2][32], dv_[2][32];
       tmem_ld_32x32(t_s + lane_base + half * 64, sv[0]);
       tmem_ld_32x32(t_dp + lane_base + half * 64, dv_[0]);
@@ -802,10 +807,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         float pf[32], dsf[32];
         if (q_ok && valid_k == kKV) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xs = fmaf(__uint_as_float(s_[j]), p.scale_log2, -lse);
-            pf[j] = ((j & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs) : exp2f(xs);   // a fixed share on the FMA pipe
-            dsf[j] = pf[j] * ((__uint_as_float(d_[j]) - dlt) * p.scale);
+          for (int j = 0; j < 16; ++j) {   // packed pairs: FFMA2, FADD2, 2 x FMUL2 per two elements
+            const float2 xs = ffma2(make_float2(__uint_as_float(s_[2 * j]), __uint_as_float(s_[2 * j + 1])), sc2, nl2);
+            const float2 pe = make_float2(exp2f(xs.x), exp2f(xs.y));
+            const float2 dd = fmul2(fadd2(make_float2(__uint_as_float(d_[2 * j]), __uint_as_float(d_[2 * j + 1])), nd2), ss2);
+            const float2 ds = fmul2(pe, dd);
+            pf[2 * j] = pe.x, pf[2 * j + 1] = pe.y;
+            dsf[2 * j] = ds.x, dsf[2 * j + 1] = ds.y;
           }
         } else {
 #pragma unroll
