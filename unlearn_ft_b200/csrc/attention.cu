@@ -47,6 +47,7 @@ struct AttnFwdParams {
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;
@@ -265,6 +266,7 @@ constexpr float kRescaleThreshold = 8.f;   // log2 domain
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                   // 2 tiles
   uint8_t* sKV = smem + 2 * kTileBytes;                 // kKVStages x (K tile, V tile)
@@ -311,6 +313,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;   // S_t: columns [128 t, 128 t + 128);  O_t: columns [256 + 64 t, 256 + 64 t + 64)
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the predecessor's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -572,7 +575,7 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
       return B200PDM_ERR_CUDA;
     }
     dim3 grid((lq + kQ - 1) / kQ, heads, batch);
-    attn_fwd_kernel<<<grid, kAttnThreads, smem, stream>>>(mq, mk, mv, p);
+    launch_pdl(attn_fwd_kernel, grid, kAttnThreads, smem, stream, mq, mk, mv, p);
   } else {
     const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256;
     e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -581,7 +584,7 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
       return B200PDM_ERR_CUDA;
     }
     dim3 grid((lq + 2 * kQ - 1) / (2 * kQ), heads, batch);
-    attn_fwd2_kernel<<<grid, kFwd2Threads, smem, stream>>>(mq, mk, mv, p);
+    launch_pdl<true>(attn_fwd2_kernel, grid, kFwd2Threads, smem, stream, mq, mk, mv, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -626,6 +629,7 @@ struct AttnBwdParams {
 
 __global__ void attn_delta_kernel(const bf16* __restrict__ dO, int64_t lddo, const bf16* __restrict__ O, int64_t ldo,
                                   float* __restrict__ delta, int B, int H, int Lq) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);  // (b*Lq + q)*H + h
   if (row >= (int64_t)B * Lq * H) return;
@@ -661,6 +665,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + kTileBytes;
@@ -711,6 +716,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_dp = tmem + 128, t_dv = tmem + 256, t_dk = tmem + 320, t_dq = tmem + 384;
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the predecessor's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -902,6 +908,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 __global__ void cast2d_f32_to_bf16_kernel(const float* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy,
                                           int64_t rows, int cols8) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = rows * cols8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / cols8;
@@ -929,7 +936,7 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
   float* dq_acc = workspace + (((int64_t)batch * heads * lq + 3) / 4) * 4;
   const int64_t ld_acc = (int64_t)heads * 64;
   const int64_t rows = (int64_t)batch * lq * heads;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dout), lddo,
+  launch_pdl(attn_delta_kernel, (unsigned)((rows + 7) / 8), 256, 0, stream, reinterpret_cast<const bf16*>(dout), lddo,
                                                                    reinterpret_cast<const bf16*>(out), ldo, delta,
                                                                    batch, heads, lq);
   if (cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)batch * lq * ld_acc, stream) != cudaSuccess)
@@ -966,7 +973,7 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
     return B200PDM_ERR_CUDA;
   }
   dim3 grid((lk + kKV - 1) / kKV, heads, batch);
-  attn_bwd_kernel<<<grid, kBwdThreads, smem, stream>>>(mq, mk, mv, mdo, mdq, p);
+  launch_pdl<true>(attn_bwd_kernel, grid, kBwdThreads, smem, stream, mq, mk, mv, mdo, mdq, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err("attention_bwd launch: %s", cudaGetErrorString(e));
@@ -976,7 +983,7 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
   const int cols8 = heads * 8;
   int64_t blocks = (nrow * cols8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  cast2d_f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(dq_acc, ld_acc, reinterpret_cast<bf16*>(dq), lddq, nrow,
+  launch_pdl(cast2d_f32_to_bf16_kernel, (int)blocks, 256, 0, stream, dq_acc, ld_acc, reinterpret_cast<bf16*>(dq), lddq, nrow,
                                                             cols8);
   e = cudaGetLastError();
   if (e != cudaSuccess) return B200PDM_ERR_CUDA;

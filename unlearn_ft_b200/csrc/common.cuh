@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #define B200PDM_OK 0
 #define B200PDM_ERR_ARG -1
@@ -114,6 +116,32 @@ __device__ __forceinline__ float exp2_fma(float x) {
   p = fmaf(f, p, 0.69327624f);
   p = fmaf(f, p, 0.99992894f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may become
+// resident while its predecessor is still draining; it must not touch global memory before pdl_wait().  pdl_trigger() at the
+// top of a kernel lets ITS successors start their prologues (barrier init, TMEM allocation, descriptor prefetch) early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Host side.  Every kernel of this library starts with pdl_trigger().  The tensor-core kernels (GEMM, attention), whose
+// prologues (mbarrier init, TMEM allocation, descriptor prefetch, cluster sync) are worth hiding, are launched with the
+// programmatic-stream-serialization attribute through launch_pdl<true> and call pdl_wait() after the prologue; the
+// streaming kernels are launched plainly through launch_pdl<false> (measured: giving them the attribute + a wait at the
+// top of every one of their thousands of short blocks costs more than it hides).  B200PDM_NO_PDL=1 disables it (A/B).
+inline int pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("B200PDM_NO_PDL") ? 0 : 1;
+  return on;
+}
+template <bool PDL = false, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (PDL && pdl_enabled()) ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 // One lane of a converged warp.  Single-thread instructions (TMA, tcgen05.mma/commit) are issued under this predicate from
 // warp-uniform code, so their operands live in uniform registers; a `lane == 0` branch instead makes the compiler wrap

@@ -3,6 +3,7 @@
 // sinusoidal timestep embedding, forward-diffusion prep.  All use 16-byte bf16x8 accesses on the common path and
 // grid-stride loops sized to a multiple of the SM count.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/b200pdm.h"
 
 #include <atomic>
@@ -23,6 +24,7 @@ static inline int grid_for(int64_t work_items, int threads) {
 // proj [rows, 2F] : value half [0,F), gate half [F,2F).  out = value * gelu_erf(gate).
 __global__ void geglu_fwd_kernel(const bf16* __restrict__ p, int64_t ldp, bf16* __restrict__ o, int64_t ldo,
                                  int64_t rows, int F, int fvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = rows * fvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / fvec;
@@ -37,6 +39,7 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ p, int64_t ldp, bf16* 
 }
 __global__ void geglu_bwd_kernel(const bf16* __restrict__ d, int64_t ldd, const bf16* __restrict__ p, int64_t ldp,
                                  bf16* __restrict__ dp, int64_t lddp, int64_t rows, int F, int fvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = rows * fvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / fvec;
@@ -59,6 +62,7 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ d, int64_t ldd, const 
 // one block per row; fp32 scores in, bf16 probabilities out. p = softmax(scale * s).
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf16* __restrict__ p, int64_t ldp, int cols,
                                    float scale) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const float* sr = s + row * lds;
@@ -75,6 +79,7 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf1
 // ds = scale * p * (dp - sum_j dp_j p_j)
 __global__ void softmax_bwd_kernel(const float* __restrict__ dp, int64_t lddp, const bf16* __restrict__ p, int64_t ldp,
                                    bf16* __restrict__ ds, int64_t ldds, int cols, float scale) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float red[32];
   const int64_t row = blockIdx.x;
   const float* dr = dp + row * lddp;
@@ -91,6 +96,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dp, int64_t lddp, c
 // grid (col_blocks, row_slices); block (32, 8): thread (tx,ty) sums column tx over its rows; smem reduce over ty.
 __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t rows, int cols,
                               int rows_per_slice) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
@@ -111,6 +117,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __
 // out[g, c] += sum over rows r of group g (r / rows_per_group == g); grid (col_blocks, groups * slices_per_group)
 __global__ void colsum_grouped_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo,
                                       int cols, int rows_per_group, int slices, int rows_per_slice) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int g = blockIdx.y / slices, s = blockIdx.y - g * slices;
@@ -129,6 +136,7 @@ __global__ void colsum_grouped_kernel(const bf16* __restrict__ x, int64_t ldx, f
   }
 }
 __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
@@ -136,6 +144,7 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __res
 // ---------------------------------------------------------------- add / copy with pitches
 __global__ void add_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ b, int64_t ldb,
                            bf16* __restrict__ o, int64_t ldo, int64_t rows, int C, int cvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = rows * cvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / cvec;
@@ -157,6 +166,7 @@ __global__ void add_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* 
 }
 __global__ void copy2d_kernel(const bf16* __restrict__ s, int64_t lds, bf16* __restrict__ d, int64_t ldd, int64_t rows,
                               int C, int cvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = rows * cvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / cvec;
@@ -172,11 +182,13 @@ __global__ void copy2d_kernel(const bf16* __restrict__ s, int64_t lds, bf16* __r
 
 // ---------------------------------------------------------------- SiLU on the (small) time embedding
 __global__ void silu_f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(silu_f(x[i]));
 }
 __global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const float* __restrict__ x, bf16* __restrict__ dx,
                                 int64_t n) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dx[i] = __float2bfloat16(__bfloat162float(dy[i]) * silu_grad_f(x[i]));
 }
@@ -188,6 +200,7 @@ __global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const float* __rest
 template <int MODE>
 __global__ void resample2x_kernel(const bf16* __restrict__ src, int64_t lds, bf16* __restrict__ dst, int64_t ldd,
                                   int batch, int h, int w, int C, int cvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   // (h, w) is the LOW resolution grid
   const int H2 = 2 * h, W2 = 2 * w;
   const int64_t total = (MODE == 1 ? (int64_t)batch * h * w : (int64_t)batch * H2 * W2) * cvec;
@@ -248,6 +261,7 @@ __global__ void resample2x_kernel(const bf16* __restrict__ src, int64_t lds, bf1
 // NCHW fp32 -> NHWC bf16 (tiny C: 4 latent channels) and back.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t ldy, int batch, int C,
                                     int hw) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = (int64_t)batch * hw * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -259,6 +273,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restric
 }
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ y, int batch, int C,
                                     int hw) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = (int64_t)batch * hw * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int p = (int)(i % hw);
@@ -272,6 +287,7 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, int64_t ldx, flo
 // ---------------------------------------------------------------- timestep embedding (flip_sin_to_cos, shift 0)
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, bf16* __restrict__ out, int64_t ldo, int batch,
                                           int dim) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int half = dim / 2;
   const int total = batch * half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -294,6 +310,7 @@ __global__ void cfg_ddim_step_kernel(const float* __restrict__ model_out, float*
                                      const float* __restrict__ alphas_cumprod, const int64_t* __restrict__ timesteps,
                                      int* __restrict__ step_idx, int64_t* __restrict__ t_dev, int n, int64_t chw, int num_steps,
                                      int train_T, float guidance, unsigned int* __restrict__ done_ctr) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int idx = *step_idx;
   const int64_t t = timesteps[idx];
   const int64_t t_prev = t - train_T / num_steps;
@@ -336,6 +353,7 @@ __global__ void diffusion_prep_kernel(const float* __restrict__ x0, const float*
                                       const int64_t* __restrict__ t, const float* __restrict__ sa,
                                       const float* __restrict__ sb, float* __restrict__ noisy, float* __restrict__ vt,
                                       int batch, int64_t n) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t total = (int64_t)batch * n;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int b = (int)(i / n);
@@ -362,7 +380,7 @@ int b200pdm_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t ldo, int
     return B200PDM_ERR_UNSUPPORTED;
   }
   const int fvec = F / 8;
-  geglu_fwd_kernel<<<grid_for(rows * fvec, 256), 256, 0, STREAM>>>(CBF(proj), ldp, BF(out), ldo, rows, F, fvec);
+  launch_pdl(geglu_fwd_kernel, grid_for(rows * fvec, 256), 256, 0, STREAM, CBF(proj), ldp, BF(out), ldo, rows, F, fvec);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -371,7 +389,7 @@ int b200pdm_geglu_bwd(const void* dout, int64_t lddo, const void* proj, int64_t 
                       int64_t rows, int F, b200pdm_stream_t stream) {
   if (F % 8 || ldp % 8 || lddo % 8 || lddp % 8) return B200PDM_ERR_UNSUPPORTED;
   const int fvec = F / 8;
-  geglu_bwd_kernel<<<grid_for(rows * fvec, 256), 256, 0, STREAM>>>(CBF(dout), lddo, CBF(proj), ldp, BF(dproj), lddp, rows,
+  launch_pdl(geglu_bwd_kernel, grid_for(rows * fvec, 256), 256, 0, STREAM, CBF(dout), lddo, CBF(proj), ldp, BF(dproj), lddp, rows,
                                                                   F, fvec);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -381,7 +399,7 @@ int b200pdm_softmax_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64
                         b200pdm_stream_t stream) {
   if (rows <= 0) return B200PDM_OK;
   int threads = cols >= 1024 ? 256 : 128;
-  softmax_fwd_kernel<<<(unsigned)rows, threads, 0, STREAM>>>(s, lds, BF(p), ldp, cols, scale);
+  launch_pdl(softmax_fwd_kernel, (unsigned)rows, threads, 0, STREAM, s, lds, BF(p), ldp, cols, scale);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -390,7 +408,7 @@ int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ld
                         int cols, float scale, b200pdm_stream_t stream) {
   if (rows <= 0) return B200PDM_OK;
   int threads = cols >= 1024 ? 256 : 128;
-  softmax_bwd_kernel<<<(unsigned)rows, threads, 0, STREAM>>>(dp, lddp, CBF(p), ldp, BF(ds), ldds, cols, scale);
+  launch_pdl(softmax_bwd_kernel, (unsigned)rows, threads, 0, STREAM, dp, lddp, CBF(p), ldp, BF(ds), ldds, cols, scale);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -402,7 +420,7 @@ int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int col
   if (rps < 64) rps = 64;
   slices = (int)((rows + rps - 1) / rps);
   dim3 grid(col_blocks, slices), block(32, 8);
-  colsum_kernel<<<grid, block, 0, STREAM>>>(CBF(x), ldx, out, rows, cols, (int)rps);
+  launch_pdl(colsum_kernel, grid, block, 0, STREAM, CBF(x), ldx, out, rows, cols, (int)rps);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -417,13 +435,13 @@ int b200pdm_colsum_grouped(const void* x, int64_t ldx, float* out, int64_t ldo, 
   if (rps < 32) rps = 32;
   slices = (rows_per_group + rps - 1) / rps;
   dim3 grid(col_blocks, groups * slices), block(32, 8);
-  colsum_grouped_kernel<<<grid, block, 0, STREAM>>>(CBF(x), ldx, out, ldo, cols, rows_per_group, slices, rps);
+  launch_pdl(colsum_grouped_kernel, grid, block, 0, STREAM, CBF(x), ldx, out, ldo, cols, rows_per_group, slices, rps);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
 }
 int b200pdm_cast_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream) {
-  cast_f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(x, BF(y), n);
+  launch_pdl(cast_f32_to_bf16_kernel, grid_for(n, 256), 256, 0, STREAM, x, BF(y), n);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -432,7 +450,7 @@ int b200pdm_add(const void* a, int64_t lda, const void* b, int64_t ldb, void* ou
                 b200pdm_stream_t stream) {
   if (lda % 8 || ldb % 8 || ldo % 8) return B200PDM_ERR_UNSUPPORTED;
   const int cvec = (C + 7) / 8;
-  add_kernel<<<grid_for(rows * cvec, 256), 256, 0, STREAM>>>(CBF(a), lda, CBF(b), ldb, BF(out), ldo, rows, C, cvec);
+  launch_pdl(add_kernel, grid_for(rows * cvec, 256), 256, 0, STREAM, CBF(a), lda, CBF(b), ldb, BF(out), ldo, rows, C, cvec);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -440,19 +458,19 @@ int b200pdm_add(const void* a, int64_t lda, const void* b, int64_t ldb, void* ou
 int b200pdm_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int C, b200pdm_stream_t stream) {
   if (lds % 8 || ldd % 8) return B200PDM_ERR_UNSUPPORTED;
   const int cvec = (C + 7) / 8;
-  copy2d_kernel<<<grid_for(rows * cvec, 256), 256, 0, STREAM>>>(CBF(src), lds, BF(dst), ldd, rows, C, cvec);
+  launch_pdl(copy2d_kernel, grid_for(rows * cvec, 256), 256, 0, STREAM, CBF(src), lds, BF(dst), ldd, rows, C, cvec);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
 }
 int b200pdm_silu_f32_to_bf16(const float* x, void* y, int64_t n, b200pdm_stream_t stream) {
-  silu_f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(x, BF(y), n);
+  launch_pdl(silu_f32_to_bf16_kernel, grid_for(n, 256), 256, 0, STREAM, x, BF(y), n);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
 }
 int b200pdm_silu_bwd(const void* dy, const float* x, void* dx, int64_t n, b200pdm_stream_t stream) {
-  silu_bwd_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(CBF(dy), x, BF(dx), n);
+  launch_pdl(silu_bwd_kernel, grid_for(n, 256), 256, 0, STREAM, CBF(dy), x, BF(dx), n);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -461,7 +479,7 @@ int b200pdm_upsample2x_fwd(const void* x, int64_t ldx, void* y, int64_t ldy, int
                            b200pdm_stream_t stream) {
   if (ldx % 8 || ldy % 8) return B200PDM_ERR_UNSUPPORTED;
   const int cvec = (C + 7) / 8;
-  resample2x_kernel<0><<<grid_for((int64_t)batch * 4 * h * w * cvec, 256), 256, 0, STREAM>>>(CBF(x), ldx, BF(y), ldy,
+  launch_pdl(resample2x_kernel<0>, grid_for((int64_t)batch * 4 * h * w * cvec, 256), 256, 0, STREAM, CBF(x), ldx, BF(y), ldy,
                                                                                              batch, h, w, C, cvec);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -471,7 +489,7 @@ int b200pdm_upsample2x_bwd(const void* dy, int64_t lddy, void* dx, int64_t lddx,
                            b200pdm_stream_t stream) {
   if (lddy % 8 || lddx % 8) return B200PDM_ERR_UNSUPPORTED;
   const int cvec = (C + 7) / 8;
-  resample2x_kernel<1><<<grid_for((int64_t)batch * h * w * cvec, 256), 256, 0, STREAM>>>(CBF(dy), lddy, BF(dx), lddx,
+  launch_pdl(resample2x_kernel<1>, grid_for((int64_t)batch * h * w * cvec, 256), 256, 0, STREAM, CBF(dy), lddy, BF(dx), lddx,
                                                                                          batch, h, w, C, cvec);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -481,7 +499,7 @@ int b200pdm_zero_insert2x(const void* x, int64_t ldx, void* y, int64_t ldy, int 
                           b200pdm_stream_t stream) {
   if (ldx % 8 || ldy % 8) return B200PDM_ERR_UNSUPPORTED;
   const int cvec = (C + 7) / 8;
-  resample2x_kernel<2><<<grid_for((int64_t)batch * 4 * h * w * cvec, 256), 256, 0, STREAM>>>(CBF(x), ldx, BF(y), ldy,
+  launch_pdl(resample2x_kernel<2>, grid_for((int64_t)batch * 4 * h * w * cvec, 256), 256, 0, STREAM, CBF(x), ldx, BF(y), ldy,
                                                                                              batch, h, w, C, cvec);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -489,21 +507,21 @@ int b200pdm_zero_insert2x(const void* x, int64_t ldx, void* y, int64_t ldy, int 
 }
 int b200pdm_nchw_f32_to_nhwc_bf16(const float* x, void* y, int64_t ldy, int batch, int C, int hw,
                                   b200pdm_stream_t stream) {
-  nchw_to_nhwc_kernel<<<grid_for((int64_t)batch * C * hw, 256), 256, 0, STREAM>>>(x, BF(y), ldy, batch, C, hw);
+  launch_pdl(nchw_to_nhwc_kernel, grid_for((int64_t)batch * C * hw, 256), 256, 0, STREAM, x, BF(y), ldy, batch, C, hw);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
 }
 int b200pdm_nhwc_bf16_to_nchw_f32(const void* x, int64_t ldx, float* y, int batch, int C, int hw,
                                   b200pdm_stream_t stream) {
-  nhwc_to_nchw_kernel<<<grid_for((int64_t)batch * C * hw, 256), 256, 0, STREAM>>>(CBF(x), ldx, y, batch, C, hw);
+  launch_pdl(nhwc_to_nchw_kernel, grid_for((int64_t)batch * C * hw, 256), 256, 0, STREAM, CBF(x), ldx, y, batch, C, hw);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
 }
 int b200pdm_timestep_embedding(const int64_t* t, void* out, int64_t ldo, int batch, int dim, b200pdm_stream_t stream) {
   if (dim % 2) return B200PDM_ERR_ARG;
-  timestep_embedding_kernel<<<grid_for((int64_t)batch * dim / 2, 128), 128, 0, STREAM>>>(t, BF(out), ldo, batch, dim);
+  launch_pdl(timestep_embedding_kernel, grid_for((int64_t)batch * dim / 2, 128), 128, 0, STREAM, t, BF(out), ldo, batch, dim);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -514,7 +532,7 @@ int b200pdm_cfg_ddim_step(const float* model_out, float* latents, float* latent_
   if (!model_out || !latents || !latent_in || !alphas_cumprod || !timesteps || !state || !t_dev || n <= 0 || chw <= 0 ||
       num_steps <= 0 || train_timesteps < num_steps)
     return B200PDM_ERR_ARG;
-  cfg_ddim_step_kernel<<<grid_for((int64_t)n * chw, 256), 256, 0, STREAM>>>(
+  launch_pdl(cfg_ddim_step_kernel, grid_for((int64_t)n * chw, 256), 256, 0, STREAM, 
       model_out, latents, latent_in, alphas_cumprod, timesteps, state, t_dev, n, chw, num_steps, train_timesteps, guidance_scale,
       reinterpret_cast<unsigned int*>(state + 1));
   B200_CHECK_LAUNCH();
@@ -524,7 +542,7 @@ int b200pdm_cfg_ddim_step(const float* model_out, float* latents, float* latent_
 int b200pdm_diffusion_prep(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
                            const float* sqrt_1macp, float* noisy, float* vtarget, int batch, int64_t n_per_sample,
                            b200pdm_stream_t stream) {
-  diffusion_prep_kernel<<<grid_for((int64_t)batch * n_per_sample, 256), 256, 0, STREAM>>>(
+  launch_pdl(diffusion_prep_kernel, grid_for((int64_t)batch * n_per_sample, 256), 256, 0, STREAM, 
       x0, noise, t, sqrt_acp, sqrt_1macp, noisy, vtarget, batch, n_per_sample);
   B200_CHECK_LAUNCH();
   g_launches++;

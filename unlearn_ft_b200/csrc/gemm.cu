@@ -378,6 +378,9 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
 template <int A_MN, int B_MN, bool PAIR>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmDev p) {
+  pdl_trigger();   // PDL: successors may start their prologues while this grid runs
+  unsigned long long gt_entry = 0;
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_b_bytes = (PAIR ? p.block_n / 2 : p.block_n) * 128;
@@ -431,7 +434,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (cluster > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the predecessor's tail; no global access before this point
   const long long t_kernel0 = (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) ? clock64() : 0;
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[8] = (long long)(gt - gt_entry);   // prologue, ns
+  }
 
   if (warp == 0) {
     {
@@ -759,6 +768,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   __syncthreads();
   if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[4] += clock64() - t_kernel0;
   if (cluster > 1) cluster_sync_all();   // no CTA exits while a peer may still arrive on / multicast into its smem
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[9] = (long long)(gt - gt_entry);   // CTA 0 entry -> after the final cluster sync, ns
+  }
   if (warp == 1) {
     tc_fence_after();
     if (pair)
@@ -955,6 +969,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldw
                                        int64_t ldo, const float* __restrict__ bias, const float* __restrict__ rowbias,
                                        int64_t ld_rowbias, int rows_per_group, const bf16* __restrict__ residual,
                                        int64_t ldr, int64_t M, int N) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int nq = (N + 3) / 4;
   const int64_t total = M * nq;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -982,7 +997,7 @@ static int launch_finalize(const b200pdm_gemm_desc* d, const float* ws, int64_t 
   const int64_t total = d->M * ((d->N + 3) / 4);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  splitk_finalize_kernel<<<(int)blocks, 256, 0, stream>>>(ws, ldws, d->out, d->out_fp32, d->ldo, d->bias, d->rowbias,
+  launch_pdl(splitk_finalize_kernel, (int)blocks, 256, 0, stream, ws, ldws, d->out, d->out_fp32, d->ldo, d->bias, d->rowbias,
                                                          d->ld_rowbias, d->rows_per_group > 0 ? d->rows_per_group : 1,
                                                          reinterpret_cast<const bf16*>(d->residual), d->ldr, d->M,
                                                          (int)d->N);
@@ -1169,8 +1184,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   static int dbg_on = -1;
   if (dbg_on < 0) dbg_on = getenv("B200PDM_GEMM_DBG") ? 1 : 0;
   if (dbg_on) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
-    cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), stream);
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
   const size_t smem = (size_t)fixed_bytes + (size_t)stages * stage_bytes;
@@ -1204,16 +1219,25 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       cudaEventCreate(&t0), cudaEventCreate(&t1);
       cudaEventRecord(t0, stream);
     }
-    if (cluster == 1) {
-      kern<<<grid, threads, smem, stream>>>(map_a, map_b, p);
-    } else {
+    {
+      static int use_pdl = -1;
+      if (use_pdl < 0) use_pdl = getenv("B200PDM_NO_PDL") ? 0 : 1;
       cudaLaunchConfig_t cfg;
       memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(grid), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = cluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr, cfg.numAttrs = 1;
+      cudaLaunchAttribute attr[2];
+      int na = 0;
+      if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+        ++na;
+      }
+      if (use_pdl) {   // may become resident during the predecessor's tail; the kernel calls griddepcontrol.wait itself
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+      }
+      cfg.attrs = attr, cfg.numAttrs = na;
       cudaLaunchKernelEx(&cfg, kern, map_a, map_b, p);
     }
     e = cudaGetLastError();
@@ -1233,12 +1257,13 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
                d->a.mode, d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.m_sub, p.splits,
                total_tiles, grid, stages, cluster);
       if (p.dbg) {
-        long long h[8];
+        long long h[16];
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
         int tiles_cta0 = (int)((total_tiles + grid / cluster - 1) / (grid / cluster));
         fprintf(stderr, "[gemm dbg] %s | cta0: total=%lld prod_wait_empty=%lld mma_wait_full=%lld mma_wait_tempty=%lld "
-                "epi_wait_tfull=%lld epi_busy=%lld tma_issue=%lld mma_issue=%lld (~%d tiles, %d kblocks)\n", key, h[4], h[0],
-                h[1], h[2], h[3], h[5], h[6], h[7], tiles_cta0, p.kb_per_split);
+                "epi_wait_tfull=%lld epi_busy=%lld tma_issue=%lld mma_issue=%lld (~%d tiles, %d kblocks) | prologue=%lld ns, "
+                "cta0 lifetime=%lld ns, kernel (events)=%.1f us\n", key, h[4], h[0], h[1], h[2], h[3], h[5], h[6], h[7], tiles_cta0,
+                p.kb_per_split, h[8], h[9], ms * 1e3);
       }
       TraceRow& r = g_trace[key];
       r.count++, r.ms += ms;

@@ -20,6 +20,7 @@ __global__ void pred_loss_kernel(const float* __restrict__ pred, const float* __
                                  const float* __restrict__ teacher, const float* __restrict__ snr_w,
                                  float* __restrict__ dpred, float* __restrict__ sums, int batch, int64_t n,
                                  float w_diff, float w_kd) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float red[32];
   const int b = blockIdx.y;
   const float wb = snr_w ? snr_w[b] : 1.f;
@@ -61,6 +62,7 @@ __global__ void pred_loss_kernel(const float* __restrict__ pred, const float* __
 __global__ void feature_loss_kernel(const bf16* __restrict__ s, const bf16* __restrict__ t, bf16* __restrict__ ds,
                                     float* __restrict__ sums, int64_t numel, float inv_maps, float gscale,
                                     float w_block) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float red[32];
   const int64_t nvec = numel >> 3;
   float acc = 0.f;
@@ -97,6 +99,7 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
                              bf16* __restrict__ shadow, int64_t n, float lr, float beta1, float beta2, float eps,
                              float wd, float bc1, float bc2_sqrt, float grad_scale, int zero_grad,
                              const float* __restrict__ dyn) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   if (dyn) {   // step-dependent scalars from device memory: the launch can sit in a replayed CUDA graph
     lr = dyn[0], bc1 = dyn[1], bc2_sqrt = dyn[2];
   }
@@ -145,6 +148,7 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
 }
 
 __global__ void refresh_shadow_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, int64_t n) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t nvec = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<const float4*>(p)[i];
@@ -171,7 +175,7 @@ int b200pdm_pred_loss(const float* pred, const float* target, const float* teach
   int bx = (int)((n_per_sample + 255) / 256);
   if (bx > 64) bx = 64;
   dim3 grid(bx, batch);
-  pred_loss_kernel<<<grid, 256, 0, STREAM>>>(pred, target, teacher, snr_w, dpred, sums, batch, n_per_sample, w_diff, w_kd);
+  launch_pdl(pred_loss_kernel, grid, 256, 0, STREAM, pred, target, teacher, snr_w, dpred, sums, batch, n_per_sample, w_diff, w_kd);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -186,7 +190,7 @@ int b200pdm_feature_loss(const void* s, const void* t, void* ds, float* sums, in
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const float gscale = w_block * inv_maps * 2.f / (float)numel;
-  feature_loss_kernel<<<(int)blocks, 256, 0, STREAM>>>(reinterpret_cast<const bf16*>(s), reinterpret_cast<const bf16*>(t),
+  launch_pdl(feature_loss_kernel, (int)blocks, 256, 0, STREAM, reinterpret_cast<const bf16*>(s), reinterpret_cast<const bf16*>(t),
                                                       reinterpret_cast<bf16*>(ds), sums, numel, inv_maps, gscale, w_block);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -206,7 +210,7 @@ int b200pdm_adamw_step(float* p, float* g, float* m, float* v, void* shadow_bf16
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, lr, beta1, beta2, eps,
+  launch_pdl(adamw_kernel, (int)blocks, 256, 0, STREAM, p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, lr, beta1, beta2, eps,
                                                weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, zero_grad, nullptr);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -223,7 +227,7 @@ int b200pdm_adamw_step_dyn(float* p, float* g, float* m, float* v, void* shadow_
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  adamw_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, 0.f, beta1, beta2, eps,
+  launch_pdl(adamw_kernel, (int)blocks, 256, 0, STREAM, p, g, m, v, reinterpret_cast<bf16*>(shadow_bf16), n, 0.f, beta1, beta2, eps,
                                                weight_decay, 1.f, 1.f, grad_scale, zero_grad, dyn);
   B200_CHECK_LAUNCH();
   g_launches++;
@@ -235,7 +239,7 @@ int b200pdm_refresh_shadow(const float* p, void* shadow_bf16, int64_t n, b200pdm
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  refresh_shadow_kernel<<<(int)blocks, 256, 0, STREAM>>>(p, reinterpret_cast<bf16*>(shadow_bf16), n);
+  launch_pdl(refresh_shadow_kernel, (int)blocks, 256, 0, STREAM, p, reinterpret_cast<bf16*>(shadow_bf16), n);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

@@ -29,6 +29,7 @@ template <int MODE>
 __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ dy, int64_t lddy,
                                    const float* __restrict__ tab, float* __restrict__ out0, float* __restrict__ out1,
                                    int B, int hw, int C, int ldc, int silu, int slices) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float red[8][32][17];
   const int b = blockIdx.x;
   const int cv = blockIdx.y * 32 + threadIdx.x;
@@ -101,6 +102,7 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
 __global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, int B, int C, int cpg, int ldc, float inv_n,
                                        float eps) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
@@ -122,6 +124,7 @@ __global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __r
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ tab,
                                 bf16* __restrict__ y, int64_t ldy, int B, int hw, int C, int ldc, int silu,
                                 int64_t total_vec, int cvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t plane = (int64_t)B * ldc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / cvec;
@@ -160,6 +163,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const f
 __global__ void gn_bwd_finalize_kernel(float* __restrict__ ws, const float* __restrict__ tab,
                                        const float* __restrict__ gamma, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, int B, int C, int cpg, int ldc, float inv_n) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
@@ -182,6 +186,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
                                     const float* __restrict__ tab, const float* __restrict__ ws,
                                     const bf16* __restrict__ res, int64_t ldr, bf16* __restrict__ dx, int64_t lddx,
                                     int B, int hw, int C, int ldc, int silu, int64_t total_vec, int cvec) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t plane = (int64_t)B * ldc;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / cvec;
@@ -244,6 +249,7 @@ template <int MAXV, int R>
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
                               const float* __restrict__ beta, bf16* __restrict__ y, int64_t ldy,
                               float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int C, float eps) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   // One warp normalises R consecutive rows; all of their loads are issued before any arithmetic and the rows stay PACKED
   // (bf16) in registers between the passes: short rows (640 bytes at C = 320) need many warps x rows in flight per SM to
   // reach HBM bandwidth, so the register footprint decides the throughput.
@@ -321,6 +327,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict_
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const bf16* __restrict__ res, int64_t ldr, bf16* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
               float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   extern __shared__ float sh[];  // dgamma[C], dbeta[C]
   float* sdg = sh;
   float* sdb = sh + C;
@@ -447,17 +454,17 @@ int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
   if (slices > hw / 16) slices = hw / 16 > 0 ? hw / 16 : 1;
   if (slices < 1) slices = 1;
   const bf16* xb = reinterpret_cast<const bf16*>(x);
-  gn_colstats_kernel<GN_FWD_STATS><<<dim3(batch, cchunks, slices), dim3(32, 8), 0, stream>>>(
+  launch_pdl(gn_colstats_kernel<GN_FWD_STATS>, dim3(batch, cchunks, slices), dim3(32, 8), 0, stream, 
       xb, ldx, nullptr, 0, nullptr, stats + 4 * plane, stats + 5 * plane, batch, hw, C, ldc, 0, slices);
   B200_CHECK_LAUNCH();
   const int n = batch * C;
-  gn_fwd_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(stats, gamma, beta, batch, C, cpg, ldc,
+  launch_pdl(gn_fwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, stats, gamma, beta, batch, C, cpg, ldc,
                                                              1.f / ((float)hw * cpg), eps);
   B200_CHECK_LAUNCH();
   const int64_t total_vec = (int64_t)batch * hw * cvec;
   int blocks = (int)((total_vec + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_apply_kernel<<<blocks, 256, 0, stream>>>(xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc, silu,
+  launch_pdl(gn_apply_kernel, blocks, 256, 0, stream, xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc, silu,
                                              total_vec, cvec);
   B200_CHECK_LAUNCH();
   g_launches += 4;
@@ -483,17 +490,17 @@ int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   if (slices < 1) slices = 1;
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
-  gn_colstats_kernel<GN_BWD_STATS><<<dim3(batch, cchunks, slices), dim3(32, 8), 0, stream>>>(
+  launch_pdl(gn_colstats_kernel<GN_BWD_STATS>, dim3(batch, cchunks, slices), dim3(32, 8), 0, stream, 
       xb, ldx, dyb, lddy, stats, workspace, workspace + plane, batch, hw, C, ldc, silu, slices);
   B200_CHECK_LAUNCH();
   const int n = batch * C;
-  gn_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(workspace, stats, gamma, dgamma, dbeta, batch, C, cpg, ldc,
+  launch_pdl(gn_bwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, workspace, stats, gamma, dgamma, dbeta, batch, C, cpg, ldc,
                                                              1.f / ((float)hw * cpg));
   B200_CHECK_LAUNCH();
   const int64_t total_vec = (int64_t)batch * hw * cvec;
   int blocks = (int)((total_vec + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gn_bwd_apply_kernel<<<blocks, 256, 0, stream>>>(dyb, lddy, xb, ldx, stats, workspace,
+  launch_pdl(gn_bwd_apply_kernel, blocks, 256, 0, stream, dyb, lddy, xb, ldx, stats, workspace,
                                                  reinterpret_cast<const bf16*>(residual), ldr,
                                                  reinterpret_cast<bf16*>(dx), lddx, batch, hw, C, ldc, silu, total_vec,
                                                  cvec);
@@ -514,13 +521,13 @@ int b200pdm_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
   bf16* yb = reinterpret_cast<bf16*>(y);
   auto nblocks = [&](int r) { return (int)((rows + (int64_t)wpb * r - 1) / ((int64_t)wpb * r)); };
   if (C <= 8 * 32 * 2)
-    ln_fwd_kernel<2, 4><<<nblocks(4), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    launch_pdl(ln_fwd_kernel<2, 4>, nblocks(4), wpb * 32, 0, stream, xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   else if (C <= 8 * 32 * 3)
-    ln_fwd_kernel<3, 2><<<nblocks(2), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    launch_pdl(ln_fwd_kernel<3, 2>, nblocks(2), wpb * 32, 0, stream, xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   else if (C <= 8 * 32 * 5)
-    ln_fwd_kernel<5, 1><<<nblocks(1), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    launch_pdl(ln_fwd_kernel<5, 1>, nblocks(1), wpb * 32, 0, stream, xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   else
-    ln_fwd_kernel<8, 1><<<nblocks(1), wpb * 32, 0, stream>>>(xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
+    launch_pdl(ln_fwd_kernel<8, 1>, nblocks(1), wpb * 32, 0, stream, xb, ldx, gamma, beta, yb, ldy, mean, rstd, rows, C, eps);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
@@ -545,13 +552,13 @@ int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   const bf16* rb = reinterpret_cast<const bf16*>(residual);
   if (residual && ldr % 8) return B200PDM_ERR_UNSUPPORTED;
   if (C <= 8 * 32 * 2)
-    ln_bwd_kernel<2, 2><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+    launch_pdl(ln_bwd_kernel<2, 2>, blocks, 256, sh, stream, dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
                                                     dbeta, rows, C, rows_per_block);
   else if (C <= 8 * 32 * 3)
-    ln_bwd_kernel<3, 1><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+    launch_pdl(ln_bwd_kernel<3, 1>, blocks, 256, sh, stream, dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
                                                     dbeta, rows, C, rows_per_block);
   else
-    ln_bwd_kernel<5, 1><<<blocks, 256, sh, stream>>>(dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
+    launch_pdl(ln_bwd_kernel<5, 1>, blocks, 256, sh, stream, dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
                                                     dbeta, rows, C, rows_per_block);
   B200_CHECK_LAUNCH();
   g_launches++;
