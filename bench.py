@@ -412,14 +412,20 @@ def main():
     ms_total = float(ms)
 
     # ---- timed: end to end from pinned host memory through the public API
+    def e2e_step(i):
+        hb = host_batches[i % len(host_batches)]
+        if use_graph:
+            loss, _, _, _ = tuner.train_step(hb)                # H2D straight from pinned memory into the graph's input buffers
+        else:
+            loss, _, _, _ = tuner.train_step({k: v.cuda(non_blocking=True) for k, v in hb.items()})
+        return float(loss)                                      # D2H read of the step's result (4 bytes) + sync
+
+    e2e_step(0)                                                 # untimed: first-use effects of this code path (allocator)
     barrier()
     e0.record()
     last = None
     for i in range(args.steps):
-        hb = host_batches[i % len(host_batches)]
-        db = {k: v.cuda(non_blocking=True) for k, v in hb.items()}
-        loss, _, _, _ = tuner.train_step(db)
-        last = float(loss)                                      # D2H read of the step's result (4 bytes) + sync
+        last = e2e_step(i)
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
