@@ -107,6 +107,16 @@ def test_colsum_add_copy():
     out = torch.zeros(170, device="cuda")
     k.colsum(x, out)
     assert rel_err(out, x.float().sum(0)) < 1e-4
+    wide = rand2d(3000, 510, 2)                       # column slice at an odd (pruned-width) offset: unaligned view
+    out2 = torch.zeros(170, device="cuda")
+    from unlearn_ft_b200 import _lib                  # (the tensor wrapper insists on aligned views; the C ABI has a scalar path)
+    view = wide[:, 170:340]
+    assert _lib.lib().b200pdm_colsum(view.data_ptr(), view.stride(0), out2.data_ptr(), view.shape[0], view.shape[1],
+                                     torch.cuda.current_stream().cuda_stream) == 0
+    assert rel_err(out2, wide[:, 170:340].float().sum(0)) < 1e-4
+    out3 = torch.zeros(320, device="cuda")
+    k.colsum(rand2d(70000, 320, 3), out3)             # > 1 slice per column block, full vectors
+    assert rel_err(out3, rand2d(70000, 320, 3).float().sum(0)) < 1e-4
     assert rel_err(k.add(x, y), x.float() + y.float()) < 1e-2
     dst = k.alloc2d(5000, 512, zero=True)
     k.copy2d(x, dst[:, 320:320 + 170])

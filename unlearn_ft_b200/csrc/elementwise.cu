@@ -94,8 +94,9 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ dp, int64_t lddp, c
 
 // ---------------------------------------------------------------- column sums (bias gradients)
 // grid (col_blocks, row_slices); block (32, 8): thread (tx,ty) sums column tx over its rows; smem reduce over ty.
-__global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t rows, int cols,
-                              int rows_per_slice) {
+// Scalar variant for views whose base or pitch is not 16-byte aligned (column slices at pruned, odd offsets).
+__global__ void colsum_scalar_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t rows, int cols,
+                                     int rows_per_slice) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   __shared__ float sh[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -110,6 +111,41 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __
     float t = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+__global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t rows, int cols,
+                              int rows_per_slice) {
+  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
+  // block (32, 8): lane -> 8 consecutive columns (one 16-byte load per row), threadIdx.y -> row lane; ldx is a multiple of 8
+  // and rows are padded to it, so the last (partial) vector of a row may be read but is masked when written.
+  __shared__ float sh[8][32][9];
+  const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t r1 = min(rows, r0 + rows_per_slice);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c0 < cols) {
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + r * ldx + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;   // 256 threads <-> 32 vectors x 8 columns
+  const int vx = tid >> 3, jj = tid & 7;
+  const int c = (blockIdx.x * 32 + vx) * 8 + jj;
+  if (c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += sh[y][vx][jj];
     atomicAdd(out + c, t);
   }
 }
@@ -414,13 +450,17 @@ int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ld
   return B200PDM_OK;
 }
 int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream) {
-  int col_blocks = (cols + 31) / 32;
+  const bool vec = (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  int col_blocks = vec ? (cols + 255) / 256 : (cols + 31) / 32;
   int slices = (148 * 4 + col_blocks - 1) / col_blocks;
   int64_t rps = (rows + slices - 1) / slices;
   if (rps < 64) rps = 64;
   slices = (int)((rows + rps - 1) / rps);
   dim3 grid(col_blocks, slices), block(32, 8);
-  launch_pdl(colsum_kernel, grid, block, 0, STREAM, CBF(x), ldx, out, rows, cols, (int)rps);
+  if (vec)
+    launch_pdl(colsum_kernel, grid, block, 0, STREAM, CBF(x), ldx, out, rows, cols, (int)rps);
+  else
+    launch_pdl(colsum_scalar_kernel, grid, block, 0, STREAM, CBF(x), ldx, out, rows, cols, (int)rps);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;
