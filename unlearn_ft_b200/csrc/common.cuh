@@ -424,9 +424,16 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return r;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid through ONE special-function op: s(x) = 0.5 + 0.5 tanh(x / 2)  (tanh.approx.f32: 2^-11 relative error; the
+// exp + reciprocal form costs two MUFU ops per element, and the GroupNorm(+SiLU) passes are MUFU-sensitive).
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
+  const float s = sigmoid_f(x);
   return s * (1.f + x * (1.f - s));
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }

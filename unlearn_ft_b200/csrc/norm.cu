@@ -30,9 +30,10 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
                                    const float* __restrict__ tab, float* __restrict__ out0, float* __restrict__ out1,
                                    int B, int hw, int C, int ldc, int silu, int slices) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
-  __shared__ float red[8][32][17];
+  __shared__ float red[256][17];   // [row lane * VL + vector lane][16 partial sums]
+  const int VL = blockDim.x, RL = blockDim.y;   // (8|16|32) x (256 / VL): see apply_geom()
   const int b = blockIdx.x;
-  const int cv = blockIdx.y * 32 + threadIdx.x;
+  const int cv = blockIdx.y * VL + threadIdx.x;
   const int c0 = cv * 8;
   const int s = blockIdx.z;
   const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
@@ -52,7 +53,7 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
     }
     const int64_t row0 = (int64_t)b * hw;
 #pragma unroll 4
-    for (int p = p0 + threadIdx.y; p < p1; p += 8) {
+    for (int p = p0 + threadIdx.y; p < p1; p += RL) {
       float xf[8];
       const bf16* xp = x + (row0 + p) * ldx + c0;
       if (nv == 8) {
@@ -83,17 +84,16 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
       }
     }
   }
+  const int tid = threadIdx.y * VL + threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = a0[j], red[threadIdx.y][threadIdx.x][8 + j] = a1[j];
+  for (int j = 0; j < 8; ++j) red[tid][j] = a0[j], red[tid][8 + j] = a1[j];
   __syncthreads();
-  // 256 threads reduce 32 vectors x 16 values over the 8 row lanes
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int k = tid; k < 32 * 16; k += 256) {
+  // 256 threads reduce VL vectors x 16 values over the RL row lanes
+  for (int k = tid; k < VL * 16; k += 256) {
     const int vx = k >> 4, jj = k & 15;
     float t = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) t += red[y][vx][jj];
-    const int c = (blockIdx.y * 32 + vx) * 8 + (jj & 7);
+    for (int y = 0; y < RL; ++y) t += red[y * VL + vx][jj];
+    const int c = (blockIdx.y * VL + vx) * 8 + (jj & 7);
     if (c < C) atomicAdd((jj < 8 ? out0 : out1) + (int64_t)b * ldc + c, t);
   }
 }
@@ -121,18 +121,29 @@ __global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __r
 }
 
 // y = act(x * scale + shift)
+// y = [silu](x * scale[b, c] + shift[b, c]).  grid (B, channel-vector chunks, row slices), block (VL, 256 / VL): a thread
+// owns 8 fixed channels of one sample -- its coefficients stay in registers -- and walks the rows of its slice (no index
+// divisions, one 16-byte load and store per row).
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ tab,
-                                bf16* __restrict__ y, int64_t ldy, int B, int hw, int C, int ldc, int silu,
-                                int64_t total_vec, int cvec) {
+                                bf16* __restrict__ y, int64_t ldy, int B, int hw, int C, int ldc, int silu, int slices) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
+  const int b = blockIdx.x;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c0 >= C) return;
+  const int nv = min(8, C - c0);
   const int64_t plane = (int64_t)B * ldc;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / cvec;
-    const int c0 = (int)(i - row * cvec) * 8;
-    const int b = (int)(row / hw);
-    const int nv = min(8, C - c0);
-    const bf16* xp = x + row * ldx + c0;
-    bf16* yp = y + row * ldy + c0;
+  const float* tp = tab + (int64_t)b * ldc + c0;   // ldc % 8 == 0 -> 32-byte aligned vector loads
+  const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
+  const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const int s = blockIdx.z;
+  const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
+  const int64_t row0 = (int64_t)b * hw;
+#pragma unroll 4
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const bf16* xp = x + (row0 + p) * ldx + c0;
+    bf16* yp = y + (row0 + p) * ldy + c0;
     float f[8];
     if (nv == 8) {
       unpack8(*reinterpret_cast<const bf16x8*>(xp), f);
@@ -140,11 +151,6 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const f
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
     }
-    const float* tp = tab + (int64_t)b * ldc + c0;   // ldc % 8 == 0 -> 32-byte aligned vector loads
-    const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float v = fmaf(f[j], sc[j], sh[j]);
@@ -182,17 +188,33 @@ __global__ void gn_bwd_finalize_kernel(float* __restrict__ ws, const float* __re
 }
 
 // dx = scale * dz + x * P + Q (+ residual)
+// dx = scale * dz + x * P + Q (+ residual), dz = dy * silu'(x * scale + shift).  Same thread layout as gn_apply_kernel.
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
                                     const float* __restrict__ tab, const float* __restrict__ ws,
                                     const bf16* __restrict__ res, int64_t ldr, bf16* __restrict__ dx, int64_t lddx,
-                                    int B, int hw, int C, int ldc, int silu, int64_t total_vec, int cvec) {
+                                    int B, int hw, int C, int ldc, int silu, int slices) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
+  const int b = blockIdx.x;
+  const int c0 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c0 >= C) return;
+  const int nv = min(8, C - c0);
   const int64_t plane = (int64_t)B * ldc;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / cvec;
-    const int c0 = (int)(i - row * cvec) * 8;
-    const int b = (int)(row / hw);
-    const int nv = min(8, C - c0);
+  const float* tp = tab + (int64_t)b * ldc + c0;
+  const float* wp = ws + (int64_t)b * ldc + c0;
+  const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
+  const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
+  const float4 q0 = *reinterpret_cast<const float4*>(wp + 2 * plane), q1 = *reinterpret_cast<const float4*>(wp + 2 * plane + 4);
+  const float4 r0 = *reinterpret_cast<const float4*>(wp + 3 * plane), r1 = *reinterpret_cast<const float4*>(wp + 3 * plane + 4);
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const float P[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  const float Q[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const int s = blockIdx.z;
+  const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
+  const int64_t row0 = (int64_t)b * hw;
+#pragma unroll 2
+  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
+    const int64_t row = row0 + p;
     float xf[8], df[8], o[8];
     const bf16* xp = x + row * ldx + c0;
     const bf16* dp = dy + row * lddy + c0;
@@ -206,16 +228,6 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
         df[j] = j < nv ? __bfloat162float(dp[j]) : 0.f;
       }
     }
-    const float* tp = tab + (int64_t)b * ldc + c0;
-    const float* wp = ws + (int64_t)b * ldc + c0;
-    const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
-    const float4 p0 = *reinterpret_cast<const float4*>(wp + 2 * plane), p1 = *reinterpret_cast<const float4*>(wp + 2 * plane + 4);
-    const float4 q0 = *reinterpret_cast<const float4*>(wp + 3 * plane), q1 = *reinterpret_cast<const float4*>(wp + 3 * plane + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    const float P[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    const float Q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float dz = df[j];
@@ -436,6 +448,28 @@ using namespace b200;
 extern "C" {
 
 // stats: fp32 [6][batch][round8(C)]: coefficient tables scale, shift, rstd, mean*rstd (+ 2 planes of scratch sums).
+// Launch geometry of the GroupNorm apply passes: VL lanes across 8-channel vectors (the narrowest of 8 / 16 / 32 that wastes
+// the fewest lanes on the last chunk), 256 / VL row lanes, and enough row slices for ~8 blocks per SM.
+struct ApplyGeom {
+  dim3 grid, block;
+  int slices;
+};
+static ApplyGeom apply_geom(int batch, int hw, int cvec) {
+  int best_vl = 32, best_waste = 1 << 30;
+  for (int vl = 8; vl <= 32; vl *= 2) {
+    const int waste = (cvec + vl - 1) / vl * vl - cvec;
+    if (waste < best_waste || (waste == best_waste && vl > best_vl)) best_waste = waste, best_vl = vl;
+  }
+  const int chunks = (cvec + best_vl - 1) / best_vl;
+  int slices = (148 * 8 + batch * chunks - 1) / (batch * chunks);
+  const int rl = 256 / best_vl;
+  if (slices > hw / (4 * rl)) slices = hw / (4 * rl) > 0 ? hw / (4 * rl) : 1;
+  if (slices < 1) slices = 1;
+  ApplyGeom g;
+  g.grid = dim3(batch, chunks, slices), g.block = dim3(best_vl, rl), g.slices = slices;
+  return g;
+}
+
 int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                           float* stats, int batch, int hw, int C, int groups, float eps, int silu,
                           b200pdm_stream_t stream_) {
@@ -449,23 +483,18 @@ int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
   const int64_t plane = (int64_t)batch * ldc;
   if (cudaMemsetAsync(stats, 0, sizeof(float) * 6 * plane, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
   const int cvec = (C + 7) / 8;
-  const int cchunks = (cvec + 31) / 32;
-  int slices = (148 * 3 + batch * cchunks - 1) / (batch * cchunks);
-  if (slices > hw / 16) slices = hw / 16 > 0 ? hw / 16 : 1;
-  if (slices < 1) slices = 1;
+  const ApplyGeom sg = apply_geom(batch, hw, cvec);
   const bf16* xb = reinterpret_cast<const bf16*>(x);
-  launch_pdl(gn_colstats_kernel<GN_FWD_STATS>, dim3(batch, cchunks, slices), dim3(32, 8), 0, stream, 
-      xb, ldx, nullptr, 0, nullptr, stats + 4 * plane, stats + 5 * plane, batch, hw, C, ldc, 0, slices);
+  launch_pdl(gn_colstats_kernel<GN_FWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, nullptr, 0, nullptr, stats + 4 * plane,
+             stats + 5 * plane, batch, hw, C, ldc, 0, sg.slices);
   B200_CHECK_LAUNCH();
   const int n = batch * C;
   launch_pdl(gn_fwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, stats, gamma, beta, batch, C, cpg, ldc,
                                                              1.f / ((float)hw * cpg), eps);
   B200_CHECK_LAUNCH();
-  const int64_t total_vec = (int64_t)batch * hw * cvec;
-  int blocks = (int)((total_vec + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  launch_pdl(gn_apply_kernel, blocks, 256, 0, stream, xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc, silu,
-                                             total_vec, cvec);
+  const ApplyGeom& ag = sg;
+  launch_pdl(gn_apply_kernel, ag.grid, ag.block, 0, stream, xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc,
+             silu, ag.slices);
   B200_CHECK_LAUNCH();
   g_launches += 4;
   return B200PDM_OK;
@@ -484,26 +513,19 @@ int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   const int64_t plane = (int64_t)batch * ldc;
   if (cudaMemsetAsync(workspace, 0, sizeof(float) * 4 * plane, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
   const int cvec = (C + 7) / 8;
-  const int cchunks = (cvec + 31) / 32;
-  int slices = (148 * 3 + batch * cchunks - 1) / (batch * cchunks);
-  if (slices > hw / 16) slices = hw / 16 > 0 ? hw / 16 : 1;
-  if (slices < 1) slices = 1;
+  const ApplyGeom sg = apply_geom(batch, hw, cvec);
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
-  launch_pdl(gn_colstats_kernel<GN_BWD_STATS>, dim3(batch, cchunks, slices), dim3(32, 8), 0, stream, 
-      xb, ldx, dyb, lddy, stats, workspace, workspace + plane, batch, hw, C, ldc, silu, slices);
+  launch_pdl(gn_colstats_kernel<GN_BWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, dyb, lddy, stats, workspace,
+             workspace + plane, batch, hw, C, ldc, silu, sg.slices);
   B200_CHECK_LAUNCH();
   const int n = batch * C;
   launch_pdl(gn_bwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, workspace, stats, gamma, dgamma, dbeta, batch, C, cpg, ldc,
                                                              1.f / ((float)hw * cpg));
   B200_CHECK_LAUNCH();
-  const int64_t total_vec = (int64_t)batch * hw * cvec;
-  int blocks = (int)((total_vec + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  launch_pdl(gn_bwd_apply_kernel, blocks, 256, 0, stream, dyb, lddy, xb, ldx, stats, workspace,
-                                                 reinterpret_cast<const bf16*>(residual), ldr,
-                                                 reinterpret_cast<bf16*>(dx), lddx, batch, hw, C, ldc, silu, total_vec,
-                                                 cvec);
+  const ApplyGeom& ag = sg;
+  launch_pdl(gn_bwd_apply_kernel, ag.grid, ag.block, 0, stream, dyb, lddy, xb, ldx, stats, workspace,
+             reinterpret_cast<const bf16*>(residual), ldr, reinterpret_cast<bf16*>(dx), lddx, batch, hw, C, ldc, silu, ag.slices);
   B200_CHECK_LAUNCH();
   g_launches += 4;
   return B200PDM_OK;
