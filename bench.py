@@ -49,6 +49,10 @@ def parse():
                          "--images per GPU, 50 DDIM steps, guidance 7.5; a 'step' is one complete 50-step sampling call")
     ap.add_argument("--images", type=int, default=32, help="--sampling: images per GPU (U-Net batch = 2x)")
     ap.add_argument("--cpu-steps", type=int, default=1)
+    ap.add_argument("--bilevel", action="store_true",
+                    help="BASELINE config 4: bilevel fine-tuning + concept suppression -- every --upper-freq lower (DDPM+KD) "
+                         "steps one upper (ESD-style unlearning) step with its own AdamW state; samples/s over whole cycles")
+    ap.add_argument("--upper-freq", type=int, default=10)
     return ap.parse_args()
 
 
@@ -348,14 +352,23 @@ def main():
     from unlearn_ft_b200 import kernels as K
     from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModel, UNet2DConditionModelPruned
     from unlearn_ft_b200.pdm.models.unet.unet_2d_conditional import SD21_CONFIG, structure_from_config
-    from unlearn_ft_b200.pdm.training import UnetFineTuner
+    from unlearn_ft_b200.pdm.training import BilevelUnetFineTuner, UnetFineTuner
 
     torch.manual_seed(43)                                           # same arch vector on every rank
     av = HyperStructure.get_random_arch_vector(args.ratio, structure_from_config(SD21_CONFIG))
     student = UNet2DConditionModelPruned(arch_vector=av, seed=43)   # random_init path (configs/*_random.yaml:27)
     teacher = UNet2DConditionModel(seed=44)
-    tuner = UnetFineTuner(student, teacher, lr=1e-6, warmup_steps=250)
     B, L = args.batch, args.latent
+    freq = max(1, args.upper_freq)
+    if args.bilevel:
+        # reference bilevel config: lower lr 1e-6 with warm-up, upper lr 5e-6, upper step every 10th lower step
+        tuner = BilevelUnetFineTuner(student, teacher, lr=1e-6, warmup_steps=250, upper_lr=5e-6, upper_step_freq=freq)
+        args.steps = -(-args.steps // freq) * freq                 # whole cycles: any K = n*freq consecutive steps hold n upper steps
+        workload = (f"bilevel fine-tuning + concept suppression: APTP r={args.ratio} pruned SD-2.1 U-Net + frozen SD-2.1 teacher, "
+                    f"{freq} lower DDPM+KD steps then 1 upper step (teacher cond/uncond, target 2*uncond-cond, second AdamW), "
+                    f"batch {args.batch}/GPU, {args.latent}x{args.latent} latent, bf16")
+    else:
+        tuner = UnetFineTuner(student, teacher, lr=1e-6, warmup_steps=250)
     g = torch.Generator().manual_seed(1000 + rank)                  # independent data per rank
 
     def host_batch():
@@ -367,6 +380,17 @@ def main():
     host_batches = [host_batch() for _ in range(4)]
     dev_batches = [{k: v.cuda(non_blocking=True) for k, v in hb.items()} for hb in host_batches]
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    host_upper = dev_upper = None
+    if args.bilevel:                                                # upper batches: own data + the "" prompt embedding for every sample
+        empty = torch.randn(1, 77, 1024, generator=g).bfloat16()
+        host_upper = [dict(host_batch(), empty_prompt_embeds=empty.expand(B, 77, 1024).contiguous().pin_memory()) for _ in range(2)]
+        dev_upper = [{k: v.cuda(non_blocking=True) for k, v in hb.items()} for hb in host_upper]
+        h2d_upper = sum(v.numel() * v.element_size() for v in host_upper[0].values())
+
+    def train_step(i, batches, upper):
+        if args.bilevel:
+            return tuner.train_step(batches[i % len(batches)], upper[i % len(upper)])
+        return tuner.train_step(batches[i % len(batches)])
 
     def barrier():
         if world > 1:
@@ -376,8 +400,13 @@ def main():
     # warm-up (eager), and the number of kernels one step launches
     for i in range(max(args.warmup, 3)):
         n_before = _lib.launch_count()
-        tuner.train_step(dev_batches[i % len(dev_batches)])
+        train_step(i, dev_batches, dev_upper)
         launches_per_step = _lib.launch_count() - n_before
+    if args.bilevel:                                                # one whole eager cycle: launches of freq lower + 1 upper step
+        n_before = _lib.launch_count()
+        for i in range(freq):
+            train_step(i, dev_batches, dev_upper)
+        launches_per_step = (_lib.launch_count() - n_before) / freq
     barrier()
     # The whole step (forward x2, backward with its overlapped per-block NCCL all-reduces, AdamW: ~2300 launches) is replayed
     # from ONE CUDA graph, so the host costs microseconds per step and a per-step result read-back cannot starve the GPU.
@@ -385,9 +414,12 @@ def main():
     use_graph = not args.no_graph
     if use_graph:
         try:
-            tuner.capture_cuda_graph(dev_batches[0])
-            for i in range(2):
-                tuner.train_step(dev_batches[i % len(dev_batches)])
+            if args.bilevel:
+                tuner.capture_cuda_graph(dev_batches[0], dev_upper[0])
+            else:
+                tuner.capture_cuda_graph(dev_batches[0])
+            for i in range(freq if args.bilevel else 2):
+                train_step(i, dev_batches, dev_upper)
         except Exception as e:                                     # report it instead of silently changing the metric
             print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); using the eager step", file=sys.stderr)
             tuner._graph = None
@@ -402,7 +434,7 @@ def main():
     barrier()
     e0.record()
     for i in range(args.steps):
-        tuner.train_step(dev_batches[i % len(dev_batches)])
+        train_step(i, dev_batches, dev_upper)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -414,10 +446,14 @@ def main():
     # ---- timed: end to end from pinned host memory through the public API
     def e2e_step(i):
         hb = host_batches[i % len(host_batches)]
-        if use_graph:
-            loss, _, _, _ = tuner.train_step(hb)                # H2D straight from pinned memory into the graph's input buffers
+        to_dev = (lambda b: b) if use_graph else (lambda b: {k: v.cuda(non_blocking=True) for k, v in b.items()})
+        if args.bilevel:                                        # (the upper batch is only copied on the steps that use it)
+            ub = to_dev(host_upper[i % len(host_upper)]) if (tuner.global_step + 1) % freq == 0 else None
+            loss, _, _, _ = tuner.train_step(to_dev(hb), ub)
+            if tuner.last_upper is not None:
+                return float(loss) + 0.0 * float(tuner.last_upper[0])   # both steps' results are read back
         else:
-            loss, _, _, _ = tuner.train_step({k: v.cuda(non_blocking=True) for k, v in hb.items()})
+            loss, _, _, _ = tuner.train_step(to_dev(hb))        # graph: H2D straight from pinned memory into its input buffers
         return float(loss)                                      # D2H read of the step's result (4 bytes) + sync
 
     e2e_step(0)                                                 # untimed: first-use effects of this code path (allocator)
@@ -453,6 +489,9 @@ def main():
         return
 
     samples = world * B * args.steps
+    if args.bilevel:
+        samples += world * B * (args.steps // freq)             # the upper steps' batches
+        h2d = h2d + h2d_upper / freq
     value = samples / (ms_total * 1e-3)
     e2e_value = samples / (ms_e2e * 1e-3)
     peaks = {}
@@ -464,6 +503,10 @@ def main():
     hbm = adamw_roofline(torch, K, student)
     peak_burst = peaks.get("bf16_tflops", 1590.0)
     step_tf = STEP_TFLOP_PER_SAMPLE.get(round(args.ratio, 2), 2.196) * B / (ms_total / args.steps * 1e-3) if ms_total else 0
+    if args.bilevel:   # upper step = 2 teacher fwd + student fwd + bwd = 2*0.804 + 3*fwd_s TFLOP/sample
+        fwd_s = (STEP_TFLOP_PER_SAMPLE.get(round(args.ratio, 2), 2.196) - 0.804) / 3
+        cyc = freq * STEP_TFLOP_PER_SAMPLE.get(round(args.ratio, 2), 2.196) + 2 * 0.804 + 3 * fwd_s
+        step_tf = cyc * B * (args.steps // freq) / (ms_total * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -491,7 +534,11 @@ def main():
                      "step_algorithmic_tflops": step_tf,
                      "step_frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", 1400.0)},
     }
-    if not args.no_cpu_baseline and world == 1:
+    if args.bilevel:
+        line["config"]["cycle"] = (f"{freq} lower + 1 upper step per cycle, {args.steps // freq} cycle(s) timed; value counts the "
+                                   f"samples of both kinds of step; ms_per_step = cycle time / {freq}")
+        line["config"]["step_launch"] += " (lower and upper step are two graphs sharing one memory pool)" if use_graph else ""
+    if not args.no_cpu_baseline and world == 1 and not args.bilevel:
         try:
             res = cpu_reference_run(args.ratio, L, args.cpu_steps, 0)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}

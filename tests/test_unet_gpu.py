@@ -272,3 +272,43 @@ def test_cuda_graph_step_matches_eager(gold):
     d0, d1 = (p0 - init.arena.master.detach()).flatten(), (p1 - init.arena.master.detach()).flatten()
     assert F.cosine_similarity(d0, d1, dim=0).item() > 0.98
     assert rel(p1, p0) < 5e-3
+
+
+def test_bilevel_cuda_graphs_match_eager(gold):
+    """Lower and upper step replayed from their two CUDA graphs (shared memory pool) follow the eager bilevel loop
+    (trainer.py:2795-2816): same losses, same schedule of the two optimizers, same parameter update; capture trains nothing."""
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel
+    from unlearn_ft_b200.pdm.training import BilevelUnetFineTuner
+    av = gold["small64_r055"]["arch_vector"]
+    g = torch.Generator().manual_seed(9)
+    empty = torch.randn(1, 77, small_cfg()["cross_attention_dim"], generator=g).expand(2, -1, -1).contiguous().cuda()
+    batches = [make_batch(seed=s) for s in range(4)]
+    uppers = [dict(make_batch(seed=10 + s), empty_prompt_embeds=empty) for s in range(4)]
+    runs = []
+    for graphed in (False, True):
+        mine, _ = build_pair(av, trainable=True)
+        teacher = UNet2DConditionModel(small_cfg(), seed=7)
+        tuner = BilevelUnetFineTuner(mine, teacher, lr=1e-4, upper_lr=1e-4, upper_step_freq=2, warmup_steps=0)
+        if graphed:
+            before = mine.arena.master.detach().clone()
+            tuner.capture_cuda_graph(batches[0], uppers[0])
+            assert torch.equal(mine.arena.master.detach(), before)
+            assert float(tuner.optimizer.exp_avg.abs().sum()) == 0.0 and float(tuner.upper_optimizer.exp_avg.abs().sum()) == 0.0
+            assert float(mine.arena.grad.abs().sum()) == 0.0
+        losses = []
+        for b, ub in zip(batches, uppers):
+            out = tuner.train_step(b, ub)
+            row = [float(v.detach()) for v in out]                      # read before the upper graph could be replayed again
+            if tuner.last_upper is not None:
+                row.append(float(tuner.last_upper[0]))
+            losses.append(row)
+        runs.append((losses, mine.arena.master.detach().clone(), tuner.optimizer.step_count, tuner.upper_optimizer.step_count))
+    (l0, p0, n0, u0), (l1, p1, n1, u1) = runs
+    assert n0 == n1 == 4 and u0 == u1 == 2
+    assert [len(r) for r in l0] == [len(r) for r in l1] == [4, 5, 4, 5]
+    for a, b in zip(l0, l1):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 1e-2 * max(abs(x), 1e-6), (l0, l1)    # six Adam updates amplify fp32 atomics-order noise
+    init, _ = build_pair(av, trainable=True)
+    d0, d1 = (p0 - init.arena.master.detach()).flatten(), (p1 - init.arena.master.detach()).flatten()
+    assert F.cosine_similarity(d0, d1, dim=0).item() > 0.97

@@ -131,21 +131,30 @@ class FusedAdamW(torch.optim.Optimizer):
         self.grad_scale = 1.0
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, ranges=None):
+        """`ranges`: optional iterable of (start, end) arena slices to update one by one (the data-parallel path steps each
+        gradient bucket as soon as its all-reduce has landed); default = the whole arena in one launch."""
         g = self.param_groups[0]
         self.step_count += 1
-        K.adamw_step(self.arena.master, self.arena.grad, self.exp_avg, self.exp_avg_sq, self.arena.shadow, g["lr"],
-                     g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count, self.grad_scale,
-                     zero_grad=True)
+        a = self.arena
+        for lo, hi in (ranges if ranges is not None else [(0, a.numel)]):
+            if hi > lo:
+                K.adamw_step(a.master[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], a.shadow[lo:hi],
+                             g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count,
+                             self.grad_scale, zero_grad=True)
         self.arena.shadow_fresh = True
 
     @torch.no_grad()
-    def step_dyn(self, dyn):
+    def step_dyn(self, dyn, ranges=None):
         """Same update with {lr, bias corrections} read from the device tensor `dyn` (see `dyn_scalars`): the launch
         does not depend on the step number, so it can be part of a replayed CUDA graph."""
         g = self.param_groups[0]
-        K.adamw_step_dyn(self.arena.master, self.arena.grad, self.exp_avg, self.exp_avg_sq, self.arena.shadow, dyn,
-                         g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.grad_scale, zero_grad=True)
+        a = self.arena
+        for lo, hi in (ranges if ranges is not None else [(0, a.numel)]):
+            if hi > lo:
+                K.adamw_step_dyn(a.master[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], a.shadow[lo:hi],
+                                 dyn, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.grad_scale,
+                                 zero_grad=True)
         self.arena.shadow_fresh = True
 
     def dyn_scalars(self, step: int, lr=None):
@@ -255,7 +264,7 @@ class GradReducer:
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
             work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        self.pending.append(work)
+        self.pending.append((work, start, end))
 
     def reduce_all(self):
         """Everything not reduced yet since the last wait()."""
@@ -268,8 +277,27 @@ class GradReducer:
             self.reduce_range(pos, self.arena.numel)
 
     def wait(self):
-        for w in self.pending:
+        for w, _, _ in self.pending:
             w.wait()
+        self.pending.clear()
+        self.done.clear()
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+    def landed_ranges(self):
+        """Arena slices in the order their all-reduces were issued; before yielding a slice the current stream is made to
+        wait for that slice's collective only, so the caller's work on it (AdamW) overlaps the collectives still in flight.
+        Covers the whole arena; world_size == 1 yields it in one piece."""
+        if self.world == 1:
+            yield (0, self.arena.numel)
+            return
+        if self.stream is None:                              # CPU/gloo path reduced synchronously
+            for lo, hi in sorted(self.done):
+                yield (lo, hi)
+        else:
+            for w, lo, hi in self.pending:
+                w.wait()
+                yield (lo, hi)
         self.pending.clear()
         self.done.clear()
         if self.stream is not None:
@@ -325,8 +353,7 @@ class UnetFineTuner:
         loss, diff, kd, blk = self.step(batch)
         loss.backward()
         self.reducer.reduce_all()
-        self.reducer.wait()
-        self.optimizer.step()
+        self.optimizer.step(ranges=self.reducer.landed_ranges())      # per bucket, as its all-reduce lands
         self.lr_scheduler.step()
         self.optimizer.zero_grad()
         self.global_step += 1
@@ -337,9 +364,29 @@ class UnetFineTuner:
         loss, diff, kd, blk = self.step(self._static_in)
         loss.backward()                          # (world > 1: each block's backward forks its all-reduce onto the side stream)
         self.reducer.reduce_all()
-        self.reducer.wait()                      # joins the side stream back, also inside a capture
-        self.optimizer.step_dyn(self._dyn)
+        # AdamW per gradient bucket as its all-reduce lands; the generator joins the side stream back at the end (also
+        # inside a capture)
+        self.optimizer.step_dyn(self._dyn, ranges=self.reducer.landed_ranges())
         return loss.detach(), diff, kd, blk
+
+    def _capture(self, body, optimizers, pool=None):
+        """Warm `body` up twice on a side stream (lazily grown scratch, allocator pools; every `dyn` holds lr = 0 so the
+        parameters do not move), capture it once, restore the optimizer moments the warm-up touched."""
+        saved = [(o.exp_avg.clone(), o.exp_avg_sq.clone()) for o in optimizers]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, pool=pool):
+            out = body()
+        for o, (m0, v0) in zip(optimizers, saved):
+            o.exp_avg.copy_(m0)
+            o.exp_avg_sq.copy_(v0)
+        return graph, out
 
     def capture_cuda_graph(self, example_batch):
         """Capture step -> backward -> AdamW (~2300 kernel launches) into ONE CUDA graph; later `train_step` calls copy the
@@ -354,33 +401,24 @@ class UnetFineTuner:
         self._static_in = {k: v.to(dev, copy=True) for k, v in example_batch.items()}
         self._dyn = torch.zeros(3, device=dev, dtype=torch.float32)
         self._dyn.copy_(torch.tensor([0.0, 1.0, 1.0]))                  # lr = 0 while warming up / capturing
-        m0, v0 = self.optimizer.exp_avg.clone(), self.optimizer.exp_avg_sq.clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):                                          # lazily grown scratch, allocator pools, ...
-                self._graph_body()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self._static_out = self._graph_body()
-        self.optimizer.exp_avg.copy_(m0)
-        self.optimizer.exp_avg_sq.copy_(v0)
-        self._graph = graph
-        return graph
+        self._graph, self._static_out = self._capture(self._graph_body, [self.optimizer])
+        return self._graph
 
     def release_cuda_graph(self):
         """Back to the eager step; frees the graph and its private memory pool."""
         self._graph = None
         self._static_out = None
 
-    def _replay(self, batch):
-        for k, buf in self._static_in.items():
+    @staticmethod
+    def _load_static(static_in, batch):
+        for k, buf in static_in.items():
             src = batch[k]
             if src.shape != buf.shape:
                 raise ValueError(f"CUDA-graph step was captured for {k}{tuple(buf.shape)}, got {tuple(src.shape)}")
             buf.copy_(src, non_blocking=True)
+
+    def _replay(self, batch):
+        self._load_static(self._static_in, batch)
         self.optimizer.step_count += 1
         self._dyn.copy_(torch.tensor(self.optimizer.dyn_scalars(self.optimizer.step_count), dtype=torch.float32))
         self._graph.replay()
@@ -399,6 +437,8 @@ class BilevelUnetFineTuner(UnetFineTuner):
                                           eps=kw.get("eps", 1e-8), weight_decay=kw.get("weight_decay", 0.0))
         self.upper_lr_scheduler = ConstantWithWarmup(self.upper_optimizer, upper_warmup_steps)
         self.upper_step_freq = upper_step_freq
+        self._upper_graph = None
+        self.last_upper = None
 
     def upper_step(self, batch):
         """trainer.py:2904-3001 with the shipped weights (diffusion 0 / distillation 1 / block 0):
@@ -415,14 +455,54 @@ class BilevelUnetFineTuner(UnetFineTuner):
         loss, _, kd, _ = fused_kd_loss(pred, None, tgt, None, None, None, 0.0, 1.0, 0.0)
         return loss, kd
 
+    def _run_upper(self, upper_batch):
+        """trainer.py:2795-2816: upper loss -> backward -> (all-reduce) -> upper optimizer -> its scheduler."""
+        if self._upper_graph is not None:
+            self._load_static(self._upper_static_in, upper_batch)
+            self.upper_optimizer.step_count += 1
+            self._upper_dyn.copy_(torch.tensor(self.upper_optimizer.dyn_scalars(self.upper_optimizer.step_count),
+                                               dtype=torch.float32))
+            self._upper_graph.replay()
+            self.upper_lr_scheduler.step()
+            return self._upper_static_out
+        loss, kd = self.upper_step(upper_batch)
+        loss.backward()                                                       # :2808
+        self.reducer.reduce_all()
+        self.upper_optimizer.step(ranges=self.reducer.landed_ranges())        # :2814
+        self.upper_lr_scheduler.step()
+        self.upper_optimizer.zero_grad()
+        return loss.detach(), kd
+
     def train_step(self, batch, upper_batch=None):
         out = super().train_step(batch)
+        self.last_upper = None
         if upper_batch is not None and self.global_step % self.upper_step_freq == 0:   # trainer.py:2795
-            loss, _ = self.upper_step(upper_batch)
-            loss.backward()                                                       # :2808
-            self.reducer.reduce_all()
-            self.reducer.wait()
-            self.upper_optimizer.step()                                           # :2814
-            self.upper_lr_scheduler.step()
-            self.upper_optimizer.zero_grad()
+            self.last_upper = self._run_upper(upper_batch)
         return out
+
+    # ------------------------------------------------------------------------------------------------ CUDA graph
+    def _upper_graph_body(self):
+        loss, kd = self.upper_step(self._upper_static_in)
+        loss.backward()
+        self.reducer.reduce_all()
+        self.upper_optimizer.step_dyn(self._upper_dyn, ranges=self.reducer.landed_ranges())
+        return loss.detach(), kd
+
+    def capture_cuda_graph(self, example_batch, example_upper_batch=None):
+        """Lower step as in `UnetFineTuner.capture_cuda_graph`; with `example_upper_batch` the upper step (teacher x2,
+        student, ESD target, backward, all-reduce, second AdamW) becomes a second graph that shares the first one's memory
+        pool -- the two never run concurrently and each step's outputs are consumed before the next replay."""
+        g = super().capture_cuda_graph(example_batch)
+        if example_upper_batch is not None:
+            dev = self.device
+            self._upper_static_in = {k: v.to(dev, copy=True) for k, v in example_upper_batch.items()}
+            self._upper_dyn = torch.zeros(3, device=dev, dtype=torch.float32)
+            self._upper_dyn.copy_(torch.tensor([0.0, 1.0, 1.0]))
+            self._upper_graph, self._upper_static_out = self._capture(self._upper_graph_body, [self.upper_optimizer],
+                                                                      pool=g.pool())
+        return g
+
+    def release_cuda_graph(self):
+        self._upper_graph = None
+        self._upper_static_out = None
+        super().release_cuda_graph()
