@@ -280,8 +280,7 @@ __global__ void resample2x_kernel(const bf16* __restrict__ src, int64_t lds, bf1
       if (nv == 8) {
         bf16x8 v;
         if (zero) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) v.v[j] = __floats2bfloat162_rn(0.f, 0.f);
+          v = zero8();
         } else {
           v = *reinterpret_cast<const bf16x8*>(sp);
         }

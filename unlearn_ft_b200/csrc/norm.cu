@@ -52,34 +52,45 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
       }
     }
     const int64_t row0 = (int64_t)b * hw;
-#pragma unroll 4
-    for (int p = p0 + threadIdx.y; p < p1; p += RL) {
-      float xf[8];
-      const bf16* xp = x + (row0 + p) * ldx + c0;
-      if (nv == 8) {
-        unpack8(*reinterpret_cast<const bf16x8*>(xp), xf);
-      } else {
+    // U rows per trip, every load issued before the first use (one row per trip left a single 16-byte load in flight per
+    // thread).  Whole vectors are always loadable (pitches are multiples of 8 elements); lanes >= nv are masked to zero.
+    constexpr int U = (MODE == GN_FWD_STATS) ? 8 : 4;
+    for (int p = p0 + threadIdx.y; p < p1; p += RL * U) {
+      bf16x8 xv[U], dv[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xf[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
-      }
-      if (MODE == GN_FWD_STATS) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a0[j] += xf[j], a1[j] += xf[j] * xf[j];
-      } else {
-        float df[8];
-        const bf16* dp = dy + (row0 + p) * lddy + c0;
-        if (nv == 8) {
-          unpack8(*reinterpret_cast<const bf16x8*>(dp), df);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) df[j] = j < nv ? __bfloat162float(dp[j]) : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * RL;
+        if (pp < p1) {
+          xv[u] = *reinterpret_cast<const bf16x8*>(x + (row0 + pp) * ldx + c0);
+          if (MODE == GN_BWD_STATS) dv[u] = *reinterpret_cast<const bf16x8*>(dy + (row0 + pp) * lddy + c0);
         }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float dz = df[j];
-          if (silu) dz *= silu_grad_f(fmaf(xf[j], sc[j], sh[j]));
-          a0[j] += dz;
-          a1[j] += dz * fmaf(xf[j], rr[j], -mr[j]);
+      for (int u = 0; u < U; ++u) {
+        if (p + u * RL >= p1) break;
+        float xf[8];
+        unpack8(xv[u], xf);
+        if (nv < 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xf[j] = j < nv ? xf[j] : 0.f;
+        }
+        if (MODE == GN_FWD_STATS) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a0[j] += xf[j], a1[j] = fmaf(xf[j], xf[j], a1[j]);
+        } else {
+          float df[8];
+          unpack8(dv[u], df);
+          if (nv < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) df[j] = j < nv ? df[j] : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float dz = df[j];
+            if (silu) dz *= silu_grad_f(fmaf(xf[j], sc[j], sh[j]));
+            a0[j] += dz;
+            a1[j] = fmaf(dz, fmaf(xf[j], rr[j], -mr[j]), a1[j]);
+          }
         }
       }
     }
@@ -140,26 +151,30 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const f
   const int s = blockIdx.z;
   const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
   const int64_t row0 = (int64_t)b * hw;
-#pragma unroll 4
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const bf16* xp = x + (row0 + p) * ldx + c0;
-    bf16* yp = y + (row0 + p) * ldy + c0;
-    float f[8];
-    if (nv == 8) {
-      unpack8(*reinterpret_cast<const bf16x8*>(xp), f);
-    } else {
+  constexpr int U = 4;   // rows per trip: all loads first, then the arithmetic and the stores
+  const int RL = blockDim.y;
+  for (int p = p0 + threadIdx.y; p < p1; p += RL * U) {
+    bf16x8 xv[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
-    }
+    for (int u = 0; u < U; ++u)
+      if (p + u * RL < p1) xv[u] = *reinterpret_cast<const bf16x8*>(x + (row0 + p + u * RL) * ldx + c0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v = fmaf(f[j], sc[j], sh[j]);
-      f[j] = silu ? silu_f(v) : v;
-    }
-    if (nv == 8) {
-      *reinterpret_cast<bf16x8*>(yp) = pack8(f);
-    } else {
-      for (int j = 0; j < nv; ++j) yp[j] = __float2bfloat16(f[j]);
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * RL;
+      if (pp >= p1) break;
+      float f[8];
+      unpack8(xv[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fmaf(f[j], sc[j], sh[j]);
+        f[j] = silu ? silu_f(v) : v;
+      }
+      bf16* yp = y + (row0 + pp) * ldy + c0;
+      if (nv == 8) {
+        *reinterpret_cast<bf16x8*>(yp) = pack8(f);
+      } else {   // tail vector of a width that is not a multiple of 8: never write past column C
+        for (int j = 0; j < nv; ++j) yp[j] = __float2bfloat16(f[j]);
+      }
     }
   }
 }
@@ -212,44 +227,44 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
   const int s = blockIdx.z;
   const int p0 = (int)((int64_t)hw * s / slices), p1 = (int)((int64_t)hw * (s + 1) / slices);
   const int64_t row0 = (int64_t)b * hw;
-#pragma unroll 2
-  for (int p = p0 + threadIdx.y; p < p1; p += blockDim.y) {
-    const int64_t row = row0 + p;
-    float xf[8], df[8], o[8];
-    const bf16* xp = x + row * ldx + c0;
-    const bf16* dp = dy + row * lddy + c0;
-    if (nv == 8) {
-      unpack8(*reinterpret_cast<const bf16x8*>(xp), xf);
-      unpack8(*reinterpret_cast<const bf16x8*>(dp), df);
-    } else {
+  constexpr int U = 4;   // rows per trip: all loads (x, dy, residual) first
+  const int RL = blockDim.y;
+  for (int p = p0 + threadIdx.y; p < p1; p += RL * U) {
+    bf16x8 xv[U], dv[U], rv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + p + u * RL;
+      if (p + u * RL < p1) {
+        xv[u] = *reinterpret_cast<const bf16x8*>(x + row * ldx + c0);
+        dv[u] = *reinterpret_cast<const bf16x8*>(dy + row * lddy + c0);
+        if (res) rv[u] = *reinterpret_cast<const bf16x8*>(res + row * ldr + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * RL >= p1) break;
+      const int64_t row = row0 + p + u * RL;
+      float xf[8], df[8], o[8];
+      unpack8(xv[u], xf);
+      unpack8(dv[u], df);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xf[j] = j < nv ? __bfloat162float(xp[j]) : 0.f;
-        df[j] = j < nv ? __bfloat162float(dp[j]) : 0.f;
+        float dz = df[j];
+        if (silu) dz *= silu_grad_f(fmaf(xf[j], sc[j], sh[j]));
+        o[j] = fmaf(sc[j], dz, fmaf(xf[j], P[j], Q[j]));
       }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float dz = df[j];
-      if (silu) dz *= silu_grad_f(fmaf(xf[j], sc[j], sh[j]));
-      o[j] = fmaf(sc[j], dz, fmaf(xf[j], P[j], Q[j]));
-    }
-    if (res) {  // fused gradient merge: dx += residual (e.g. the skip/shortcut branch's gradient)
-      const bf16* rp = res + row * ldr + c0;
-      if (nv == 8) {
+      if (res) {  // fused gradient merge: dx += residual (e.g. the skip/shortcut branch's gradient)
         float rf[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(rp), rf);
+        unpack8(rv[u], rf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += rf[j];
-      } else {
-        for (int j = 0; j < nv; ++j) o[j] += __bfloat162float(rp[j]);
       }
-    }
-    bf16* op = dx + row * lddx + c0;
-    if (nv == 8) {
-      *reinterpret_cast<bf16x8*>(op) = pack8(o);
-    } else {
-      for (int j = 0; j < nv; ++j) op[j] = __float2bfloat16(o[j]);
+      bf16* op = dx + row * lddx + c0;
+      if (nv == 8) {
+        *reinterpret_cast<bf16x8*>(op) = pack8(o);
+      } else {
+        for (int j = 0; j < nv; ++j) op[j] = __float2bfloat16(o[j]);
+      }
     }
   }
 }
