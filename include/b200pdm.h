@@ -40,6 +40,10 @@ int b200pdm_version(void);
 const char* b200pdm_last_error(void);
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
 uint64_t b200pdm_launch_count(void);
+/* Library-owned scratch (split-K partial sums) exists once per lane, 0 <= lane < 4.  A host thread that enqueues work
+ * on a second stream which may run concurrently with lane 0's (the trainer does this for the frozen teacher's forward,
+ * pdm/training/trainer.py) selects another lane for those calls and switches back afterwards.  Default lane 0. */
+int b200pdm_set_lane(int lane);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tensor-core core: one persistent, warp-specialised tcgen05 kernel (TMA -> smem ring -> tcgen05.mma -> TMEM ->

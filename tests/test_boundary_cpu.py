@@ -76,3 +76,37 @@ def test_hard_concrete_and_snr_match_reference(gold):
 
     assert torch.equal(hard_concrete(gold["hard_concrete_in"]), gold["hard_concrete_out"])
     assert torch.equal(compute_snr(S, gold["snr_timesteps"]), gold["snr"])
+
+
+def test_checkpoint_wire_format_roundtrip(gold, tmp_path):
+    """`save_pretrained` writes the reference's checkpoint layout (trainer.py:314-327,2366-2368) -- `<root>/unet/
+    config.json` + `diffusion_pytorch_model.safetensors` under the diffusers key names with the pruned shapes, `<root>/
+    arch_vector.pt` -- and `from_pretrained(root, subfolder="unet", checkpoint_loading=True)` (reference :2185-2495) restores it
+    bit for bit."""
+    import json
+    import os
+
+    from safetensors.torch import load_file
+
+    from oracle.make_golden import SMALL64
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModelPruned
+    g = gold["small64_r055"]
+    cfg = dict(block_out_channels=SMALL64["block_out_channels"], attention_head_dim=SMALL64["heads"],
+               cross_attention_dim=SMALL64["cross_attention_dim"])
+    m = UNet2DConditionModelPruned(cfg, arch_vector=g["arch_vector"], device="cpu", seed=5)
+    root = str(tmp_path / "checkpoint-10")
+    m.save_pretrained(os.path.join(root, "unet"))
+    assert sorted(os.listdir(root)) == ["arch_vector.pt", "unet"]
+    assert sorted(os.listdir(os.path.join(root, "unet"))) == ["config.json", "diffusion_pytorch_model.safetensors"]
+    sd = load_file(os.path.join(root, "unet", "diffusion_pytorch_model.safetensors"))
+    assert {k: list(v.shape) for k, v in sd.items()} == g["shapes"]                 # the reference's keys and pruned shapes
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    cj = json.load(open(os.path.join(root, "unet", "config.json")))
+    assert cj["_class_name"] == "UNet2DConditionModelPruned" and cj["block_out_channels"] == list(SMALL64["block_out_channels"])
+    assert torch.equal(torch.load(os.path.join(root, "arch_vector.pt")), g["arch_vector"].float())
+    back = UNet2DConditionModelPruned.from_pretrained(root, subfolder="unet", checkpoint_loading=True, device="cpu", seed=None)
+    assert torch.equal(back.arch_vector, m.arch_vector)
+    a, b = m.state_dict(), back.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k

@@ -312,3 +312,30 @@ def test_bilevel_cuda_graphs_match_eager(gold):
     init, _ = build_pair(av, trainable=True)
     d0, d1 = (p0 - init.arena.master.detach()).flatten(), (p1 - init.arena.master.detach()).flatten()
     assert F.cosine_similarity(d0, d1, dim=0).item() > 0.97
+
+
+def test_trainer_checkpoint_resume(gold, tmp_path):
+    """save_checkpoint / load_checkpoint (reference hooks trainer.py:311-346): a tuner restored from the files continues
+    exactly where the saved one was (weights, AdamW moments and step, LR schedule)."""
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel, UNet2DConditionModelPruned
+    from unlearn_ft_b200.pdm.training import UnetFineTuner
+    av = gold["small64_r055"]["arch_vector"]
+    batches = [make_batch(seed=s) for s in range(3)]
+    mine, _ = build_pair(av, trainable=True)
+    teacher = UNet2DConditionModel(small_cfg(), seed=7)
+    tuner = UnetFineTuner(mine, teacher, lr=1e-4, warmup_steps=4)
+    tuner.train_step(batches[0]), tuner.train_step(batches[1])
+    root = str(tmp_path / "checkpoint-2")
+    tuner.save_checkpoint(root)
+    ref = [float(v) for v in tuner.train_step(batches[2])]
+    p_ref = mine.arena.master.detach().clone()
+    back = UNet2DConditionModelPruned.from_pretrained(root, subfolder="unet", checkpoint_loading=True)
+    assert torch.equal(back.arch_vector, mine.arch_vector)
+    tuner2 = UnetFineTuner(back, teacher, lr=1e-4, warmup_steps=4)
+    tuner2.load_checkpoint(root)
+    assert tuner2.global_step == 2 and tuner2.optimizer.step_count == 2
+    assert tuner2.optimizer.param_groups[0]["lr"] == pytest.approx(1e-4 * 2 / 4)
+    got = [float(v) for v in tuner2.train_step(batches[2])]
+    for x, y in zip(ref, got):
+        assert abs(x - y) <= 2e-3 * max(abs(x), 1e-6), (ref, got)      # fp32 atomics order only
+    assert rel(back.arena.master.detach(), p_ref) < 1e-4

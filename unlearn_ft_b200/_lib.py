@@ -48,6 +48,7 @@ _SIGS = {
     "b200pdm_version": [],
     "b200pdm_last_error": [],
     "b200pdm_launch_count": [],
+    "b200pdm_set_lane": [i32],
     "b200pdm_gemm_trace_dump": [C.c_char_p],
     "b200pdm_gemm": [C.POINTER(GemmDesc), c_p],
     "b200pdm_linear_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i32, i64, i64, i64, c_p],
@@ -136,3 +137,17 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().b200pdm_launch_count())
+
+
+class lane:
+    """`with lane(1): ...` -- library scratch lane for calls enqueued on a stream that may run next to lane 0's work."""
+
+    def __init__(self, index: int):
+        self.index = index
+
+    def __enter__(self):
+        check(lib().b200pdm_set_lane(self.index))
+
+    def __exit__(self, *exc):
+        lib().b200pdm_set_lane(0)
+        return False

@@ -945,24 +945,31 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
 }
 
 // Library-owned fp32 scratch for split-K partial sums (lazily grown; the only device allocation the library makes).
+// One buffer per "lane" (b200pdm_set_lane): the trainer enqueues the frozen teacher's forward on a second stream next to the
+// student's, and two split-K GEMMs in flight at once must not share partial sums.  Lanes are a host-side notion (the
+// enqueueing thread switches lane together with the stream), so the same buffers are used eagerly and under stream
+// capture -- nothing is allocated while a graph is being captured, the eager warm-up steps have sized every lane.
+constexpr int kMaxLanes = 4;
+static int g_lane = 0;
 static float* scratch_f32(size_t elems, cudaStream_t stream) {
-  static float* buf = nullptr;
-  static size_t cap = 0;
-  if (elems > cap) {
-    if (buf) {
+  static float* buf[kMaxLanes] = {};
+  static size_t cap[kMaxLanes] = {};
+  const int l = g_lane;
+  if (elems > cap[l]) {
+    if (buf[l]) {
       cudaStreamSynchronize(stream);
-      cudaFree(buf);
+      cudaFree(buf[l]);
     }
     size_t want = elems < (8u << 20) ? (8u << 20) : elems;
-    if (cudaMalloc(&buf, want * sizeof(float)) != cudaSuccess) {
-      buf = nullptr, cap = 0;
+    if (cudaMalloc(&buf[l], want * sizeof(float)) != cudaSuccess) {
+      buf[l] = nullptr, cap[l] = 0;
       set_err("split-K scratch allocation failed");
       return nullptr;
     }
-    cap = want;
+    cap[l] = want;
   }
-  if (cudaMemsetAsync(buf, 0, elems * sizeof(float), stream) != cudaSuccess) return nullptr;
-  return buf;
+  if (cudaMemsetAsync(buf[l], 0, elems * sizeof(float), stream) != cudaSuccess) return nullptr;
+  return buf[l];
 }
 
 __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldws, void* __restrict__ out, int out_fp32,
@@ -1293,6 +1300,11 @@ extern "C" {
 int b200pdm_version(void) { return 100; }
 const char* b200pdm_last_error(void) { return get_err(); }
 uint64_t b200pdm_launch_count(void) { return g_launches.load(); }
+int b200pdm_set_lane(int lane) {
+  if (lane < 0 || lane >= kMaxLanes) return B200PDM_ERR_ARG;
+  g_lane = lane;
+  return B200PDM_OK;
+}
 
 int b200pdm_gemm_trace_dump(const char* path) {
   FILE* f = fopen(path, "w");

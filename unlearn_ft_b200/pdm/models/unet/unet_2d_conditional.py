@@ -276,6 +276,27 @@ class UNet2DConditionModelGated(nn.Module):
                 model.load_unpruned_state_dict(sd)
         return model
 
+    def save_pretrained(self, save_directory, safe_serialization: bool = True, save_arch_vector: bool = True, **_):
+        """diffusers `ModelMixin.save_pretrained` layout, as the reference's checkpoint hook uses it (trainer.py:314-327):
+        `<dir>/config.json` + `<dir>/diffusion_pytorch_model.safetensors` with the diffusers key names and the PRUNED shapes
+        (fp32 master weights).  The arch vector that explains those shapes goes to `<parent>/arch_vector.pt`, where the
+        reference keeps it next to the `unet` folder (trainer.py:2163,2366-2368; read back at :2429-2441), so
+        `from_pretrained(parent, subfolder=basename, checkpoint_loading=True)` restores the model from these files."""
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in self._config.items()}
+        cfg.update({"_class_name": type(self).__name__, "_diffusers_version": "0.30.3"})
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+        sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in self.state_dict().items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file(sd, os.path.join(save_directory, "diffusion_pytorch_model.safetensors"), metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "diffusion_pytorch_model.bin"))
+        if save_arch_vector:
+            parent = os.path.dirname(os.path.abspath(save_directory))
+            torch.save(self.arch_vector.clone(), os.path.join(parent, "arch_vector.pt"))
+
     # ------------------------------------------------------------------------------------------------ weights
     def load_state_dict(self, state_dict, strict=True, assign=False):
         out = super().load_state_dict(state_dict, strict=strict, assign=False)

@@ -16,11 +16,13 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import contextlib
 import os
 
 import torch
 import torch.distributed as dist
 
+from ... import _lib
 from ... import kernels as K
 from ..models.unet.unet_2d_conditional import UNet2DConditionModel, UNet2DConditionModelPruned
 from ..utils.metric_utils import compute_snr
@@ -320,6 +322,9 @@ class UnetFineTuner:
         if teacher is not None:
             cast_block_act_hooks(teacher, self.block_act_teacher)
         self.reducer = GradReducer(student)
+        # second stream for the teacher's forward (env B200PDM_SERIAL_TEACHER=1: A/B measurement of the serial order)
+        self.teacher_stream = (torch.cuda.Stream() if (teacher is not None and torch.cuda.is_available()
+                                                       and not os.environ.get("B200PDM_SERIAL_TEACHER")) else None)
         self.global_step = 0
         self._graph = None                                                        # see capture_cuda_graph()
 
@@ -338,10 +343,22 @@ class UnetFineTuner:
         ehs = batch["prompt_embeds"]
         noisy, target = self.noise_scheduler.add_noise_and_velocity(latents, noise, timesteps)
         teacher_pred = None
-        if self.w_block > 0 or self.w_kd > 0:
+        need_teacher = self.w_block > 0 or self.w_kd > 0
+        ts = self.teacher_stream if need_teacher else None
+        if ts is not None:
+            # The frozen teacher's forward does not depend on the student's: it runs on a second stream (a parallel branch
+            # of the captured graph), so its kernels fill the SMs that the many small launches of the 8x8 / 16x16 levels
+            # leave idle.  Joined before the loss, which is the first consumer of the teacher's prediction and features.
+            cur = torch.cuda.current_stream()
+            ts.wait_stream(cur)
+            with torch.cuda.stream(ts), _lib.lane(1), torch.no_grad():
+                teacher_pred = self.teacher(noisy, timesteps, ehs).sample
+        elif need_teacher:
             with torch.no_grad():
                 teacher_pred = self.teacher(noisy, timesteps, ehs).sample
         model_pred = self.student(noisy, timesteps, ehs).sample
+        if ts is not None:
+            torch.cuda.current_stream().wait_stream(ts)
         w = self.snr_weights(timesteps) if self.snr_gamma is not None else None
         return fused_kd_loss(model_pred, target, teacher_pred if self.w_kd > 0 else None, w, self.block_act_student,
                              self.block_act_teacher, self.w_diff, self.w_kd, self.w_block)
@@ -358,6 +375,25 @@ class UnetFineTuner:
         self.optimizer.zero_grad()
         self.global_step += 1
         return loss.detach(), diff, kd, blk
+
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, output_dir, subfolder="unet"):
+        """`Trainer.save_checkpoint` -> accelerate `save_state` with the reference's hooks (trainer.py:311-327,2366-2368):
+        `<dir>/<subfolder>/{config.json, diffusion_pytorch_model.safetensors}`, `<dir>/arch_vector.pt`, optimizer + scheduler
+        state (`optimizer.bin` / `scheduler.bin`, the accelerate file names)."""
+        self.student.save_pretrained(os.path.join(output_dir, subfolder))
+        torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.optimizer.state_dict().items()},
+                   os.path.join(output_dir, "optimizer.bin"))
+        torch.save({"t": self.lr_scheduler.t, "global_step": self.global_step}, os.path.join(output_dir, "scheduler.bin"))
+
+    def load_checkpoint(self, input_dir, subfolder="unet"):
+        """Counterpart of the reference's load hook (trainer.py:329-346): pruned weights by key, then optimizer / scheduler."""
+        from safetensors.torch import load_file
+        self.student.load_state_dict(load_file(os.path.join(input_dir, subfolder, "diffusion_pytorch_model.safetensors")))
+        self.optimizer.load_state_dict(torch.load(os.path.join(input_dir, "optimizer.bin"), map_location=self.device))
+        st = torch.load(os.path.join(input_dir, "scheduler.bin"))
+        self.lr_scheduler.t, self.global_step = int(st["t"]), int(st["global_step"])
+        self.lr_scheduler._apply()
 
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def _graph_body(self):
@@ -446,10 +482,16 @@ class BilevelUnetFineTuner(UnetFineTuner):
         latents, noise, timesteps = batch["latents"], batch["noise"], batch["timesteps"]
         ehs, empty = batch["prompt_embeds"], batch["empty_prompt_embeds"]
         noisy, _ = self.noise_scheduler.add_noise_and_velocity(latents, noise, timesteps)
-        with torch.no_grad():
+        ts = self.teacher_stream
+        if ts is not None:                                                        # teacher x2 next to the student (see step())
+            ts.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(ts) if ts is not None else contextlib.nullcontext()), \
+                (_lib.lane(1) if ts is not None else contextlib.nullcontext()), torch.no_grad():
             cond = self.teacher(noisy, timesteps, ehs).sample                     # :2951
             uncond = self.teacher(noisy, timesteps, empty).sample                 # :2953
         pred = self.student(noisy, timesteps, ehs).sample                         # :2957
+        if ts is not None:
+            torch.cuda.current_stream().wait_stream(ts)
         tgt, _ = K.diffusion_prep(uncond, cond, torch.zeros_like(timesteps),
                                   torch.full((1,), 2.0, device=pred.device), torch.full((1,), -1.0, device=pred.device))
         loss, _, kd, _ = fused_kd_loss(pred, None, tgt, None, None, None, 0.0, 1.0, 0.0)
