@@ -46,6 +46,7 @@ class _BlockFn(torch.autograd.Function):
         if ctx.bwd is None:
             raise RuntimeError("backward through a block that ran without gradient bookkeeping")
         in_grads = ctx.bwd(*grads)
+        bnn.wgrad_join()  # the block's weight gradients ran on the side stream (nn.wgrad_branch): final from here on
         ctx.bwd = None  # release saved activations
         # this block's parameter gradients are final now: let the data-parallel reducer start on them while the rest of
         # the backward pass runs (GradReducer installs the callbacks; None on a single GPU)

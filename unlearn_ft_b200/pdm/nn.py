@@ -14,11 +14,14 @@ Design
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import List, Optional, Tuple
 
 import torch
 from torch import nn
 
+from .. import _lib
 from .. import kernels as K
 
 BF16, F32 = torch.bfloat16, torch.float32
@@ -240,6 +243,44 @@ def ln(x, m: PLayerNorm, need_bwd):
     return y, bwd
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# Weight-gradient branch.  A layer's wgrad (and bias column sum) only feeds the gradient arena, nothing downstream in the
+# backward pass waits for it, so it is enqueued on a second stream: in the captured graph it becomes a parallel branch whose
+# kernels fill the SMs the dgrad chain leaves idle (small 8x8 / 16x16 levels, tails of persistent kernels).  The branch is
+# joined at the end of every top-level block's backward (blocks._BlockFn.backward), before the block's all-reduce is fired;
+# the operands are kept alive until then so the allocator cannot recycle them under the side stream.
+# ----------------------------------------------------------------------------------------------------------------
+class _WgradBranch:
+    enabled = not os.environ.get("B200PDM_SERIAL_WGRAD")     # (env: A/B measurement of the serial order)
+    stream = None
+    keep: list = []
+    open_ = False
+
+
+@contextlib.contextmanager
+def wgrad_branch(*operands):
+    wb = _WgradBranch
+    if not wb.enabled or not operands[0].is_cuda:
+        yield
+        return
+    if wb.stream is None:
+        wb.stream = torch.cuda.Stream()
+    wb.stream.wait_stream(torch.cuda.current_stream())
+    wb.keep.extend(operands)
+    wb.open_ = True
+    with torch.cuda.stream(wb.stream), _lib.lane(2):
+        yield
+
+
+def wgrad_join():
+    """Current stream waits for every wgrad enqueued so far; their operands may be released afterwards."""
+    wb = _WgradBranch
+    if wb.open_:
+        torch.cuda.current_stream().wait_stream(wb.stream)
+        wb.keep.clear()
+        wb.open_ = False
+
+
 def linear(x, m: PLinear, need_bwd, residual=None, out_fp32=False, w16=None, gw=None, bias="own"):
     """y = x @ W^T + b (+ residual).  `w16`/`gw` override lets several adjacent parameters act as one fused matrix
     (e.g. to_q|to_k|to_v stacked in the arena)."""
@@ -251,9 +292,10 @@ def linear(x, m: PLinear, need_bwd, residual=None, out_fp32=False, w16=None, gw=
     g = (m.gw if gw is None else gw)
 
     def bwd(dy, residual=None, need_dx=True):
-        K.linear_wgrad(dy, x, g)
-        if b is not None:
-            K.colsum(dy, b.grad)
+        with wgrad_branch(dy, x):
+            K.linear_wgrad(dy, x, g)
+            if b is not None:
+                K.colsum(dy, b.grad)
         return K.linear_dgrad(dy, w, residual=residual) if need_dx else None
 
     return y, bwd
@@ -269,8 +311,9 @@ def conv(x, m: PConv2d, B, H, W, need_bwd, rowbias=None, residual=None):
     Ho, Wo = H // st, W // st
 
     def bwd(dy, residual=None, want_rowbias=False, need_dx=True):
-        K.conv_wgrad(dy, x, m.gw, B, H, W, m.ksize, st)
-        K.colsum(dy, m.bias.grad)
+        with wgrad_branch(dy, x):
+            K.conv_wgrad(dy, x, m.gw, B, H, W, m.ksize, st)
+            K.colsum(dy, m.bias.grad)
         drb = None
         if want_rowbias:
             drb = K.alloc2d(B, m.out_channels, dy.device, F32, zero=True)
