@@ -140,14 +140,20 @@ def launch_count() -> int:
 
 
 class lane:
-    """`with lane(1): ...` -- library scratch lane for calls enqueued on a stream that may run next to lane 0's work."""
+    """`with lane(1): ...` -- library scratch lane for calls enqueued on a stream that may run next to another lane's work.
+    Nests: the previous lane is restored on exit."""
+
+    current = 0
 
     def __init__(self, index: int):
         self.index = index
 
     def __enter__(self):
+        self.prev = lane.current
         check(lib().b200pdm_set_lane(self.index))
+        lane.current = self.index
 
     def __exit__(self, *exc):
-        lib().b200pdm_set_lane(0)
+        lib().b200pdm_set_lane(self.prev)
+        lane.current = self.prev
         return False

@@ -146,8 +146,10 @@ class ResnetBlock2DWidthGated(nn.Module):
 
             return y, bwd_drop
         hw = H * W
+        with bnn.side_branch(temb_act):   # 16-row GEMM on a handful of CTAs: next to GroupNorm instead of in front of conv1
+            t, b_t = bnn.linear(temb_act, self.time_emb_proj, need_bwd, out_fp32=True)  # blocks.py:334-337
         h1, b_n1 = bnn.gn(x, self.norm1, B, hw, True, need_bwd)                       # blocks.py:318-319
-        t, b_t = bnn.linear(temb_act, self.time_emb_proj, need_bwd, out_fp32=True)      # blocks.py:334-337
+        bnn.side_join()
         h2, b_c1 = bnn.conv(h1, self.conv1, B, H, W, need_bwd, rowbias=t)               # blocks.py:332,339-341
         h3, b_n2 = bnn.gn(h2, self.norm2, B, hw, True, need_bwd)                       # blocks.py:348,371
         if self.conv_shortcut is not None:
@@ -162,7 +164,8 @@ class ResnetBlock2DWidthGated(nn.Module):
             dh3, _ = b_c2(dy)
             dh2 = b_n2(dh3)
             dh1, dt = b_c1(dh2, want_rowbias=True)
-            dtemb = b_t(K.cast2d_f32_to_bf16(dt))
+            with bnn.side_branch(dt):     # time-embedding gradient chain: off the dgrad chain, joined at the block's end
+                dtemb = b_t(K.cast2d_f32_to_bf16(dt))
             if b_sc is not None:
                 dsc, _ = b_sc(dy)
             else:
@@ -552,5 +555,9 @@ def _merge(a, b):
 
 
 def _merge_small(a, b):
-    """Accumulate the (tiny) [B, 1280] time-embedding gradients of the resnets inside one block."""
-    return _merge(a, b)
+    """Accumulate the (tiny) [B, 1280] time-embedding gradients of the resnets inside one block -- on the side stream, where
+    the resnets' backward produces them (ResnetBlock2DWidthGated.run); the block's backward joins it before returning."""
+    if a is None or b is None:
+        return _merge(a, b)
+    with bnn.side_branch(a, b):
+        return K.add(a, b)

@@ -250,35 +250,48 @@ def ln(x, m: PLayerNorm, need_bwd):
 # joined at the end of every top-level block's backward (blocks._BlockFn.backward), before the block's all-reduce is fired;
 # the operands are kept alive until then so the allocator cannot recycle them under the side stream.
 # ----------------------------------------------------------------------------------------------------------------
-class _WgradBranch:
+class _Side:
     enabled = not os.environ.get("B200PDM_SERIAL_WGRAD")     # (env: A/B measurement of the serial order)
-    stream = None
-    keep: list = []
-    open_ = False
+    streams: dict = {}      # main stream -> its side stream (the teacher's stream and the student's each get their own)
+    keep: dict = {}         # main stream -> operands kept alive until the join
+    open_: set = set()
+    inside = False
 
 
 @contextlib.contextmanager
-def wgrad_branch(*operands):
-    wb = _WgradBranch
-    if not wb.enabled or not operands[0].is_cuda:
-        yield
+def side_branch(*operands):
+    """Enqueue the body on the current stream's side stream (after everything enqueued on the current stream so far)."""
+    if not _Side.enabled or _Side.inside or not torch.cuda.is_available() or (operands and not operands[0].is_cuda):
+        yield               # (nested use runs inline on the side stream it is already on)
         return
-    if wb.stream is None:
-        wb.stream = torch.cuda.Stream()
-    wb.stream.wait_stream(torch.cuda.current_stream())
-    wb.keep.extend(operands)
-    wb.open_ = True
-    with torch.cuda.stream(wb.stream), _lib.lane(2):
-        yield
+    main = torch.cuda.current_stream()
+    side = _Side.streams.get(main)
+    if side is None:
+        side = _Side.streams[main] = torch.cuda.Stream()
+    side.wait_stream(main)
+    _Side.keep.setdefault(main, []).extend(operands)
+    _Side.open_.add(main)
+    _Side.inside = True
+    try:
+        with torch.cuda.stream(side), _lib.lane(_lib.lane.current + 2):
+            yield
+    finally:
+        _Side.inside = False
+
+
+wgrad_branch = side_branch
 
 
 def wgrad_join():
-    """Current stream waits for every wgrad enqueued so far; their operands may be released afterwards."""
-    wb = _WgradBranch
-    if wb.open_:
-        torch.cuda.current_stream().wait_stream(wb.stream)
-        wb.keep.clear()
-        wb.open_ = False
+    """Current stream waits for everything enqueued on its side stream; kept operands may be released afterwards."""
+    main = torch.cuda.current_stream()
+    if main in _Side.open_:
+        main.wait_stream(_Side.streams[main])
+        _Side.keep[main].clear()
+        _Side.open_.discard(main)
+
+
+side_join = wgrad_join
 
 
 def linear(x, m: PLinear, need_bwd, residual=None, out_fp32=False, w16=None, gw=None, bias="own"):
