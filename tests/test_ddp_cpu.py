@@ -30,7 +30,11 @@ def _worker(rank, world, port, out):
     red.reduce_range(600, 1000)       # bucketed, as issued per U-Net block from its backward (last block first)
     red.reduce_range(100, 300)
     red.reduce_all()                  # the complement: [0,100) and [300,600), each exactly once
-    red.wait()
+    # the optimizer walks the buckets as their collectives land (FusedAdamW.step(ranges=...)): the slices it is handed
+    # partition the arena exactly once, and the walk leaves the reducer ready for the next step
+    spans = sorted(red.landed_ranges())
+    assert spans[0][0] == 0 and spans[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(spans, spans[1:])), spans
+    assert not red.pending and not red.done
     out[rank] = model.arena.grad.clone()
     dist.destroy_process_group()
 
