@@ -238,6 +238,8 @@ def sampling_bench(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own prints ("NCCL version ...", NCCL_DEBUG output) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from unlearn_ft_b200 import _lib
     from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModelPruned
@@ -347,6 +349,7 @@ def main():
     import torch.distributed as dist
 
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from unlearn_ft_b200 import _lib
     from unlearn_ft_b200 import kernels as K

@@ -339,3 +339,35 @@ def test_trainer_checkpoint_resume(gold, tmp_path):
     for x, y in zip(ref, got):
         assert abs(x - y) <= 2e-3 * max(abs(x), 1e-6), (ref, got)      # fp32 atomics order only
     assert rel(back.arena.master.detach(), p_ref) < 1e-4
+
+
+def test_optimizer_inside_backward_matches_serial_order(gold, monkeypatch):
+    """AdamW applied per top-level block from inside the backward pass (UnetFineTuner._backward_and_update) is the reference's
+    optimizer.step() after backward (trainer.py:2320-2329): same losses, same AdamW state, same parameters; the gradient arena
+    is zero afterwards and both step counters advance once per step."""
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel
+    from unlearn_ft_b200.pdm.training import UnetFineTuner
+    av = gold["small64_r055"]["arch_vector"]
+    batches = [make_batch(seed=s) for s in range(3)]
+    runs = []
+    for serial in (True, False):
+        if serial:
+            monkeypatch.setenv("B200PDM_OPT_AFTER_BACKWARD", "1")
+        else:
+            monkeypatch.delenv("B200PDM_OPT_AFTER_BACKWARD", raising=False)
+        mine, _ = build_pair(av, trainable=True)
+        teacher = UNet2DConditionModel(small_cfg(), seed=7)
+        tuner = UnetFineTuner(mine, teacher, lr=1e-4, warmup_steps=0)
+        assert len(tuner.reducer.buckets) == 4 + 1 + 4 + 2
+        losses = [[float(v.detach()) for v in tuner.train_step(b)] for b in batches]
+        assert tuner.optimizer.step_count == 3 and float(mine.arena.grad.abs().sum()) == 0.0
+        assert not tuner.reducer.consumed and not tuner.reducer.pending
+        runs.append((losses, mine.arena.master.detach().clone(), tuner.optimizer.exp_avg.clone(), tuner.optimizer.exp_avg_sq.clone()))
+    (l0, p0, m0, v0), (l1, p1, m1, v1) = runs
+    for a, b in zip(l0, l1):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-3 * max(abs(x), 1e-6), (l0, l1)
+    assert rel(m1, m0) < 2e-2 and rel(v1, v0) < 2e-2            # fp32 atomics order in the wgrad kernels only
+    init, _ = build_pair(av, trainable=True)
+    d0, d1 = (p0 - init.arena.master.detach()).flatten(), (p1 - init.arena.master.detach()).flatten()
+    assert F.cosine_similarity(d0, d1, dim=0).item() > 0.98

@@ -132,6 +132,29 @@ class FusedAdamW(torch.optim.Optimizer):
         self.step_count = 0
         self.grad_scale = 1.0
 
+    def begin_step(self):
+        """Start of an optimizer step whose ranges are applied one by one (`apply_range`), e.g. from the backward pass."""
+        self.step_count += 1
+
+    @torch.no_grad()
+    def apply_range(self, lo, hi):
+        g = self.param_groups[0]
+        a = self.arena
+        if hi > lo:
+            K.adamw_step(a.master[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], a.shadow[lo:hi],
+                         g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.step_count,
+                         self.grad_scale, zero_grad=True)
+        a.shadow_fresh = True
+
+    @torch.no_grad()
+    def apply_range_dyn(self, dyn, lo, hi):
+        g = self.param_groups[0]
+        a = self.arena
+        if hi > lo:
+            K.adamw_step_dyn(a.master[lo:hi], a.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], a.shadow[lo:hi],
+                             dyn, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], self.grad_scale, zero_grad=True)
+        a.shadow_fresh = True
+
     @torch.no_grad()
     def step(self, closure=None, ranges=None):
         """`ranges`: optional iterable of (start, end) arena slices to update one by one (the data-parallel path steps each
@@ -214,11 +237,18 @@ class GradReducer:
         self.arena = model.arena
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        self.stream = torch.cuda.Stream() if (self.world > 1 and torch.cuda.is_available()) else None
+        on_gpu = torch.cuda.is_available() and getattr(self.arena.grad, "is_cuda", False)
+        self.stream = torch.cuda.Stream() if on_gpu else None
         self.pending = []
         self.done = []          # (start, end) slices already handed to NCCL since the last wait()
+        self.consumed = []      # slices whose consumer (`on_landed`) has already been enqueued behind their collective
+        # Optional consumer of a bucket's final gradient (the trainer sets it to the AdamW range update for the duration of
+        # its backward): it is enqueued on the reducer's stream right behind the bucket's all-reduce (world_size == 1: right
+        # behind the block's backward), i.e. the optimizer runs INSIDE the backward pass, next to the remaining blocks.
+        self.on_landed = None
+        self.stream_used = False
         self.buckets = self.block_buckets(model)
-        if self.world > 1 and overlap and not os.environ.get("B200PDM_NO_OVERLAP"):   # (env: A/B measurement only)
+        if overlap and (self.world > 1 or on_gpu) and not os.environ.get("B200PDM_NO_OVERLAP"):   # (env: A/B measurement only)
             self.install(model)
 
     @staticmethod
@@ -253,48 +283,81 @@ class GradReducer:
             object.__setattr__(mod, attr, (lambda lo=lo, hi=hi: self.reduce_range(lo, hi)))
 
     def reduce_range(self, start: int, end: int):
-        if self.world == 1 or end <= start:
+        """The gradient slice [start, end) is final on the current stream: exchange it (world_size > 1) and hand it to the
+        `on_landed` consumer, if one is set."""
+        if end <= start or (self.world == 1 and self.on_landed is None):
             return
-        self.done.append((start, end))
         buf = self.arena.grad[start:end]
         if self.stream is None:                              # CPU/gloo test path
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            buf.div_(self.world)
+            if self.world > 1:
+                self.done.append((start, end))
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                buf.div_(self.world)
+            if self.on_landed is not None:
+                self.on_landed(start, end)
+                self.consumed.append((start, end))
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
+        self.stream_used = True
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        self.pending.append((work, start, end))
+            work = None
+            if self.world > 1:
+                self.done.append((start, end))
+                work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            if self.on_landed is not None:
+                if work is not None:
+                    work.wait()                              # this stream waits for the collective, the host does not
+                self.on_landed(start, end)
+                self.consumed.append((start, end))
+            else:
+                self.pending.append((work, start, end))
+
+    def _join(self):
+        """Current stream waits for the reducer's stream -- only if this step put work on it (inside a graph capture, waiting
+        on a stream that carries no captured work invalidates the capture)."""
+        if self.stream is not None and self.stream_used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.stream_used = False
+
+    def _gaps(self, spans):
+        pos = 0
+        for lo, hi in sorted(spans):
+            if lo > pos:
+                yield (pos, lo)
+            pos = max(pos, hi)
+        if pos < self.arena.numel:
+            yield (pos, self.arena.numel)
 
     def reduce_all(self):
         """Everything not reduced yet since the last wait()."""
-        pos = 0
-        for lo, hi in sorted(self.done):
-            if lo > pos:
-                self.reduce_range(pos, lo)
-            pos = max(pos, hi)
-        if pos < self.arena.numel:
-            self.reduce_range(pos, self.arena.numel)
+        if self.world == 1:
+            return
+        for lo, hi in list(self._gaps(self.done)):
+            self.reduce_range(lo, hi)
 
     def wait(self):
         for w, _, _ in self.pending:
             w.wait()
         self.pending.clear()
         self.done.clear()
-        if self.stream is not None:
-            torch.cuda.current_stream().wait_stream(self.stream)
+        self.consumed.clear()
+        self._join()
 
     def landed_ranges(self):
-        """Arena slices in the order their all-reduces were issued; before yielding a slice the current stream is made to
-        wait for that slice's collective only, so the caller's work on it (AdamW) overlaps the collectives still in flight.
-        Covers the whole arena; world_size == 1 yields it in one piece."""
+        """Arena slices that no `on_landed` consumer has taken yet, in the order their all-reduces were issued; before
+        yielding a slice the current stream is made to wait for that slice's collective only, so the caller's work on it
+        (AdamW) overlaps the collectives still in flight.  Together with the consumed slices they cover the whole arena.
+        Ends the exchange of this step: afterwards the current stream has joined the reducer's stream."""
         if self.world == 1:
-            yield (0, self.arena.numel)
-            return
-        if self.stream is None:                              # CPU/gloo path reduced synchronously
-            for lo, hi in sorted(self.done):
+            rest = list(self._gaps(self.consumed))
+        elif self.stream is None:                            # CPU/gloo path reduced synchronously
+            rest = [r for r in sorted(self.done) if r not in self.consumed]
+        else:
+            rest = None
+        if rest is not None:
+            for lo, hi in rest:
                 yield (lo, hi)
         else:
             for w, lo, hi in self.pending:
@@ -302,8 +365,8 @@ class GradReducer:
                 yield (lo, hi)
         self.pending.clear()
         self.done.clear()
-        if self.stream is not None:
-            torch.cuda.current_stream().wait_stream(self.stream)
+        self.consumed.clear()
+        self._join()
 
 
 class UnetFineTuner:
@@ -368,13 +431,33 @@ class UnetFineTuner:
         if self._graph is not None:
             return self._replay(batch)
         loss, diff, kd, blk = self.step(batch)
-        loss.backward()
-        self.reducer.reduce_all()
-        self.optimizer.step(ranges=self.reducer.landed_ranges())      # per bucket, as its all-reduce lands
+        self._backward_and_update(loss, self.optimizer)
         self.lr_scheduler.step()
         self.optimizer.zero_grad()
         self.global_step += 1
         return loss.detach(), diff, kd, blk
+
+    def _backward_and_update(self, loss, optimizer, dyn=None):
+        """backward -> gradient exchange -> AdamW, with the optimizer INSIDE the backward pass: each top-level block's slice
+        of the arena is updated as soon as that block's backward has finished (and, with world_size > 1, its all-reduce has
+        landed), on the reducer's stream, next to the backward of the remaining blocks -- AdamW is pure HBM traffic, the
+        backward GEMMs are tensor-core work.  Exactly the reference's update (trainer.py:2320-2329): a parameter's step only
+        needs its own final gradient, and no later part of the backward reads a finished block's weights.  (Gradient
+        clipping by global norm, off in the shipped configs, would need the whole gradient first: B200PDM_OPT_AFTER_BACKWARD=1
+        restores the serial order.)  `dyn`: device scalars of the graph-replayable AdamW variant."""
+        if dyn is None:
+            optimizer.begin_step()
+            apply = optimizer.apply_range
+        else:
+            apply = (lambda lo, hi: optimizer.apply_range_dyn(dyn, lo, hi))
+        self.reducer.on_landed = None if os.environ.get("B200PDM_OPT_AFTER_BACKWARD") else apply
+        try:
+            loss.backward()                      # each block's backward hands its finished slice to the reducer
+        finally:
+            self.reducer.on_landed = None
+        self.reducer.reduce_all()                # what no block claimed
+        for lo, hi in self.reducer.landed_ranges():
+            apply(lo, hi)
 
     # ------------------------------------------------------------------------------------------------ checkpoints
     def save_checkpoint(self, output_dir, subfolder="unet"):
@@ -398,11 +481,7 @@ class UnetFineTuner:
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def _graph_body(self):
         loss, diff, kd, blk = self.step(self._static_in)
-        loss.backward()                          # (world > 1: each block's backward forks its all-reduce onto the side stream)
-        self.reducer.reduce_all()
-        # AdamW per gradient bucket as its all-reduce lands; the generator joins the side stream back at the end (also
-        # inside a capture)
-        self.optimizer.step_dyn(self._dyn, ranges=self.reducer.landed_ranges())
+        self._backward_and_update(loss, self.optimizer, self._dyn)    # all-reduces and AdamW ranges become graph branches
         return loss.detach(), diff, kd, blk
 
     def _capture(self, body, optimizers, pool=None):
@@ -508,9 +587,7 @@ class BilevelUnetFineTuner(UnetFineTuner):
             self.upper_lr_scheduler.step()
             return self._upper_static_out
         loss, kd = self.upper_step(upper_batch)
-        loss.backward()                                                       # :2808
-        self.reducer.reduce_all()
-        self.upper_optimizer.step(ranges=self.reducer.landed_ranges())        # :2814
+        self._backward_and_update(loss, self.upper_optimizer)                 # :2808-2814
         self.upper_lr_scheduler.step()
         self.upper_optimizer.zero_grad()
         return loss.detach(), kd
@@ -525,9 +602,7 @@ class BilevelUnetFineTuner(UnetFineTuner):
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def _upper_graph_body(self):
         loss, kd = self.upper_step(self._upper_static_in)
-        loss.backward()
-        self.reducer.reduce_all()
-        self.upper_optimizer.step_dyn(self._upper_dyn, ranges=self.reducer.landed_ranges())
+        self._backward_and_update(loss, self.upper_optimizer, self._upper_dyn)
         return loss.detach(), kd
 
     def capture_cuda_graph(self, example_batch, example_upper_batch=None):
