@@ -238,8 +238,6 @@ def sampling_bench(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own prints ("NCCL version ...", NCCL_DEBUG output) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from unlearn_ft_b200 import _lib
     from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModelPruned
@@ -311,14 +309,37 @@ def sampling_bench(args, rank, world, local_rank):
                         "d2h_bytes_per_step": n * 4 * L * L * 4},
                 "gpu_launches": int(launches_per_call * args.steps), "clocks": clocks,
                 "algorithmic_tflops": None if fl is None else fl * images / (float(ms) * 1e-3) / 1e12}
-        print(json.dumps(line), flush=True)
+        emit(line)
     torch.cuda.synchronize()
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def own_stdout():
+    """stdout carries exactly ONE JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr, so that whatever
+    libraries print from C (NCCL writes "NCCL version ..." to stdout at the first collective) cannot precede the result."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     args = parse()
+    own_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -338,7 +359,7 @@ def main():
                            "installable offline); timed steps capped at 3, warm-up at 1 to bound the run"},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -349,7 +370,6 @@ def main():
     import torch.distributed as dist
 
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from unlearn_ft_b200 import _lib
     from unlearn_ft_b200 import kernels as K
@@ -548,7 +568,7 @@ def main():
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e!r}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     shutdown()
 
 
