@@ -4,7 +4,9 @@
 
 Unlike tests/golden (recorded once), this re-runs the reference's gated blocks / prune() / forward (through oracle/refshim)
 on arch vectors and seeds that are NOT in the golden file, and additionally compares GRADIENTS: d(loss)/d(parameter) of the
-reference's forward under torch autograd against the oracle's, for every parameter of the pruned network.
+reference's forward under torch autograd against the oracle's, for every parameter of the pruned network.  It also executes
+the reference TRAINER's own `step()` and `upper_step()` source (lifted out of pdm/training/trainer.py by name, see
+`_reference_trainer_methods`) against the oracle's `finetune_step` / `upper_step`: loss terms and gradients.
 Run by tests/test_oracle_vs_reference.py in a subprocess (the shim puts a fake `diffusers` into sys.modules), skipped
 where /root/reference does not exist (the GPU box).
 """
@@ -62,8 +64,132 @@ def main() -> int:
             e = float((po[k].grad - p.grad).abs().max()) / scale
             worst_grad = max(worst_grad, e)
             assert e < 1e-4, ("gradient", case, k, e)
-    print(f"live check ok: {len(CASES)} pruned networks, worst output error {worst_out:.2e}, worst gradient error {worst_grad:.2e}")
+    worst_step = check_training_steps(ref)
+    print(f"live check ok: {len(CASES)} pruned networks, worst output error {worst_out:.2e}, worst gradient error "
+          f"{worst_grad:.2e}; step()/upper_step() of the reference trainer vs oracle: worst loss-term error {worst_step:.2e}")
     return 0
+
+
+def _reference_trainer_methods(names):
+    """The reference's OWN `step`, `upper_step`, `cast_block_act_hooks` (pdm/training/trainer.py:557-572, 2403-2488,
+    2904-3001), lifted out of the file by name with `ast` and compiled as plain functions: importing trainer.py would pull in
+    accelerate / diffusers pipelines / wandb, none of which are installed, but these three bodies only need torch, F and
+    compute_snr."""
+    import ast
+    import os
+    import torch.nn.functional as F_
+
+    path = os.path.join(refshim.REFERENCE_ROOT, "pdm", "training", "trainer.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    found = {}
+    for cls in [n for n in tree.body if isinstance(n, ast.ClassDef)]:
+        for fn in [n for n in cls.body if isinstance(n, ast.FunctionDef)]:
+            key = (cls.name, fn.name)
+            if key in names:
+                fn.decorator_list = []
+                mod = ast.Module(body=[fn], type_ignores=[])
+                ns = {"torch": torch, "F": F_, "compute_snr": refshim.load_reference().metric.compute_snr}
+                exec(compile(ast.fix_missing_locations(mod), path, "exec"), ns)
+                found[key] = ns[fn.name]
+    missing = set(names) - set(found)
+    assert not missing, f"not found in the reference trainer: {missing}"
+    return found
+
+
+def check_training_steps(ref) -> float:
+    """Reference trainer `step()` / `upper_step()` (their own source, see above) on a stub `self` whose models are the
+    reference's own pruned U-Net + the teacher, against oracle.pdm_restated.finetune_step / upper_step on the same inputs:
+    the four loss terms and every parameter gradient."""
+    from types import SimpleNamespace as NS
+
+    from oracle import diffusers_restated as D
+
+    fns = _reference_trainer_methods({("UnetFineTuner", "step"), ("BilevelUnetFineTuner", "upper_step"),
+                                      ("Trainer", "cast_block_act_hooks")})
+    ref_step, ref_upper = fns[("UnetFineTuner", "step")], fns[("BilevelUnetFineTuner", "upper_step")]
+    ref_hooks = fns[("Trainer", "cast_block_act_hooks")]
+
+    class Sched(D.DDIMSchedulerLite):
+        def register_to_config(self, **kw):                      # diffusers ConfigMixin.register_to_config
+            for k, v in kw.items():
+                setattr(self.config, k, v)
+
+    orc = P.UNetGated(**TINY)
+    deterministic_fill(orc, 4)
+    av = make_arch_vector(orc.get_structure(), 0.6, 41, (1,))
+    orc.set_structure(P.transform_arch_vector(av, orc.get_structure()))
+    orc.prune()
+    orc.eval()
+    rm = ref_pruned_model(ref, TINY, av, 4)
+    teacher = D.UNet2DConditionModel(**{**D.SD21_UNET_CONFIG, "block_out_channels": TINY["block_out_channels"],
+                                        "attention_head_dim": TINY["heads"],
+                                        "cross_attention_dim": TINY["cross_attention_dim"]}).eval()
+    deterministic_fill(teacher, 6)
+    teacher.requires_grad_(False)
+
+    g = torch.Generator().manual_seed(77)
+    latents = torch.randn(2, 4, 16, 16, generator=g)
+    ehs = torch.randn(2, 77, TINY["cross_attention_dim"], generator=g)
+    empty = torch.randn(1, 77, TINY["cross_attention_dim"], generator=g).expand(2, -1, -1).contiguous()
+    losses_cfg = NS(diffusion_loss=NS(snr_gamma=5.0, weight=1.0), block_loss=NS(weight=0.1, upper_weight=0.0),
+                    distillation_loss=NS(weight=2.0, upper_weight=1.0))      # the shipped YAML weights (SURVEY 8d)
+    me = NS(vae=NS(encode=lambda x: NS(latent_dist=NS(sample=lambda: x)), config=NS(scaling_factor=1.0)),
+            weight_dtype=torch.float32, accelerator=NS(device=torch.device("cpu"), unwrap_model=lambda m: m),
+            config=NS(model=NS(prediction_model=NS(noise_offset=0, input_perturbation=0, max_scheduler_steps=None,
+                                                   prediction_type="v_prediction")),
+                      training=NS(losses=losses_cfg)),
+            noise_scheduler=Sched(), teacher_model=teacher, prediction_model=rm, block_act_student={}, block_act_teacher={})
+    ref_hooks(me, rm, me.block_act_student)
+    ref_hooks(me, teacher, me.block_act_teacher)
+    fs, ft = {}, {}
+    P.cast_block_act_hooks(orc, fs)
+    P.cast_block_act_hooks(teacher, ft)
+    batch = {"pixel_values": latents, "prompt_embeds": ehs, "empty_prompt_embeds": empty}
+    worst = 0.0
+
+    def grads_equal(tag):
+        nonlocal worst
+        po, pr = dict(orc.named_parameters()), dict(rm.named_parameters())
+        compared = 0
+        for k, p in pr.items():
+            if p.grad is None or float(p.grad.abs().max()) == 0.0:
+                continue
+            e = float((po[k].grad - p.grad).abs().max() / p.grad.abs().max())
+            worst = max(worst, e)
+            assert e < 1e-4, (tag, k, e)
+            compared += 1
+        assert compared > 0.8 * len(pr), (tag, compared, len(pr))   # (a depth-dropped block's parameters get no gradient)
+        for p in list(po.values()) + list(pr.values()):
+            p.grad = None
+
+    for seed in (123, 124):
+        # lower step: the reference draws noise and timesteps itself (trainer.py:2409,2421); same RNG calls, same order
+        torch.manual_seed(seed)
+        out_r = ref_step(me, batch)
+        torch.manual_seed(seed)
+        noise = torch.randn_like(latents)
+        timesteps = torch.randint(0, 1000, (latents.shape[0],)).long()
+        out_o = P.finetune_step(orc, teacher, D.DDIMSchedulerLite(), latents, noise, timesteps, ehs, fs, ft)
+        for a, b, name in zip(out_o, out_r, ("loss", "diff_loss", "distillation_loss", "block_loss")):
+            e = abs(float(a.detach()) - float(b.detach())) / max(abs(float(b.detach())), 1e-12)
+            worst = max(worst, e)
+            assert e < 1e-6, ("step", name, float(a), float(b))
+        out_o[0].backward(), out_r[0].backward()
+        grads_equal("step")
+        # upper (concept-suppression) step
+        torch.manual_seed(seed)
+        up_r = ref_upper(me, batch)
+        torch.manual_seed(seed)
+        noise = torch.randn_like(latents)
+        timesteps = torch.randint(0, 1000, (latents.shape[0],)).long()
+        up_o = P.upper_step(orc, teacher, D.DDIMSchedulerLite(), latents, noise, timesteps, ehs, empty)
+        e = abs(float(up_o.detach()) - float(up_r[0].detach())) / abs(float(up_r[0].detach()))
+        worst = max(worst, e)
+        assert e < 1e-6 and float(up_r[1]) == 0.0 and float(up_r[3]) == 0.0, ("upper_step", float(up_o), [float(v) for v in up_r])
+        up_o.backward(), up_r[0].backward()
+        grads_equal("upper_step")
+    return worst
 
 
 if __name__ == "__main__":

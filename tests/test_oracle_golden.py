@@ -8,7 +8,7 @@ import torch
 
 from oracle import diffusers_restated as D
 from oracle import pdm_restated as P
-from oracle.make_golden import TINY, deterministic_fill, tensor_digest
+from oracle.make_golden import SMALL64, TINY, deterministic_fill, tensor_digest
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_golden.pt")
 
@@ -121,3 +121,29 @@ def test_step_loss_terms():
     assert torch.allclose(diff, exp_diff, rtol=1e-5) and torch.allclose(kd, exp_kd, rtol=1e-5)
     assert torch.allclose(loss.detach(), exp_diff + 0.1 * blk + 2.0 * exp_kd, rtol=1e-5)
     assert len(fs) == 9 and set(fs) == set(P.BLOCK_KEYS)
+
+
+def test_step_and_upper_step_match_reference_trainer_golden():
+    """tests/golden/reference_step_golden.pt holds the loss terms the reference TRAINER's own `step()` / `upper_step()` source
+    (trainer.py:2403-2488, 2904-3001, run by oracle/make_step_golden.py on the reference's own pruned U-Net) produced, with the
+    noise / timesteps it drew: the oracle reproduces them on the same sample."""
+    from oracle.make_step_golden import teacher_model
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_step_golden.pt"), weights_only=False)
+    m = P.UNetGated(**SMALL64)
+    deterministic_fill(m, g["student_seed"])
+    m.set_structure(P.transform_arch_vector(g["arch_vector"], m.get_structure()))
+    m.prune()
+    m.eval()
+    teacher = teacher_model()
+    fs, ft = {}, {}
+    P.cast_block_act_hooks(m, fs), P.cast_block_act_hooks(teacher, ft)
+    for case in g["cases"]:
+        with torch.no_grad():
+            out = P.finetune_step(m, teacher, D.DDIMSchedulerLite(), g["latents"], case["noise"], case["timesteps"],
+                                  g["prompt_embeds"], fs, ft)
+            up = P.upper_step(m, teacher, D.DDIMSchedulerLite(), g["latents"], case["noise"], case["timesteps"],
+                              g["prompt_embeds"], g["empty_prompt_embeds"])
+        for a, b in zip(out, case["step"]):
+            assert abs(float(a) - b) <= 1e-6 * abs(b), (case["rng_seed"], [float(v) for v in out], case["step"])
+        assert abs(float(up) - case["upper_step"][0]) <= 1e-6 * case["upper_step"][0]
+        assert case["upper_step"][1] == 0.0 and case["upper_step"][3] == 0.0       # shipped upper weights: 0 / 1 / 0

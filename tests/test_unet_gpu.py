@@ -371,3 +371,35 @@ def test_optimizer_inside_backward_matches_serial_order(gold, monkeypatch):
     init, _ = build_pair(av, trainable=True)
     d0, d1 = (p0 - init.arena.master.detach()).flatten(), (p1 - init.arena.master.detach()).flatten()
     assert F.cosine_similarity(d0, d1, dim=0).item() > 0.98
+
+
+def test_step_losses_match_reference_trainer_golden():
+    """The CUDA path against values produced by the reference TRAINER's own `step()` / `upper_step()` source on the reference's
+    own pruned U-Net (tests/golden/reference_step_golden.pt, written by oracle/make_step_golden.py in the builder container):
+    same networks, same latents / noise / timesteps / text states; bf16 pipeline vs the reference's fp32 -> 2e-2 (north star)."""
+    from oracle import diffusers_restated as D
+    from oracle import pdm_restated as P
+    from oracle.make_golden import SMALL64, deterministic_fill
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel, UNet2DConditionModelPruned
+    from unlearn_ft_b200.pdm.training import BilevelUnetFineTuner
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_step_golden.pt"), weights_only=False)
+    full = P.UNetGated(**SMALL64)
+    deterministic_fill(full, g["student_seed"])
+    student = UNet2DConditionModelPruned(small_cfg(), arch_vector=g["arch_vector"], seed=None)
+    student.load_unpruned_state_dict(full.state_dict())
+    t_o = D.UNet2DConditionModel(**{**D.SD21_UNET_CONFIG, "block_out_channels": SMALL64["block_out_channels"],
+                                    "attention_head_dim": SMALL64["heads"],
+                                    "cross_attention_dim": SMALL64["cross_attention_dim"]})
+    deterministic_fill(t_o, g["teacher_seed"])
+    teacher = UNet2DConditionModel(small_cfg(), seed=None)
+    teacher.load_state_dict(t_o.state_dict())
+    tuner = BilevelUnetFineTuner(student, teacher, lr=1e-5, warmup_steps=0)
+    for case in g["cases"]:
+        batch = dict(latents=g["latents"].cuda(), noise=case["noise"].cuda(), timesteps=case["timesteps"].cuda(),
+                     prompt_embeds=g["prompt_embeds"].cuda(), empty_prompt_embeds=g["empty_prompt_embeds"].cuda())
+        vals = [float(v.detach()) for v in tuner.step(batch)]
+        print("b200", vals, "reference trainer", case["step"])
+        for a, b in zip(vals, case["step"]):
+            assert abs(a - b) <= 2e-2 * abs(b), (vals, case["step"])
+        up, _ = tuner.upper_step(batch)
+        assert abs(float(up.detach()) - case["upper_step"][0]) <= 2e-2 * case["upper_step"][0], (float(up), case["upper_step"])
