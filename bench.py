@@ -48,7 +48,8 @@ def parse():
                     help="BASELINE config 5 instead of the default config 2: forward-only CFG sampling loop (U-Net only), "
                          "--images per GPU, 50 DDIM steps, guidance 7.5; a 'step' is one complete 50-step sampling call")
     ap.add_argument("--images", type=int, default=32, help="--sampling: images per GPU (U-Net batch = 2x)")
-    ap.add_argument("--cpu-steps", type=int, default=1)
+    ap.add_argument("--cpu-steps", type=int, default=4,
+                    help="cpu_baseline: timed batch-1 oracle steps after one untimed step (about 10-15 s on the GPU box's host cores)")
     ap.add_argument("--bilevel", action="store_true",
                     help="BASELINE config 4: bilevel fine-tuning + concept suppression -- every --upper-freq lower (DDPM+KD) "
                          "steps one upper (ESD-style unlearning) step with its own AdamW state; samples/s over whole cycles")
@@ -563,7 +564,7 @@ def main():
         line["config"]["step_launch"] += " (lower and upper step are two graphs sharing one memory pool)" if use_graph else ""
     if not args.no_cpu_baseline and world == 1 and not args.bilevel:
         try:
-            res = cpu_reference_run(args.ratio, L, args.cpu_steps, 0)
+            res = cpu_reference_run(args.ratio, L, args.cpu_steps, 1)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
