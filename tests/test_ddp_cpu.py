@@ -39,6 +39,50 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_fused(rank, world, port, out):
+    """Optimizer-inside-backward path: buckets handed over during 'backward' are exchanged and immediately given to the
+    consumer; what no bucket claimed is exchanged by reduce_all() and left to landed_ranges()."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unlearn_ft_b200.pdm.training.trainer import GradReducer
+    g = torch.Generator().manual_seed(200 + rank)
+    grad = torch.randn(1000, generator=g)
+    model = SimpleNamespace(arena=SimpleNamespace(grad=grad.clone(), numel=1000))
+    red = GradReducer(model)
+    seen = []                          # (lo, hi, copy of the slice at hand-over time) -- must already be the cross-rank mean
+
+    def consumer(lo, hi):
+        seen.append((lo, hi, model.arena.grad[lo:hi].clone()))
+        model.arena.grad[lo:hi].zero_()            # what AdamW does (zero_grad fused into the update)
+
+    red.on_landed = consumer
+    red.reduce_range(700, 1000)
+    red.reduce_range(200, 500)
+    red.on_landed = None
+    red.reduce_all()
+    rest = list(red.landed_ranges())
+    assert sorted(rest) == [(0, 200), (500, 700)], rest
+    assert not red.pending and not red.done and not red.consumed
+    out[rank] = dict(seen=[(lo, hi, t) for lo, hi, t in seen], grad=model.arena.grad.clone())
+    dist.destroy_process_group()
+
+
+def test_optimizer_in_backward_consumer_world2_gloo():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_fused, args=(world, port, out), nprocs=world, join=True)
+    expect = sum(torch.randn(1000, generator=torch.Generator().manual_seed(200 + r)) for r in range(world)) / world
+    for r in range(world):
+        seen = out[r]["seen"]
+        assert [(lo, hi) for lo, hi, _ in seen] == [(700, 1000), (200, 500)]
+        for lo, hi, t in seen:
+            assert torch.allclose(t, expect[lo:hi], atol=1e-6)           # the consumer saw the averaged gradient
+        gr = out[r]["grad"]
+        assert float(gr[700:1000].abs().sum()) == 0.0 and float(gr[200:500].abs().sum()) == 0.0
+        assert torch.allclose(gr[0:200], expect[0:200], atol=1e-6) and torch.allclose(gr[500:700], expect[500:700], atol=1e-6)
+
+
 def test_gradreducer_world2_gloo():
     world, port = 2, _free_port()
     mgr = mp.Manager()
