@@ -64,10 +64,40 @@ def main() -> int:
             e = float((po[k].grad - p.grad).abs().max()) / scale
             worst_grad = max(worst_grad, e)
             assert e < 1e-4, ("gradient", case, k, e)
+    worst_gated = check_gated_mode(ref, sample, tsteps, ctx)
     worst_step = check_training_steps(ref)
     print(f"live check ok: {len(CASES)} pruned networks, worst output error {worst_out:.2e}, worst gradient error "
-          f"{worst_grad:.2e}; step()/upper_step() of the reference trainer vs oracle: worst loss-term error {worst_step:.2e}")
+          f"{worst_grad:.2e}; gated (un-pruned, multiplicative gates) forward: {worst_gated:.2e}; step()/upper_step() of the "
+          f"reference trainer vs oracle: worst loss-term error {worst_step:.2e}")
     return 0
+
+
+def check_gated_mode(ref, sample, tsteps, ctx) -> float:
+    """The reference's OTHER code path for the same arch vector: gates applied multiplicatively at run time, nothing sliced
+    (`pruned=False`; blocks.py:56-58,267-272,343-348,582-587 -- what the pruning phase trains with).  Reference gated model
+    vs the oracle's gated model, structure set, prune() NOT called."""
+    from oracle.make_golden import REF_BLOCKS
+    worst = 0.0
+    for case in CASES:
+        orc = P.UNetGated(**TINY)
+        deterministic_fill(orc, 13)
+        av = make_arch_vector(orc.get_structure(), case["ratio"], case["seed"] + 100, case["drop"])
+        orc.set_structure(P.transform_arch_vector(av, orc.get_structure()))
+        orc.eval()
+        rm = ref.unet.UNet2DConditionModelGated(sample_size=16, block_out_channels=TINY["block_out_channels"],
+                                                attention_head_dim=TINY["heads"],
+                                                cross_attention_dim=TINY["cross_attention_dim"], use_linear_projection=True,
+                                                norm_eps=1e-5, gated_ff=True, ff_gate_width=32, **REF_BLOCKS)
+        deterministic_fill(rm, 13)
+        rm.set_structure(ref.hypernet.HyperStructure.transform_arch_vector(av, rm.get_structure()))
+        rm.eval()
+        with torch.no_grad():
+            y_o = orc(sample, tsteps, ctx).sample
+            y_r = rm(sample, tsteps, ctx).sample
+        err = float((y_o - y_r).abs().max() / y_r.abs().max())
+        worst = max(worst, err)
+        assert err < 1e-5, ("gated forward", case, err)
+    return worst
 
 
 def _reference_trainer_methods(names):
