@@ -6,7 +6,8 @@ Unlike tests/golden (recorded once), this re-runs the reference's gated blocks /
 on arch vectors and seeds that are NOT in the golden file, and additionally compares GRADIENTS: d(loss)/d(parameter) of the
 reference's forward under torch autograd against the oracle's, for every parameter of the pruned network.  It also executes
 the reference TRAINER's own `step()` and `upper_step()` source (lifted out of pdm/training/trainer.py by name, see
-`_reference_trainer_methods`) against the oracle's `finetune_step` / `upper_step`: loss terms and gradients.
+`_reference_trainer_methods`) against the oracle's `finetune_step` / `upper_step`: loss terms and gradients; the reference's
+gated (un-pruned) forward; and the reference pipeline's own `generate_samples` CFG loop against `cfg_sample_loop`.
 Run by tests/test_oracle_vs_reference.py in a subprocess (the shim puts a fake `diffusers` into sys.modules), skipped
 where /root/reference does not exist (the GPU box).
 """
@@ -66,9 +67,11 @@ def main() -> int:
             assert e < 1e-4, ("gradient", case, k, e)
     worst_gated = check_gated_mode(ref, sample, tsteps, ctx)
     worst_step = check_training_steps(ref)
+    worst_loop = check_sampling_loop(ref)
     print(f"live check ok: {len(CASES)} pruned networks, worst output error {worst_out:.2e}, worst gradient error "
           f"{worst_grad:.2e}; gated (un-pruned, multiplicative gates) forward: {worst_gated:.2e}; step()/upper_step() of the "
-          f"reference trainer vs oracle: worst loss-term error {worst_step:.2e}")
+          f"reference trainer vs oracle: worst loss-term error {worst_step:.2e}; generate_samples() CFG loop of the reference "
+          f"pipeline vs oracle: {worst_loop:.2e}")
     return 0
 
 
@@ -97,6 +100,74 @@ def check_gated_mode(ref, sample, tsteps, ctx) -> float:
         err = float((y_o - y_r).abs().max() / y_r.abs().max())
         worst = max(worst, err)
         assert err < 1e-5, ("gated forward", case, err)
+    return worst
+
+
+def check_sampling_loop(ref) -> float:
+    """The reference pipeline's OWN `generate_samples` (pdm/pipelines/pruning_pipelines.py:867-1010), lifted out of the file by
+    name like the trainer methods, on a stub `self` (reference pruned U-Net; restated DDIM scheduler; given text states and
+    initial latents; output_type="latent") against oracle.pdm_restated.cfg_sample_loop: pins the classifier-free-guidance
+    loop -- batch doubling, scalar-timestep U-Net call with return_dict=False, chunk + guidance combine, scheduler hand-off."""
+    import ast
+    import contextlib
+    import os
+    from types import SimpleNamespace as NS
+    from typing import Any, Callable, Dict, List, Optional, Union
+
+    from oracle import diffusers_restated as D
+
+    path = os.path.join(refshim.REFERENCE_ROOT, "pdm", "pipelines", "pruning_pipelines.py")
+    tree = ast.parse(open(path).read())
+    fn = None
+    for cls in [n for n in tree.body if isinstance(n, ast.ClassDef)]:
+        for f in [n for n in cls.body if isinstance(n, ast.FunctionDef)]:
+            if f.name == "generate_samples" and fn is None:
+                fn = f
+    assert fn is not None, "generate_samples not found in the reference pipelines"
+    fn.decorator_list = []
+    ns = {"torch": torch, "Union": Union, "List": List, "Optional": Optional, "Callable": Callable, "Dict": Dict, "Any": Any,
+          "StableDiffusionPipelineOutput": lambda images, nsfw_content_detected: NS(images=images),
+          "rescale_noise_cfg": None}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=[fn], type_ignores=[])), path, "exec"), ns)
+    generate_samples = ns["generate_samples"]
+
+    class Sched(D.DDIMSchedulerLite):
+        order = 1
+
+        def step(self, model_output, timestep, sample, return_dict=False, **kw):       # diffusers returns a tuple
+            return (super().step(model_output, timestep, sample, **kw),)
+
+    orc = P.UNetGated(**TINY)
+    deterministic_fill(orc, 8)
+    av = make_arch_vector(orc.get_structure(), 0.7, 51, (4,))
+    orc.set_structure(P.transform_arch_vector(av, orc.get_structure()))
+    orc.prune()
+    orc.eval()
+    rm = ref_pruned_model(ref, TINY, av, 8)
+    g = torch.Generator().manual_seed(5)
+    lat0 = torch.randn(2, 4, 16, 16, generator=g)
+    pe = torch.randn(2, 77, TINY["cross_attention_dim"], generator=g)
+    ne = torch.randn(1, 77, TINY["cross_attention_dim"], generator=g).expand(2, -1, -1).contiguous()
+    sched = Sched()
+    me = NS(unet=rm, vae_scale_factor=8, check_inputs=lambda *a, **k: None, _execution_device=torch.device("cpu"),
+            encode_prompt=lambda prompt, device, n, cfg, neg, prompt_embeds=None, negative_prompt_embeds=None, lora_scale=None:
+            (prompt_embeds, negative_prompt_embeds),
+            scheduler=sched,
+            prepare_latents=lambda b, c, h, w, dtype, device, generator, latents: latents * sched.init_noise_sigma,
+            prepare_extra_step_kwargs=lambda generator, eta: {},
+            progress_bar=lambda total=None: contextlib.nullcontext(NS(update=lambda: None)),
+            image_processor=NS(postprocess=lambda image, output_type=None, do_denormalize=None: image),
+            maybe_free_model_hooks=lambda: None, vae=None)
+    worst = 0.0
+    for steps, scale in ((4, 7.5), (5, 1.5)):
+        with torch.no_grad():
+            out_r = generate_samples(me, prompt=None, num_inference_steps=steps, guidance_scale=scale, latents=lat0.clone(),
+                                     prompt_embeds=pe, negative_prompt_embeds=ne, output_type="latent").images
+            out_o = P.cfg_sample_loop(orc, D.DDIMSchedulerLite(), lat0.clone(), pe, ne, num_inference_steps=steps,
+                                      guidance_scale=scale)
+        err = float((out_o - out_r).abs().max() / out_r.abs().max())
+        worst = max(worst, err)
+        assert err < 1e-5, ("cfg loop", steps, scale, err)
     return worst
 
 
