@@ -44,6 +44,11 @@ uint64_t b200pdm_launch_count(void);
  * on a second stream which may run concurrently with lane 0's (the trainer does this for the frozen teacher's forward,
  * pdm/training/trainer.py) selects another lane for those calls and switches back afterwards.  Default lane 0. */
 int b200pdm_set_lane(int lane);
+/* Host-only: the tile plan b200pdm_gemm would pick (no device work; usable without a GPU).  n = N per group, tiles_m =
+ * ceil(M / 128), kblocks = number of 64-wide K blocks; can_split: the output may be split along K (fp32 accumulate, or a
+ * scratch + finalize pass when split_needs_finalize).  out[7] = {block_n, splits, pair, m_sub, stages, tiles, slots}. */
+int b200pdm_gemm_plan(int64_t n, int n_groups, int b_mn, int tiles_m, int Z, int kblocks, int can_split,
+                      int split_needs_finalize, int* out);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tensor-core core: one persistent, warp-specialised tcgen05 kernel (TMA -> smem ring -> tcgen05.mma -> TMEM ->

@@ -110,3 +110,36 @@ def test_checkpoint_wire_format_roundtrip(gold, tmp_path):
     assert list(a.keys()) == list(b.keys())
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_gemm_tile_planner_invariants():
+    """Host logic of the tensor-core core, queried without a GPU (b200pdm_gemm_plan): for the shape families of the U-Net
+    (conv fprop / dgrad / wgrad, attention and feed-forward projections, time-embedding rows) the plan always satisfies the
+    kernel's hard limits -- tile width granularity, two TMEM accumulators of <= 256 columns, >= 2 pipeline stages inside
+    227 KB of shared memory, split-K only where allowed and never below 8 k-blocks per split -- and fills the machine."""
+    from unlearn_ft_b200 import _lib
+    shapes = []
+    for tiles_m in (1, 2, 8, 32, 128, 512, 2048):                       # M = 16 ... 262144 rows
+        for n in (4, 64, 170, 320, 340, 640, 680, 960, 1280, 2560, 5120, 10240):
+            for kb in (2, 5, 10, 20, 45, 90, 135, 180, 360, 1024):
+                shapes.append((n, tiles_m, kb))
+    for n, tiles_m, kb in shapes:
+        for b_mn in (False, True):
+            for can_split, fin in ((False, True), (True, True), (True, False)):
+                p = _lib.gemm_plan(n, tiles_m=tiles_m, kblocks=kb, b_mn=b_mn, can_split=can_split, split_needs_finalize=fin)
+                g = 64 if b_mn else 16
+                assert p["block_n"] % g == 0 and g <= p["block_n"] <= 256, (n, tiles_m, kb, p)
+                assert p["m_sub"] in (1, 2) and p["m_sub"] * p["block_n"] <= 512
+                assert p["pair"] in (0, 1) and (p["pair"] == 0 or tiles_m >= 2)
+                assert p["m_sub"] == 1 or tiles_m >= 2 * (2 if p["pair"] else 1)
+                assert p["splits"] >= 1 and (can_split or p["splits"] == 1)
+                assert p["splits"] == 1 or kb // p["splits"] >= 8
+                stage = p["m_sub"] * 16384 + (p["block_n"] // 2 if p["pair"] else p["block_n"]) * 128
+                assert 2 <= p["stages"] <= 8 and p["stages"] * stage <= 227 * 1024
+                assert p["slots"] == (74 if p["pair"] else 148) and p["tiles"] >= 1
+                if p["block_n"] > n:                                     # a padded tile only when N itself is small
+                    assert p["block_n"] - n < g or n < 64
+    # the planner prefers plans that fill whole waves: the 1280 -> 1280 conv at 8x8 (M = 1024) is split along K
+    p = _lib.gemm_plan(1280, tiles_m=8, kblocks=180, can_split=True)
+    assert p["splits"] > 1 and p["tiles"] >= 0.9 * p["slots"]
+    assert _lib.lib().b200pdm_launch_count() == 0

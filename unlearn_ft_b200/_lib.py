@@ -49,6 +49,7 @@ _SIGS = {
     "b200pdm_last_error": [],
     "b200pdm_launch_count": [],
     "b200pdm_set_lane": [i32],
+    "b200pdm_gemm_plan": [i64, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int)],
     "b200pdm_gemm_trace_dump": [C.c_char_p],
     "b200pdm_gemm": [C.POINTER(GemmDesc), c_p],
     "b200pdm_linear_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i32, i64, i64, i64, c_p],
@@ -133,6 +134,13 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().b200pdm_last_error()
         raise B200PdmError(f"b200pdm call {what} failed with status {rc}: {msg.decode() if msg else ''}")
+
+
+def gemm_plan(n, n_groups=1, b_mn=False, tiles_m=1, Z=1, kblocks=1, can_split=False, split_needs_finalize=True) -> dict:
+    """Tile plan the GEMM core would choose (host-only query; works without a GPU)."""
+    out = (C.c_int * 7)()
+    check(lib().b200pdm_gemm_plan(n, n_groups, int(b_mn), tiles_m, Z, kblocks, int(can_split), int(split_needs_finalize), out))
+    return dict(zip(("block_n", "splits", "pair", "m_sub", "stages", "tiles", "slots"), list(out)))
 
 
 def launch_count() -> int:

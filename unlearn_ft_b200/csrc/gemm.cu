@@ -1300,6 +1300,27 @@ extern "C" {
 int b200pdm_version(void) { return 100; }
 const char* b200pdm_last_error(void) { return get_err(); }
 uint64_t b200pdm_launch_count(void) { return g_launches.load(); }
+// Host-only query of the tile planner (no device work): what launch_gemm would choose for a GEMM whose N per group is `n`,
+// with `tiles_m` 128-row tiles, `Z` batch slabs and `kblocks` 64-wide K blocks.  out = {block_n, splits, pair, m_sub, stages,
+// tiles (CTA-slot units incl. splits), slots (148 or 74 pairs)}.  Used by the CPU tests and tools/plan_report.py.
+int b200pdm_gemm_plan(int64_t n, int n_groups, int b_mn, int tiles_m, int Z, int kblocks, int can_split,
+                      int split_needs_finalize, int* out) {
+  if (!out || n <= 0 || n_groups <= 0 || tiles_m <= 0 || Z <= 0 || kblocks <= 0) return B200PDM_ERR_ARG;
+  const Plan plan = plan_gemm(n, n_groups, b_mn != 0, tiles_m, Z, kblocks, can_split != 0, split_needs_finalize != 0, 0);
+  if (plan.bn <= 0) return B200PDM_ERR_ARG;
+  const int epi_groups = 2;
+  const int stage_bytes = plan.m_sub * kStageABytes + (plan.pair ? plan.bn / 2 : plan.bn) * 128;
+  const int fixed_bytes = 1024 + (2 * 8 + 6) * 8 + 64 + 128 + 4 * epi_groups * 1024;
+  int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const int cs = plan.pair ? 2 : 1;
+  const long tiles_n = (long)((n + plan.bn - 1) / plan.bn) * n_groups;
+  const long tiles = (long)((tiles_m + cs * plan.m_sub - 1) / (cs * plan.m_sub)) * tiles_n * Z * plan.splits;
+  out[0] = plan.bn, out[1] = plan.splits, out[2] = plan.pair, out[3] = plan.m_sub, out[4] = stages;
+  out[5] = (int)tiles, out[6] = 148 / cs;
+  return B200PDM_OK;
+}
 int b200pdm_set_lane(int lane) {
   if (lane < 0 || lane >= kMaxLanes) return B200PDM_ERR_ARG;
   g_lane = lane;
