@@ -16,3 +16,34 @@ def test_oracle_matches_reference_code_live():
     r = subprocess.run([sys.executable, "-m", "oracle.live_check"], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "live check ok" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs"), reason="reference tree not present (GPU box)")
+def test_trainer_defaults_equal_the_shipped_reference_configs():
+    """Defaults of the B200 tuners (and what bench.py runs) = the reference's fine-tuning YAMLs: loss weights and snr_gamma,
+    AdamW hyper-parameters, constant-with-warmup schedule, bilevel upper learning rate / frequency / upper weights."""
+    import inspect
+
+    import yaml
+
+    from unlearn_ft_b200.pdm.training import BilevelUnetFineTuner, UnetFineTuner
+    base = "/root/reference/configs/baselines"
+    cfg = yaml.safe_load(open(os.path.join(base, "sd-2-1_coco_aptp_both_512.yaml")))
+    bil = yaml.safe_load(open(os.path.join(base, "sd-2-1_coco_aptp_both_512_bilevel.yaml")))
+    d = {k: v.default for k, v in inspect.signature(UnetFineTuner.__init__).parameters.items() if v.default is not inspect._empty}
+    losses, optim = cfg["training"]["losses"], cfg["training"]["optim"]
+    assert d["w_diff"] == losses["diffusion_loss"]["weight"] and d["snr_gamma"] == losses["diffusion_loss"]["snr_gamma"]
+    assert d["w_kd"] == losses["distillation_loss"]["weight"] and d["w_block"] == losses["block_loss"]["weight"]
+    assert d["lr"] == float(optim["prediction_model_learning_rate"])
+    assert d["weight_decay"] == float(optim["prediction_model_weight_decay"])
+    assert d["betas"] == (optim["adam_beta1"], optim["adam_beta2"]) and d["eps"] == float(optim["adam_epsilon"])
+    assert optim["lr_scheduler"] == "constant_with_warmup" and d["warmup_steps"] == optim["lr_warmup_steps"]
+    assert not optim.get("clip_grad_norm")            # the optimizer-inside-backward schedule relies on this
+    db = {k: v.default for k, v in inspect.signature(BilevelUnetFineTuner.__init__).parameters.items()
+          if v.default is not inspect._empty}
+    bl, bo = bil["training"]["losses"], bil["training"]["optim"]
+    assert db["upper_lr"] == float(bo["prediction_model_upper_learning_rate"])
+    assert db["upper_step_freq"] == bil["training"]["upper_step_freq"]
+    assert (bl["diffusion_loss"]["upper_weight"], bl["distillation_loss"]["upper_weight"], bl["block_loss"]["upper_weight"]) \
+        == (0.0, 1.0, 0.0)                            # what BilevelUnetFineTuner.upper_step implements
+    assert not bo.get("clip_grad_norm")
