@@ -216,20 +216,35 @@ int b200pdm_timestep_embedding(const int64_t* t, void* out, int64_t ldo, int bat
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused distillation loss (trainer.py:2451-2486): min-SNR weighted MSE(pred, target) + output-KD MSE(pred, teacher)
- * + mean over feature maps of MSE(student_feat, teacher_feat), forward AND gradients in one pass per tensor.
+ * + mean over feature maps of MSE(student_feat, teacher_feat), forward AND gradients in a single kernel launch.
  * ------------------------------------------------------------------------------------------------------------ */
-/* pred/target/teacher: fp32 [B, n_per_sample]; snr_w: fp32 [B] (min(snr+1,gamma)/(snr+1), trainer.py:2457-2466).
- * sums[0] += sum_b w_b * mean_chw (p-y)^2 / B     (diff loss)
- * sums[1] += mean (p - p_T)^2                     (distillation loss)
- * sums[3] += w_diff * (diff term) + w_kd * (kd term)    (running weighted total; sums is fp32 [4], caller-zeroed)
- * dpred = w_diff * 2 w_b (p-y)/(B n) + w_kd * 2 (p-p_T)/(B n)                                              */
-int b200pdm_pred_loss(const float* pred, const float* target, const float* teacher, const float* snr_w,
-                      float* dpred, float* sums, int batch, int64_t n_per_sample, float w_diff, float w_kd,
-                      b200pdm_stream_t stream);
-/* One feature pair (bf16, same pitch layout): sums[2] += mean((s-t)^2) / n_maps ; ds = scale * 2 (s-t)/numel
- * with scale = w_block / n_maps (trainer.py:2475-2481); sums[3] += w_block * that term.                    */
-int b200pdm_feature_loss(const void* s, const void* t, void* ds, float* sums, int64_t numel, float inv_maps,
-                         float w_block, b200pdm_stream_t stream);
+/* ONE launch for the whole loss, value AND gradients (north star (c); replaces the 11 F.mse_loss calls + autograd of
+ * trainer.py:2451-2486).  pred/target/teacher: fp32 [batch, n_per_sample] (the reference's explicit .float() casts,
+ * :2452,2468,2485; target or teacher may be NULL to drop that term).  Per-sample min-SNR weights (:2457-2466): either
+ * snr_w (fp32 [batch]) or, when snr_w is NULL, computed in the kernel from alphas_cumprod (fp32 table) and timesteps
+ * (int64 [batch]): snr = acp/(1-acp) (+1 first for v_prediction), w = min(snr, snr_gamma)/snr; all three NULL = weight 1.
+ * pairs: HOST array of n_pairs (<= 16) dense bf16 feature maps (student, teacher, gradient out or NULL, numel) -- the hook
+ * outputs of trainer.py:557-572, which the reference does not upcast (:2478).
+ *   sums[0] = mean_b(w_b * mean_chw (pred - target)^2)          diff_loss
+ *   sums[1] = mean((pred - teacher)^2)                          distillation_loss
+ *   sums[2] = (1/n_pairs) * sum_k mean((s_k - t_k)^2)           block_loss
+ *   sums[3] = w_diff*sums[0] + w_block*sums[2] + w_kd*sums[1]   loss
+ *   dpred   = d sums[3] / d pred (fp32, may be NULL);  pairs[k].ds = d sums[3] / d s_k (bf16)
+ * Two-stage reduction inside the launch (per-block partial rows in `workspace`, summed in block order by the block that
+ * arrives last): bit-identical from run to run, no floating-point atomics.  workspace: b200pdm_kd_loss_workspace() bytes,
+ * 16-byte aligned, contents irrelevant. */
+typedef struct {
+  const void* s;  /* student feature map, bf16, dense */
+  const void* t;  /* teacher feature map, bf16, same layout */
+  void* ds;       /* gradient w.r.t. s (bf16) or NULL */
+  int64_t numel;
+} b200pdm_feature_pair;
+size_t b200pdm_kd_loss_workspace(int n_pairs);
+int b200pdm_kd_loss_fused(const float* pred, const float* target, const float* teacher, const float* snr_w,
+                          const float* alphas_cumprod, const int64_t* timesteps, float snr_gamma, int v_prediction,
+                          float* dpred, int batch, int64_t n_per_sample, float w_diff, float w_kd,
+                          const b200pdm_feature_pair* pairs, int n_pairs, float w_block, float* sums, void* workspace,
+                          size_t ws_bytes, b200pdm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Multi-tensor AdamW over the flat parameter arena (torch.optim.AdamW semantics; trainer.py:265-284,2327,2814).

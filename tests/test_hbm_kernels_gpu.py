@@ -157,27 +157,46 @@ def test_layout_and_timestep():
 
 
 def test_losses():
+    """b200pdm_kd_loss_fused = trainer.py:2451-2486 in one launch: values, gradients, in-kernel min-SNR weights, and
+    run-to-run bit-exactness (two-stage reduction, no float atomics)."""
     k = _k()
     B, n = 4, 4 * 64 * 64
     pred, tgt, tea = (torch.randn(B, n, device="cuda") for _ in range(3))
     w = torch.rand(B, device="cuda") + 0.1
-    sums = torch.zeros(4, device="cuda")
-    dpred = k.pred_loss(pred, tgt, tea, w, sums, 1.0, 2.0)
+    shapes = [(B, 320, 32, 32), (B, 640, 16, 16), (B, 1280, 8, 8), (B, 1280, 8, 8), (B, 1280, 8, 8), (B, 1280, 16, 16),
+              (B, 1280, 32, 32), (B, 640, 64, 64), (B, 320, 64, 64)]
+    fs = [torch.randn(*s, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last) for s in shapes]
+    ft = [torch.randn(*s, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last) for s in shapes]
+    sums, dpred, dfs = k.kd_loss_fused(pred, tgt, tea, fs, ft, 1.0, 2.0, 0.1, snr_w=w)
     pr = pred.clone().requires_grad_(True)
+    srs = [s.float().requires_grad_(True) for s in fs]
     l_d = (((pr - tgt) ** 2).mean(1) * w).mean()
     l_k = F.mse_loss(pr, tea)
-    (1.0 * l_d + 2.0 * l_k).backward()
-    assert abs(sums[0].item() - l_d.item()) / l_d.item() < 1e-5
-    assert abs(sums[1].item() - l_k.item()) / l_k.item() < 1e-5
+    l_b = sum(F.mse_loss(a, b.float()) for a, b in zip(srs, ft)) / len(fs)
+    total = 1.0 * l_d + 0.1 * l_b + 2.0 * l_k
+    total.backward()
+    for got, ref in zip(sums.tolist(), (l_d.item(), l_k.item(), l_b.item(), total.item())):
+        assert abs(got - ref) / ref < 1e-5, (sums.tolist(), ref)
     assert rel_err(dpred, pr.grad) < 1e-5
-    s = torch.randn(2, 1280, 16, 16, device="cuda").bfloat16()
-    t = torch.randn(2, 1280, 16, 16, device="cuda").bfloat16()
-    ds = k.feature_loss(s, t, sums, 9, 0.1)
-    sr = s.float().requires_grad_(True)
-    lb = F.mse_loss(sr, t.float()) / 9
-    (0.1 * lb).backward()
-    assert abs(sums[2].item() - lb.item()) / lb.item() < 1e-4
-    assert rel_err(ds, sr.grad) < 1e-2
+    for d, s in zip(dfs, srs):
+        assert d.shape == s.shape and rel_err(d, s.grad) < 1e-2           # bf16 gradient maps
+    # deterministic: identical bits on every run
+    for _ in range(3):
+        s2, d2, f2 = k.kd_loss_fused(pred, tgt, tea, fs, ft, 1.0, 2.0, 0.1, snr_w=w)
+        assert torch.equal(s2, sums) and torch.equal(d2, dpred) and all(torch.equal(a, b) for a, b in zip(f2, dfs))
+    # min-SNR weights computed inside the kernel == the reference expression (trainer.py:2457-2466, +1 before the min)
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, device="cuda") ** 2
+    acp = torch.cumprod(1 - betas, 0)
+    t = torch.tensor([0, 10, 500, 999], device="cuda")
+    snr = (acp[t].sqrt() / (1 - acp[t]).sqrt()) ** 2 + 1
+    w_ref = torch.stack([snr, 5.0 * torch.ones_like(snr)], 1).min(1)[0] / snr
+    s3, d3, _ = k.kd_loss_fused(pred, tgt, None, [], [], 1.0, 0.0, 0.0, alphas_cumprod=acp, timesteps=t, snr_gamma=5.0)
+    ref = (((pred - tgt) ** 2).mean(1) * w_ref).mean().item()
+    assert abs(s3[0].item() - ref) / ref < 1e-5 and abs(s3[3].item() - ref) / ref < 1e-5 and s3[1].item() == 0.0
+    # upper-step form (trainer.py:2996-2998): only the KD term
+    s4, d4, _ = k.kd_loss_fused(pred, None, tea, [], [], 0.0, 1.0, 0.0)
+    assert abs(s4[3].item() - l_k.item()) / l_k.item() < 1e-5
+    assert rel_err(d4, 2 * (pred - tea) / pred.numel()) < 1e-5
 
 
 def test_adamw_matches_torch():

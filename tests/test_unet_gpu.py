@@ -134,14 +134,16 @@ def test_training_step_matches_oracle(gold):
     vals = [loss.item(), diff.item(), kd.item(), blk.item()]
     r32 = [v.item() for v in ref32]
     print("b200", vals, "oracle fp32", r32)
+    print("rel vs fp32", [abs(a - b) / abs(b) for a, b in zip(vals, r32)])
     for a, b in zip(vals, r32):
-        assert abs(a - b) / abs(b) < 1e-2       # bf16 pipeline vs fp32 oracle
+        assert abs(a - b) / abs(b) < 2e-3       # bf16 pipeline vs fp32 oracle: 2x the measured worst term (8.6e-4)
     orc_bf = copy.deepcopy(orc)
     rbf = [v.item() for v in _oracle_step(orc_bf, teacher_o, batch, autocast=True)]
     print("oracle bf16-autocast", rbf)
     # two independent bf16 pipelines agree with each other about as well as each agrees with fp32
+    print("rel vs bf16", [abs(a - b) / abs(b) for a, b in zip(vals, rbf)])
     for a, b in zip(vals, rbf):
-        assert abs(a - b) / abs(b) < 1e-2
+        assert abs(a - b) / abs(b) < 3e-3       # (torch's bf16 evaluation is itself ~1e-3 away from fp32 at this size)
     # gradients
     loss.backward()
     ref32[0].backward()
@@ -151,12 +153,12 @@ def test_training_step_matches_oracle(gold):
     for k, p in orc.named_parameters():
         g_ref = p.grad.float()
         g_mine = params[k].grad.float()
-        cos = F.cosine_similarity(g_ref.flatten(), g_mine.flatten(), dim=0).item()
         if g_ref.abs().max() > 1e-8:
-            worst = max(worst, 1 - cos)
-            assert cos > 0.98, (k, cos)
+            err = ((g_mine.double() - g_ref.double()).norm() / g_ref.double().norm()).item()
+            worst = max(worst, err)
+            assert err < 8e-2, (k, err)          # relative L2 error per parameter (bf16 pipeline vs fp32 autograd)
             n_checked += 1
-    print("checked", n_checked, "params; worst 1-cos", worst)
+    print("checked", n_checked, "params; worst relative L2 gradient error", worst)
     # AdamW: one fused step vs torch.optim.AdamW on the oracle fed with OUR gradients (isolates the optimiser)
     ref_params = [p for _, p in orc.named_parameters()]
     for k, p in orc.named_parameters():
@@ -218,14 +220,17 @@ def test_bilevel_upper_step_matches_oracle(gold):
     ref = P.upper_step(orc, teacher_o, D.DDIMSchedulerLite(), batch["latents"], batch["noise"], batch["timesteps"],
                        batch["prompt_embeds"], batch["empty_prompt_embeds"])
     print("upper loss", loss.item(), "oracle", ref.item())
-    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-2
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 5e-3
     loss.backward()
     ref.backward()
     params = dict(mine.named_parameters())
+    worst = 0.0
     for k, p in orc.named_parameters():
         if p.grad.abs().max() > 1e-8:
-            cos = F.cosine_similarity(p.grad.flatten().float(), params[k].grad.flatten().float(), dim=0).item()
-            assert cos > 0.98, (k, cos)
+            err = ((params[k].grad.double() - p.grad.double()).norm() / p.grad.double().norm()).item()
+            worst = max(worst, err)
+            assert err < 8e-2, (k, err)
+    print("worst relative L2 gradient error", worst)
     mine.arena.grad.zero_()
     # schedule: lower steps every call, upper step on every 2nd call, separate optimiser states
     p0 = mine.arena.master.detach().clone()
@@ -399,7 +404,9 @@ def test_step_losses_match_reference_trainer_golden():
                      prompt_embeds=g["prompt_embeds"].cuda(), empty_prompt_embeds=g["empty_prompt_embeds"].cuda())
         vals = [float(v.detach()) for v in tuner.step(batch)]
         print("b200", vals, "reference trainer", case["step"])
+        print("rel", [abs(a - b) / abs(b) for a, b in zip(vals, case["step"])])
         for a, b in zip(vals, case["step"]):
-            assert abs(a - b) <= 2e-2 * abs(b), (vals, case["step"])
+            assert abs(a - b) <= 2e-3 * abs(b), (vals, case["step"])     # 2x the measured worst term (8.6e-4)
         up, _ = tuner.upper_step(batch)
-        assert abs(float(up.detach()) - case["upper_step"][0]) <= 2e-2 * case["upper_step"][0], (float(up), case["upper_step"])
+        print("upper rel", abs(float(up.detach()) - case["upper_step"][0]) / case["upper_step"][0])
+        assert abs(float(up.detach()) - case["upper_step"][0]) <= 5e-3 * case["upper_step"][0], (float(up), case["upper_step"])

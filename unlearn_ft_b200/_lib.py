@@ -41,6 +41,12 @@ class GemmDesc(C.Structure):
     ]
 
 
+class FeaturePair(C.Structure):
+    """Mirror of ``b200pdm_feature_pair``."""
+
+    _fields_ = [("s", c_p), ("t", c_p), ("ds", c_p), ("numel", i64)]
+
+
 OP_K2D, OP_MN2D, OP_CONV_ACT, OP_CONV_W, OP_CONV_WT, OP_CONV_ACT_MN = range(6)
 
 # name -> argtypes (restype is int unless listed in _RESTYPES)
@@ -82,15 +88,17 @@ _SIGS = {
     "b200pdm_nchw_f32_to_nhwc_bf16": [c_p, c_p, i64, i32, i32, i32, c_p],
     "b200pdm_nhwc_bf16_to_nchw_f32": [c_p, i64, c_p, i32, i32, i32, c_p],
     "b200pdm_timestep_embedding": [c_p, c_p, i64, i32, i32, c_p],
-    "b200pdm_pred_loss": [c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, f32, f32, c_p],
-    "b200pdm_feature_loss": [c_p, c_p, c_p, c_p, i64, f32, f32, c_p],
+    "b200pdm_kd_loss_workspace": [i32],
+    "b200pdm_kd_loss_fused": [c_p, c_p, c_p, c_p, c_p, c_p, f32, i32, c_p, i32, i64, f32, f32, C.POINTER(FeaturePair), i32,
+                              f32, c_p, c_p, C.c_size_t, c_p],
     "b200pdm_adamw_step": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i64, f32, i32, c_p],
     "b200pdm_cfg_ddim_step": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, i32, i32, f32, c_p],
     "b200pdm_adamw_step_dyn": [c_p, c_p, c_p, c_p, c_p, i64, c_p, f32, f32, f32, f32, f32, i32, c_p],
     "b200pdm_refresh_shadow": [c_p, c_p, i64, c_p],
     "b200pdm_diffusion_prep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, c_p],
 }
-_RESTYPES = {"b200pdm_last_error": C.c_char_p, "b200pdm_launch_count": C.c_uint64}
+_RESTYPES = {"b200pdm_last_error": C.c_char_p, "b200pdm_launch_count": C.c_uint64,
+             "b200pdm_kd_loss_workspace": C.c_size_t}
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -424,12 +424,21 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return r;
 }
 
-// sigmoid through ONE special-function op: s(x) = 0.5 + 0.5 tanh(x / 2)  (tanh.approx.f32: 2^-11 relative error; the
-// exp + reciprocal form costs two MUFU ops per element, and the GroupNorm(+SiLU) passes are MUFU-sensitive).
+// sigmoid = 1 / (1 + 2^(-x log2 e)): ex2.approx (2^-22) + rcp.approx (1 ulp).  Round 1 used the single-MUFU form
+// 0.5 + 0.5 tanh.approx(x / 2); tanh.approx.f32 is only good to 2^-11 and its error is not zero-mean: after the 61
+// GroupNorm+SiLU layers of a U-Net the network output carried a systematic gain of +8e-4, i.e. +2.7e-3 on the output-KD
+// loss term (tools/diag_parity.py, profiles/r2_parity_diag_*).  The GroupNorm passes are HBM/latency-bound; the second
+// MUFU op is free there.
 __device__ __forceinline__ float sigmoid_f(float x) {
+#ifdef B200PDM_TANH_SIGMOID
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return fmaf(0.5f, t, 0.5f);
+#else
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  return __fdividef(1.f, 1.f + e);
+#endif
 }
 __device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float silu_grad_f(float x) {

@@ -362,20 +362,28 @@ def timestep_embedding(t, dim):
 
 
 # ------------------------------------------------------------------------------------------------ loss / optimiser
-def pred_loss(pred, target, teacher, snr_w, sums, w_diff, w_kd, want_grad=True):
+def kd_loss_fused(pred, target, teacher, feats_s, feats_t, w_diff, w_kd, w_block, snr_w=None, alphas_cumprod=None,
+                  timesteps=None, snr_gamma=5.0, v_prediction=True, want_grad=True):
+    """The whole loss of trainer.py:2451-2486 in ONE launch (see include/b200pdm.h).  pred/target/teacher fp32 [B, ...]
+    contiguous; feats_*: lists of dense bf16 maps.  Returns (sums fp32[4] = diff, kd, block, total; dpred; [ds_k])."""
     B = pred.shape[0]
     n = pred.numel() // B
+    n_pairs = len(feats_s)
     dpred = torch.empty_like(pred) if want_grad else None
-    check(_lib.lib().b200pdm_pred_loss(pred.data_ptr(), _ptr(target), _ptr(teacher), _ptr(snr_w), _ptr(dpred),
-                                       sums.data_ptr(), B, n, w_diff, w_kd, _stream()), "pred_loss")
-    return dpred
-
-
-def feature_loss(s, t, sums, n_maps, w_block, want_grad=True):
-    ds = torch.empty_like(s) if want_grad else None
-    check(_lib.lib().b200pdm_feature_loss(s.data_ptr(), t.data_ptr(), _ptr(ds), sums.data_ptr(), s.numel(),
-                                          1.0 / n_maps, w_block, _stream()), "feature_loss")
-    return ds
+    dfeats = [torch.empty_like(s) for s in feats_s] if want_grad else [None] * n_pairs
+    pairs = (_lib.FeaturePair * max(n_pairs, 1))()
+    for i, (s, t) in enumerate(zip(feats_s, feats_t)):
+        if s.dtype != BF16 or t.dtype != BF16 or s.shape != t.shape or s.stride() != t.stride():
+            raise ValueError("kd_loss_fused: feature pairs must be bf16 maps of identical shape and layout")
+        pairs[i].s, pairs[i].t, pairs[i].ds, pairs[i].numel = s.data_ptr(), t.data_ptr(), _ptr(dfeats[i]), s.numel()
+    ws_bytes = _lib.lib().b200pdm_kd_loss_workspace(n_pairs)
+    ws = torch.empty(ws_bytes // 4, device=pred.device, dtype=F32)
+    sums = torch.empty(4, device=pred.device, dtype=F32)
+    check(_lib.lib().b200pdm_kd_loss_fused(pred.data_ptr(), _ptr(target), _ptr(teacher), _ptr(snr_w), _ptr(alphas_cumprod),
+                                           _ptr(timesteps), float(snr_gamma if snr_gamma is not None else 0.0),
+                                           int(v_prediction), _ptr(dpred), B, n, w_diff, w_kd, pairs, n_pairs, w_block,
+                                           sums.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "kd_loss_fused")
+    return sums, dpred, dfeats
 
 
 def adamw_step(p, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, zero_grad=True):

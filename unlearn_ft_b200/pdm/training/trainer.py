@@ -76,22 +76,22 @@ def _dense_cl(t):
 
 class _FusedKDLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, target, teacher_pred, snr_w, w_diff, w_kd, w_block, n_maps, *feats):
+    def forward(ctx, pred, target, teacher_pred, snr, w_diff, w_kd, w_block, n_maps, *feats):
         need = any(ctx.needs_input_grad)
-        sums = torch.zeros(4, device=pred.device, dtype=F32)
-        pred_c = pred.contiguous()
-        dpred = K.pred_loss(pred_c, None if target is None else target.contiguous().float(),
-                            None if teacher_pred is None else teacher_pred.contiguous().float(), snr_w, sums,
-                            w_diff, w_kd, want_grad=need)
-        fs, ft = feats[:n_maps], feats[n_maps:]
-        dfeats = []
-        for s, t in zip(fs, ft):
-            s_c, t_c = _dense_cl(s), _dense_cl(t)
-            ds = K.feature_loss(s_c, t_c, sums, n_maps, w_block, want_grad=need)
-            dfeats.append(ds)
+        fs = [_dense_cl(s) for s in feats[:n_maps]]
+        ft = [_dense_cl(t) for t in feats[n_maps:]]
+        kw = {}
+        if torch.is_tensor(snr):
+            kw["snr_w"] = snr.float().contiguous()
+        elif snr is not None:                     # (alphas_cumprod, timesteps, gamma, v_prediction): weights made in-kernel
+            kw = dict(alphas_cumprod=snr[0], timesteps=snr[1].to(torch.int64).contiguous(), snr_gamma=snr[2],
+                      v_prediction=snr[3])
+        sums, dpred, dfeats = K.kd_loss_fused(pred.contiguous(), None if target is None else target.contiguous().float(),
+                                              None if teacher_pred is None else teacher_pred.contiguous().float(),
+                                              fs, ft, w_diff, w_kd, w_block, want_grad=need, **kw)
         ctx.saved = (dpred, dfeats)
-        # sums = [diff, kd, block, w_diff*diff + w_kd*kd + w_block*block], all accumulated by the kernels
-        return sums[3].clone(), sums[0].clone(), sums[1].clone(), sums[2].clone()
+        # sums = [diff, kd, block, w_diff*diff + w_block*block + w_kd*kd]
+        return sums[3], sums[0], sums[1], sums[2]
 
     @staticmethod
     def backward(ctx, g_total, g_diff, g_kd, g_block):
@@ -104,16 +104,18 @@ class _FusedKDLoss(torch.autograd.Function):
 
 def fused_kd_loss(pred, target, teacher_pred, snr_weights, feats_s: Optional[Dict[str, torch.Tensor]],
                   feats_t: Optional[Dict[str, torch.Tensor]], w_diff=1.0, w_kd=2.0, w_block=0.1):
-    """(loss, diff_loss, distillation_loss, block_loss) of trainer.py:2451-2488.
+    """(loss, diff_loss, distillation_loss, block_loss) of trainer.py:2451-2488, one kernel launch, deterministic.
 
     pred/target/teacher_pred: fp32 [B, 4, H, W] (the reference's explicit .float() casts, :2452,2468,2485);
+    snr_weights: fp32 [B] tensor, None, or the tuple (alphas_cumprod, timesteps, snr_gamma, v_prediction) to have the
+    min-SNR weights of :2457-2466 computed inside the kernel;
     feats_*: hook dictionaries (bf16 block outputs; the reference does NOT upcast them, :2478).
     `loss.backward()` must be called with the default unit gradient (it is the root of the graph)."""
     keys = list(feats_s.keys()) if (feats_s and w_block > 0) else []
     fs = [feats_s[k] for k in keys]
     ft = [feats_t[k].detach() for k in keys]
     return _FusedKDLoss.apply(pred, target, teacher_pred, snr_weights, float(w_diff), float(w_kd),
-                              float(w_block) if keys else 0.0, max(len(keys), 1) if keys else 0, *fs, *ft)
+                              float(w_block) if keys else 0.0, len(keys), *fs, *ft)
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -193,15 +195,42 @@ class FusedAdamW(torch.optim.Optimizer):
         return None
 
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        """torch.optim.Optimizer layout (what accelerate's `save_state` pickles into optimizer.bin, trainer.py:311-327):
+        {"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [{..., "params": [i...]}]} with one entry per
+        parameter in `model.parameters()` order and the parameter's own shape -- so a checkpoint written here loads into
+        `torch.optim.AdamW(student.parameters())` of the reference and vice versa."""
+        a = self.arena
+        state = {}
+        for i, (mod, mod_name, attr, shape, kind, o, n) in enumerate(a.entries):
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": a._view(self.exp_avg, shape, kind, o).detach().clone(),
+                        "exp_avg_sq": a._view(self.exp_avg_sq, shape, kind, o).detach().clone()}
+        groups = [dict({k: v for k, v in g.items() if k != "params"}, params=list(range(len(a.entries))))
+                  for g in self.param_groups]
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        a = self.arena
+        if "state" not in sd:                      # flat layout written by round-1 checkpoints
+            self.step_count = int(sd["step"])
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        else:
+            if len(sd["state"]) not in (0, len(a.entries)):
+                raise ValueError(f"optimizer state has {len(sd['state'])} entries, the model has {len(a.entries)} parameters")
+            steps = set()
+            for i, (mod, mod_name, attr, shape, kind, o, n) in enumerate(a.entries):
+                st = sd["state"].get(i)
+                if st is None:
+                    continue
+                a._view(self.exp_avg, shape, kind, o).copy_(st["exp_avg"])
+                a._view(self.exp_avg_sq, shape, kind, o).copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+            if len(steps) > 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the flat AdamW keeps one")
+            self.step_count = steps.pop() if steps else 0
         for g, s in zip(self.param_groups, sd["param_groups"]):
-            g.update(s)
+            g.update({k: v for k, v in s.items() if k != "params"})
 
 
 class ConstantWithWarmup:
@@ -422,7 +451,9 @@ class UnetFineTuner:
         model_pred = self.student(noisy, timesteps, ehs).sample
         if ts is not None:
             torch.cuda.current_stream().wait_stream(ts)
-        w = self.snr_weights(timesteps) if self.snr_gamma is not None else None
+        # min-SNR weights (trainer.py:2457-2466) are evaluated inside the loss kernel; `snr_weights()` is the torch form
+        w = ((self.noise_scheduler.alphas_cumprod, timesteps, float(self.snr_gamma),
+              self.noise_scheduler.config.prediction_type == "v_prediction") if self.snr_gamma is not None else None)
         return fused_kd_loss(model_pred, target, teacher_pred if self.w_kd > 0 else None, w, self.block_act_student,
                              self.block_act_teacher, self.w_diff, self.w_kd, self.w_block)
 
@@ -465,18 +496,39 @@ class UnetFineTuner:
         `<dir>/<subfolder>/{config.json, diffusion_pytorch_model.safetensors}`, `<dir>/arch_vector.pt`, optimizer + scheduler
         state (`optimizer.bin` / `scheduler.bin`, the accelerate file names)."""
         self.student.save_pretrained(os.path.join(output_dir, subfolder))
-        torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.optimizer.state_dict().items()},
-                   os.path.join(output_dir, "optimizer.bin"))
-        torch.save({"t": self.lr_scheduler.t, "global_step": self.global_step}, os.path.join(output_dir, "scheduler.bin"))
+        self._save_optim(output_dir, self.optimizer, self.lr_scheduler, "")
+
+    @staticmethod
+    def _cpu(obj):
+        if torch.is_tensor(obj):
+            return obj.cpu()
+        if isinstance(obj, dict):
+            return {k: UnetFineTuner._cpu(v) for k, v in obj.items()}
+        if isinstance(obj, list):
+            return [UnetFineTuner._cpu(v) for v in obj]
+        return obj
+
+    def _save_optim(self, output_dir, optimizer, scheduler, suffix):
+        """accelerate's file names: optimizer.bin / scheduler.bin for the first prepared pair, optimizer_1.bin /
+        scheduler_1.bin for the second (bilevel: trainer.py:2720-2724)."""
+        torch.save(self._cpu(optimizer.state_dict()), os.path.join(output_dir, f"optimizer{suffix}.bin"))
+        torch.save({"t": scheduler.t, "last_epoch": scheduler.t, "global_step": self.global_step},
+                   os.path.join(output_dir, f"scheduler{suffix}.bin"))
+
+    def _load_optim(self, input_dir, optimizer, scheduler, suffix):
+        optimizer.load_state_dict(torch.load(os.path.join(input_dir, f"optimizer{suffix}.bin"), map_location=self.device,
+                                             weights_only=False))
+        st = torch.load(os.path.join(input_dir, f"scheduler{suffix}.bin"), weights_only=False)
+        scheduler.t = int(st.get("t", st.get("last_epoch", 0)))
+        scheduler._apply()
+        return st
 
     def load_checkpoint(self, input_dir, subfolder="unet"):
         """Counterpart of the reference's load hook (trainer.py:329-346): pruned weights by key, then optimizer / scheduler."""
         from safetensors.torch import load_file
         self.student.load_state_dict(load_file(os.path.join(input_dir, subfolder, "diffusion_pytorch_model.safetensors")))
-        self.optimizer.load_state_dict(torch.load(os.path.join(input_dir, "optimizer.bin"), map_location=self.device))
-        st = torch.load(os.path.join(input_dir, "scheduler.bin"))
-        self.lr_scheduler.t, self.global_step = int(st["t"]), int(st["global_step"])
-        self.lr_scheduler._apply()
+        st = self._load_optim(input_dir, self.optimizer, self.lr_scheduler, "")
+        self.global_step = int(st.get("global_step", self.lr_scheduler.t))
 
     # ------------------------------------------------------------------------------------------------ CUDA graph
     def _graph_body(self):
@@ -533,6 +585,7 @@ class UnetFineTuner:
             buf.copy_(src, non_blocking=True)
 
     def _replay(self, batch):
+        self.student.arena.ensure_shadow()      # eager refresh if the masters were written since (load_checkpoint, ...)
         self._load_static(self._static_in, batch)
         self.optimizer.step_count += 1
         self._dyn.copy_(torch.tensor(self.optimizer.dyn_scalars(self.optimizer.step_count), dtype=torch.float32))
@@ -546,14 +599,28 @@ class BilevelUnetFineTuner(UnetFineTuner):
     """Reference `BilevelUnetFineTuner` (trainer.py:2577-3001): every `upper_step_freq` steps an ESD-style
     concept-suppression step with its own AdamW state and learning rate on the SAME parameters."""
 
-    def __init__(self, student, teacher, upper_lr=5e-6, upper_step_freq=10, upper_warmup_steps=0, **kw):
+    def __init__(self, student, teacher, upper_lr=5e-6, upper_step_freq=10, upper_warmup_steps=None, **kw):
         super().__init__(student, teacher, **kw)
+        if upper_warmup_steps is None:
+            # reference init_upper_lr_scheduler (trainer.py:2666-2673): `upper_lr_warmup_steps` falls back to
+            # `lr_warmup_steps` when absent -- and the shipped bilevel YAML has no upper value, so the upper optimizer warms
+            # up over the same 250 (upper) steps, with lr 0 on the first one
+            upper_warmup_steps = kw.get("warmup_steps", 250)
         self.upper_optimizer = FusedAdamW(student, lr=upper_lr, betas=kw.get("betas", (0.9, 0.999)),
                                           eps=kw.get("eps", 1e-8), weight_decay=kw.get("weight_decay", 0.0))
         self.upper_lr_scheduler = ConstantWithWarmup(self.upper_optimizer, upper_warmup_steps)
         self.upper_step_freq = upper_step_freq
         self._upper_graph = None
         self.last_upper = None
+
+    def save_checkpoint(self, output_dir, subfolder="unet"):
+        """Both prepared optimizer / scheduler pairs, as the reference saves them (trainer.py:2720-2724)."""
+        super().save_checkpoint(output_dir, subfolder)
+        self._save_optim(output_dir, self.upper_optimizer, self.upper_lr_scheduler, "_1")
+
+    def load_checkpoint(self, input_dir, subfolder="unet"):
+        super().load_checkpoint(input_dir, subfolder)
+        self._load_optim(input_dir, self.upper_optimizer, self.upper_lr_scheduler, "_1")
 
     def upper_step(self, batch):
         """trainer.py:2904-3001 with the shipped weights (diffusion 0 / distillation 1 / block 0):
@@ -579,6 +646,7 @@ class BilevelUnetFineTuner(UnetFineTuner):
     def _run_upper(self, upper_batch):
         """trainer.py:2795-2816: upper loss -> backward -> (all-reduce) -> upper optimizer -> its scheduler."""
         if self._upper_graph is not None:
+            self.student.arena.ensure_shadow()
             self._load_static(self._upper_static_in, upper_batch)
             self.upper_optimizer.step_count += 1
             self._upper_dyn.copy_(torch.tensor(self.upper_optimizer.dyn_scalars(self.upper_optimizer.step_count),
