@@ -10,7 +10,10 @@
  * Conventions:
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless noted; no torch types;
  *   - every call enqueues on `stream` and returns immediately: 0 on success, a negative B200PDM_ERR_* otherwise;
- *     nothing here allocates device memory, synchronises the device, or throws;
+ *     nothing here allocates device memory, synchronises the device, or throws.  Calls that need scratch take a
+ *     caller-owned `workspace` of at least b200pdm_<op>_workspace(...) bytes (32-byte aligned; contents irrelevant on entry;
+ *     it must stay alive until the call's work has run -- allocate it from the stream-ordered / graph-pool allocator).
+ *     A NULL workspace is legal for the GEMM-class calls: the planner then restricts itself to plans without scratch;
  *   - activations are bf16, channels-last ("NHWC"): a [B,C,H,W] tensor is a row-major [B*H*W, ld] matrix whose
  *     first C columns are valid, ld % 8 == 0 (16-byte rows; TMA requirement);
  *   - weights used as tensor-core operands are bf16 "shadow" copies of the fp32 masters, kept in the layout
@@ -40,10 +43,6 @@ int b200pdm_version(void);
 const char* b200pdm_last_error(void);
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
 uint64_t b200pdm_launch_count(void);
-/* Library-owned scratch (split-K partial sums) exists once per lane, 0 <= lane < 4.  A host thread that enqueues work
- * on a second stream which may run concurrently with lane 0's (the trainer does this for the frozen teacher's forward,
- * pdm/training/trainer.py) selects another lane for those calls and switches back afterwards.  Default lane 0. */
-int b200pdm_set_lane(int lane);
 /* Host-only: the tile plan b200pdm_gemm would pick (no device work; usable without a GPU).  n = N per group, tiles_m =
  * ceil(M / 128), kblocks = number of 64-wide K blocks; can_split: the output may be split along K (fp32 accumulate, or a
  * scratch + finalize pass when split_needs_finalize).  out[7] = {block_n, splits, pair, m_sub, stages, tiles, slots}. */
@@ -91,29 +90,34 @@ typedef struct {
   const void* residual;     /* bf16 [M, N] pitch ldr (+ rbs1/rbs2 batch strides) or NULL                  */
   int64_t ldr, rbs1, rbs2;
   float alpha;              /* out = alpha*acc + bias + rowbias + residual                                */
-  int accumulate;           /* fp32 out only: out += ... (atomic adds; required when splits > 1)          */
-  int splits;               /* split-K factor, 0/1 = none                                                  */
+  int accumulate;           /* fp32 out only: out += ... (vector atomic adds; split-K allowed)             */
+  int splits;               /* accumulate only: fixed split-K factor, 0/1 = planner's choice               */
   int block_n;              /* 0 = choose                                                                  */
 } b200pdm_gemm_desc;
 
 /* Diagnostics: with B200PDM_GEMM_TRACE=1 in the environment every GEMM launch is timed (serialising); this writes the
  * per-shape table (tab separated) to `path` (host string) and clears it. */
 int b200pdm_gemm_trace_dump(const char* path);
-/* Generic launch. */
-int b200pdm_gemm(const b200pdm_gemm_desc* desc, b200pdm_stream_t stream);
+/* Generic launch.  Non-accumulating outputs of small-M problems may be split along K: every split writes its partial tile
+ * into its own fp32 slab of `workspace`, a finalize kernel adds the slabs in split order (deterministic) and applies the
+ * epilogue.  b200pdm_gemm_workspace() = bytes that plan needs (0 when the planner does not split). */
+size_t b200pdm_gemm_workspace(const b200pdm_gemm_desc* desc);
+int b200pdm_gemm(const b200pdm_gemm_desc* desc, void* workspace, size_t ws_bytes, b200pdm_stream_t stream);
 
 /* out[M,N] = x[M,K] . w[N,K]^T + bias + residual.            Replaces F.linear at pdm/models/unet/blocks.py:49
  * (GEGLU proj), :244,:251-252,:283 (attention projections), diffusers Transformer2DModel.proj_in/proj_out
  * (called at blocks.py:1172,1221), FeedForward.net[2], TimestepEmbedding (unet_2d_conditional.py:1521) and
  * time_emb_proj (blocks.py:337,538).                                                                       */
+size_t b200pdm_linear_fwd_workspace(int64_t M, int64_t N, int64_t K, int out_fp32);
 int b200pdm_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
                        const void* residual, int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M,
-                       int64_t N, int64_t K, b200pdm_stream_t stream);
+                       int64_t N, int64_t K, void* workspace, size_t ws_bytes, b200pdm_stream_t stream);
 /* dx[M,K] = dy[M,N] . w[N,K] (+ residual[M,K]); autograd backward of the call sites above.                 */
+size_t b200pdm_linear_dgrad_workspace(int64_t M, int64_t N, int64_t K);
 int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual,
-                         int64_t ldr, void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K,
-                         b200pdm_stream_t stream);
-/* dw[N,K] += dy[M,N]^T . x[M,K]   (fp32 accumulate, split-K).                                              */
+                         int64_t ldr, void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, void* workspace,
+                         size_t ws_bytes, b200pdm_stream_t stream);
+/* dw[N,K] += dy[M,N]^T . x[M,K]   (fp32 accumulate into the gradient arena, split-K through vector atomics).  */
 int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
                          int64_t M, int64_t N, int64_t K, b200pdm_stream_t stream);
 
@@ -121,14 +125,16 @@ int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ld
  *   out[b,ho,wo,:Cout] = sum_tap x[b, ho*s+kh-1, wo*s+kw-1, :Cin] . w[:, tap, :Cin]^T + bias + rowbias[b] + residual
  * Replaces conv1/conv2/conv_shortcut at blocks.py:332,374,377,533,575,578 (rowbias = the time-embedding add of
  * blocks.py:339-341), conv_in/conv_out at unet_2d_conditional.py:1616,1723 and the Down/Upsample2D convs.   */
+size_t b200pdm_conv_fwd_workspace(int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride);
 int b200pdm_conv_fwd(const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias,
                      const float* rowbias, int64_t ld_rowbias, const void* residual, int64_t ldr, void* out,
                      int64_t ldo, int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride,
-                     b200pdm_stream_t stream);
+                     void* workspace, size_t ws_bytes, b200pdm_stream_t stream);
 /* dx[b,h,w,:Cin] = sum_tap dy[b, h+1-kh, w+1-kw, :Cout] . w[:, tap, :Cin] (+ residual)  (stride 1 only).    */
+size_t b200pdm_conv_dgrad_workspace(int batch, int h, int w_sp, int c_in, int c_out, int ksize);
 int b200pdm_conv_dgrad(const void* dy, int64_t lddy, const void* w, int64_t w_ild, const void* residual,
                        int64_t ldr, void* dx, int64_t lddx, int batch, int h, int w_sp, int c_in, int c_out,
-                       int ksize, b200pdm_stream_t stream);
+                       int ksize, void* workspace, size_t ws_bytes, b200pdm_stream_t stream);
 /* dw[Cout][tap][:Cin] += sum_pixels dy[p,:Cout]^T . x[shift_tap(p), :Cin]   (fp32 accumulate, split-K).      */
 int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t w_ild,
                        int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride,
@@ -161,12 +167,10 @@ int b200pdm_geglu_fwd(const void* proj, int64_t ldp, void* out, int64_t ldo, int
                       b200pdm_stream_t stream);
 int b200pdm_geglu_bwd(const void* dout, int64_t lddo, const void* proj, int64_t ldp, void* dproj, int64_t lddp,
                       int64_t rows, int F, b200pdm_stream_t stream);
-/* Row softmax of fp32 scores -> bf16 probabilities (unfused attention path, blocks.py:275-277).             */
+/* Row softmax of fp32 scores -> bf16 probabilities: p = softmax(scale * s) per row (used between two batched
+ * b200pdm_gemm calls where the fused head_dim-64 attention below does not apply).                           */
 int b200pdm_softmax_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols, float scale,
                         b200pdm_stream_t stream);
-/* ds = scale * p * (dp - sum(dp*p)) ; dp fp32 in, ds bf16 out.                                              */
-int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ldp, void* ds, int64_t ldds,
-                        int64_t rows, int cols, float scale, b200pdm_stream_t stream);
 /* Fused flash-style attention forward on tcgen05, head_dim 64, no mask (blocks.py:275-277 = SDPA): scores and
  * probabilities stay in TMEM / shared memory.  q: [B*Lq, >= H*64] pitch ldq (head h = columns [64h, 64h+64));
  * k, v: [B*Lk, ...] pitches ldk/ldv; out like q (pitch ldo); lse: fp32 [B, H, Lq] = log2-domain log-sum-exp of

@@ -143,3 +143,34 @@ def test_gemm_tile_planner_invariants():
     p = _lib.gemm_plan(1280, tiles_m=8, kblocks=180, can_split=True)
     assert p["splits"] > 1 and p["tiles"] >= 0.9 * p["slots"]
     assert _lib.lib().b200pdm_launch_count() == 0
+
+
+def test_two_phase_prune_api_matches_direct_construction():
+    """Reference two-phase API (unet_2d_conditional.py:1367-1415 set_structure, then the module loop calling prune() /
+    prune_module(), :2455-2461) run UNCHANGED on a full-width model == constructing at pruned width: same keys, same
+    shapes, same parameter count (values: tests/test_unet_gpu.py::test_two_phase_prune_values)."""
+    import torch
+
+    from unlearn_ft_b200.pdm.models import HyperStructure, UNet2DConditionModelPruned
+    from unlearn_ft_b200.pdm.models.unet.unet_2d_conditional import SD21_CONFIG, structure_from_config
+    torch.manual_seed(1)
+    av = HyperStructure.get_random_arch_vector(0.55, structure_from_config(SD21_CONFIG))
+    av[0, -3] = 0.1                                                  # one depth gate closed
+    direct = UNet2DConditionModelPruned(arch_vector=av, device="meta", seed=None)
+    model = UNet2DConditionModelPruned(arch_vector=None, device="meta", seed=None)
+    assert not model.is_pruned() and model.num_parameters() == 865_910_724
+    model.set_structure(HyperStructure.transform_arch_vector(av, model.get_structure()))
+    for name, m in model.named_modules():                            # the reference's loop, verbatim
+        if hasattr(m, "prune"):
+            m.prune()
+    for m in model.modules():
+        if hasattr(m, "prune_module"):
+            m.prune_module()
+    sa, sb = direct.state_dict(), model.state_dict()
+    assert set(sa) == set(sb) and all(sa[k].shape == sb[k].shape for k in sa)
+    assert model.is_pruned() and model.num_parameters() == direct.num_parameters()
+    assert torch.equal(model.arch_vector, direct.arch_vector)
+    import pytest
+    with pytest.raises(RuntimeError):
+        model.set_structure(av)
+        model.prune()                                                # pruning twice is an error, as in the reference

@@ -83,24 +83,6 @@ def test_geglu():
     assert rel_err(dp, pr.grad) < 1e-2
 
 
-def test_softmax_bwd():
-    k = _k()
-    rows, cols = 512, 1000
-    s = torch.randn(rows, 1000, device="cuda") * 3
-    p = torch.zeros(rows, 1000, device="cuda", dtype=torch.bfloat16)
-    k.softmax_fwd(s, p, rows, cols, 0.125)
-    sr = s.clone().requires_grad_(True)
-    pr = torch.softmax(sr * 0.125, -1)
-    assert rel_err(p, pr) < 1e-2
-    dp = torch.randn(rows, cols, device="cuda")
-    # use the bf16-rounded p as the reference's p so only the kernel arithmetic is compared
-    pb = p.float()
-    ref = 0.125 * pb * (dp - (dp * pb).sum(-1, keepdim=True))
-    ds = torch.zeros(rows, cols, device="cuda", dtype=torch.bfloat16)
-    k.softmax_bwd(dp, p, ds, rows, cols, 0.125)
-    assert rel_err(ds, ref) < 1e-2
-
-
 def test_colsum_add_copy():
     k = _k()
     x, y = rand2d(5000, 170, 0), rand2d(5000, 170, 1)

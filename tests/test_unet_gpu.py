@@ -410,3 +410,51 @@ def test_step_losses_match_reference_trainer_golden():
         up, _ = tuner.upper_step(batch)
         print("upper rel", abs(float(up.detach()) - case["upper_step"][0]) / case["upper_step"][0])
         assert abs(float(up.detach()) - case["upper_step"][0]) <= 5e-3 * case["upper_step"][0], (float(up), case["upper_step"])
+
+
+def test_two_phase_prune_values(gold):
+    """set_structure() + prune() on a full-width model holding the full weights == the directly constructed pruned model
+    (bit-exact index selection), and the pruned model runs."""
+    from oracle import pdm_restated as P
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModelPruned
+    av = gold["small64_r082_drop"]["arch_vector"]
+    direct, _ = build_pair(av, trainable=False)
+    full = full_state_dict(3)
+    model = UNet2DConditionModelPruned(small_cfg(), arch_vector=None, trainable=False, seed=None)
+    model.load_state_dict(full.state_dict())
+    model.set_structure(P.transform_arch_vector(av, model.get_structure()))
+    for name, m in model.named_modules():
+        if hasattr(m, "prune"):
+            m.prune()
+    sa, sb = direct.state_dict(), model.state_dict()
+    assert set(sa) == set(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    b = make_batch(seed=4)
+    with torch.no_grad():
+        y0 = direct(b["latents"], b["timesteps"], b["prompt_embeds"]).sample
+        y1 = model(b["latents"], b["timesteps"], b["prompt_embeds"]).sample
+    assert torch.equal(y0, y1)
+
+
+def test_step_draws_noise_and_timesteps_like_the_reference(gold):
+    """A batch without 'noise' / 'timesteps' (the reference's batch contract) gets them drawn inside step()
+    (trainer.py:2409,2421); with a seeded generator the draw -- and therefore the loss -- is reproducible and equals the
+    step fed with the same tensors explicitly."""
+    from unlearn_ft_b200.pdm.models import UNet2DConditionModel
+    from unlearn_ft_b200.pdm.training import UnetFineTuner
+    av = gold["small64_r055"]["arch_vector"]
+    mine, _ = build_pair(av, trainable=True)
+    teacher = UNet2DConditionModel(small_cfg(), seed=7)
+    tuner = UnetFineTuner(mine, teacher, lr=1e-5, warmup_steps=0)
+    b = make_batch(seed=5)
+    short = {k: b[k] for k in ("latents", "prompt_embeds")}
+    tuner.generator = torch.Generator(device="cuda").manual_seed(123)
+    with torch.no_grad():
+        l0 = [float(v) for v in tuner.step(short)]
+    g = torch.Generator(device="cuda").manual_seed(123)
+    noise = torch.randn(b["latents"].shape, device="cuda", generator=g)
+    t = torch.randint(0, 1000, (2,), device="cuda", generator=g).long()
+    with torch.no_grad():
+        l1 = [float(v) for v in tuner.step(dict(short, noise=noise, timesteps=t))]
+    assert l0 == l1

@@ -11,12 +11,13 @@ import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-_SO = _PKG / "libb200pdm.so"
+_SO = _PKG / os.environ.get("B200PDM_LIB", "libb200pdm.so")   # (libb200pdm_diag.so = `make -C csrc diag`, tools/diag_*.py only)
 
 c_p = C.c_void_p
 i64 = C.c_int64
 i32 = C.c_int
 f32 = C.c_float
+sz = C.c_size_t
 
 
 class Operand(C.Structure):
@@ -54,15 +55,19 @@ _SIGS = {
     "b200pdm_version": [],
     "b200pdm_last_error": [],
     "b200pdm_launch_count": [],
-    "b200pdm_set_lane": [i32],
     "b200pdm_gemm_plan": [i64, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int)],
     "b200pdm_gemm_trace_dump": [C.c_char_p],
-    "b200pdm_gemm": [C.POINTER(GemmDesc), c_p],
-    "b200pdm_linear_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i32, i64, i64, i64, c_p],
-    "b200pdm_linear_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i64, i64, i64, c_p],
+    "b200pdm_gemm_workspace": [C.POINTER(GemmDesc)],
+    "b200pdm_gemm": [C.POINTER(GemmDesc), c_p, sz, c_p],
+    "b200pdm_linear_fwd_workspace": [i64, i64, i64, i32],
+    "b200pdm_linear_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i32, i64, i64, i64, c_p, sz, c_p],
+    "b200pdm_linear_dgrad_workspace": [i64, i64, i64],
+    "b200pdm_linear_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i64, i64, i64, c_p, sz, c_p],
     "b200pdm_linear_wgrad": [c_p, i64, c_p, i64, c_p, i64, i64, i64, i64, c_p],
-    "b200pdm_conv_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p],
-    "b200pdm_conv_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, c_p],
+    "b200pdm_conv_fwd_workspace": [i32, i32, i32, i32, i32, i32, i32],
+    "b200pdm_conv_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p, sz, c_p],
+    "b200pdm_conv_dgrad_workspace": [i32, i32, i32, i32, i32, i32],
+    "b200pdm_conv_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, c_p, sz, c_p],
     "b200pdm_conv_wgrad": [c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p],
     "b200pdm_groupnorm_fwd": [c_p, i64, c_p, c_p, c_p, i64, c_p, i32, i32, i32, i32, f32, i32, c_p],
     "b200pdm_groupnorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, i64, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p],
@@ -71,7 +76,6 @@ _SIGS = {
     "b200pdm_geglu_fwd": [c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_geglu_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_softmax_fwd": [c_p, i64, c_p, i64, i64, i32, f32, c_p],
-    "b200pdm_softmax_bwd": [c_p, i64, c_p, i64, c_p, i64, i64, i32, f32, c_p],
     "b200pdm_attention_fwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i32, i32, i32, i32, f32, c_p],
     "b200pdm_attention_bwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, c_p,
                               i32, i32, i32, i32, f32, c_p],
@@ -97,8 +101,8 @@ _SIGS = {
     "b200pdm_refresh_shadow": [c_p, c_p, i64, c_p],
     "b200pdm_diffusion_prep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, c_p],
 }
-_RESTYPES = {"b200pdm_last_error": C.c_char_p, "b200pdm_launch_count": C.c_uint64,
-             "b200pdm_kd_loss_workspace": C.c_size_t}
+_RESTYPES = {"b200pdm_last_error": C.c_char_p, "b200pdm_launch_count": C.c_uint64}
+_RESTYPES.update({n: C.c_size_t for n in _SIGS if n.endswith("_workspace")})
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
@@ -153,23 +157,3 @@ def gemm_plan(n, n_groups=1, b_mn=False, tiles_m=1, Z=1, kblocks=1, can_split=Fa
 
 def launch_count() -> int:
     return int(lib().b200pdm_launch_count())
-
-
-class lane:
-    """`with lane(1): ...` -- library scratch lane for calls enqueued on a stream that may run next to another lane's work.
-    Nests: the previous lane is restored on exit."""
-
-    current = 0
-
-    def __init__(self, index: int):
-        self.index = index
-
-    def __enter__(self):
-        self.prev = lane.current
-        check(lib().b200pdm_set_lane(self.index))
-        lane.current = self.index
-
-    def __exit__(self, *exc):
-        lib().b200pdm_set_lane(self.prev)
-        lane.current = self.prev
-        return False

@@ -33,7 +33,6 @@ constexpr int kQ = 128, kKV = 128, kD = 64;
 #endif
 constexpr int kExpFmaMask = B200PDM_EXP_FMA_MASK;
 constexpr int kTileBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B tile
-constexpr int kAttnThreads = 192;
 
 struct AttnFwdParams {
   int B, H, Lq, Lk, nkv;
@@ -41,213 +40,15 @@ struct AttnFwdParams {
   bf16* out;
   int64_t ldo;
   float* lse;  // [B, H, Lq] log2-domain log-sum-exp (may be null)
-  long long* dbg;  // optional phase timers of CTA 0 / warp 2 (diagnostics)
+#ifdef B200PDM_DIAG
+  long long* dbg;  // optional phase timers of CTA 0 / warp 2 (`make diag`)
+#else
+  static constexpr long long* dbg = nullptr;
+#endif
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
-  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTileBytes;
-  uint8_t* sV = smem + 3 * kTileBytes;
-  uint8_t* sP = smem + 5 * kTileBytes;  // two [128 x 64] sub-tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * kQ;
-
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023) {
-      printf("b200pdm attention: dynamic smem not 1024-byte aligned\n");
-      __trap();
-    }
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_k);
-    tma_prefetch_desc(&tm_v);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(pv_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_s = tmem;         // 128 columns
-  const uint32_t tmem_pv = tmem + 128;  // 64 columns
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kTileBytes);
-      tma_load_4d(sQ, &tm_q, q_full, 0, q0, h, b);
-      for (int j = 0; j < p.nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
-        tma_load_4d(sK + s * kTileBytes, &tm_k, &kv_full[s], 0, j * kKV, h, b);
-        tma_load_4d(sV + s * kTileBytes, &tm_v, &kv_full[s], 0, j * kKV, h, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(kKV, 0, 0);  // S: N = 128 keys, A/B K-major
-      const uint32_t idesc_o = make_idesc_bf16(kD, 0, 1);   // PV: N = 64, B (= V) MN-major
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < p.nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK + s * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_bf16(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                    make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP), v_addr = smem_u32(sV + s * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kKV / 16; ++k)
-          umma_bf16(tmem_pv, make_smem_desc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(v_addr + k * 2048, 8192, 1024), idesc_o, k > 0);
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[s]);
-      }
-    }
-  } else {
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;  // query row within the block == TMEM lane
-    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
-    float m = -INFINITY, l = 0.f;
-    float o[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) o[i] = 0.f;
-    const uint32_t p_row = smem_u32(sP) + r * 128;
-    const int sw = r & 7;
-    for (int j = 0; j < p.nkv; ++j) {
-      const int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // pass 1: row maximum (4 independent chains; masking only on the ragged last block)
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
-        tmem_ld_wait();
-        if (valid == kKV) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-        }
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      const float alpha = exp2f(m - m_new);
-      l *= alpha;
-      // pass 2: probabilities -> bf16 P tile (K-major, swizzle-128B)
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_base + c * 32, v);
-        tmem_ld_wait();
-        float pf[32];
-        if (valid == kKV) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pf[i] = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-            l4[i & 3] += pf[i];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-            e = (c * 32 + i < valid) ? e : 0.f;
-            pf[i] = e;
-            l4[i & 3] += e;
-          }
-        }
-        const uint32_t base = p_row + (c >> 1) * kTileBytes;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          __nv_bfloat162 a0 = __floats2bfloat162_rn(pf[g * 8 + 0], pf[g * 8 + 1]);
-          __nv_bfloat162 a1 = __floats2bfloat162_rn(pf[g * 8 + 2], pf[g * 8 + 3]);
-          __nv_bfloat162 a2 = __floats2bfloat162_rn(pf[g * 8 + 4], pf[g * 8 + 5]);
-          __nv_bfloat162 a3 = __floats2bfloat162_rn(pf[g * 8 + 6], pf[g * 8 + 7]);
-          const int chunk = ((c & 1) * 4 + g) ^ sw;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + chunk * 16),
-                       "r"(*reinterpret_cast<uint32_t*>(&a0)), "r"(*reinterpret_cast<uint32_t*>(&a1)),
-                       "r"(*reinterpret_cast<uint32_t*>(&a2)), "r"(*reinterpret_cast<uint32_t*>(&a3))
-                       : "memory");
-        }
-      }
-      l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      m = m_new;
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-#pragma unroll
-      for (int i = 0; i < kD; ++i) o[i] *= alpha;
-      mbar_wait(pv_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_pv + lane_base + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-    }
-    const int q = q0 + r;
-    if (q < p.Lq) {
-      const float inv = 1.f / l;
-      bf16* dst = p.out + (static_cast<int64_t>(b) * p.Lq + q) * p.ldo + h * kD;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        float t8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t8[i] = o[g * 8 + i] * inv;
-        *reinterpret_cast<bf16x8*>(dst + g * 8) = pack8(t8);
-      }
-      if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = m + log2f(l);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
-
 // ----------------------------------------------------------------------------------------------------------------
-// Forward, version 2: one CTA = one (sample, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor
+// Forward: one CTA = one (sample, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor
 // core; one CTA per SM.
 //   warp 0            : TMA producer  - both Q tiles once, then K/V blocks of 128 keys through a 3-stage smem ring
 //   warp 1            : MMA issuer    - per key block and query tile t:  O_t += P_t V (accumulating in TMEM), then
@@ -556,6 +357,7 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
   p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nkv = (lk + kKV - 1) / kKV;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(out), p.ldo = ldo, p.lse = lse;
+#ifdef B200PDM_DIAG
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) dbg_on = getenv("B200PDM_ATTN_DBG") ? 1 : 0;
@@ -564,34 +366,27 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
     cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
-  static int use_v1 = -1;
-  if (use_v1 < 0) use_v1 = getenv("B200PDM_ATTN_V1") ? 1 : 0;   // A/B measurement only
+#endif
   cudaError_t e;
-  if (use_v1) {
-    const size_t smem = 7 * kTileBytes + 256;
-    e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_err("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return B200PDM_ERR_CUDA;
-    }
-    dim3 grid((lq + kQ - 1) / kQ, heads, batch);
-    launch_pdl(attn_fwd_kernel, grid, kAttnThreads, smem, stream, mq, mk, mv, p);
-  } else {
-    const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256;
+  const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256;
+  static bool attr_set = false;   // once, not per launch (graph capture)
+  if (!attr_set) {
     e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_err("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return B200PDM_ERR_CUDA;
     }
-    dim3 grid((lq + 2 * kQ - 1) / (2 * kQ), heads, batch);
-    launch_pdl<true>(attn_fwd2_kernel, grid, kFwd2Threads, smem, stream, mq, mk, mv, p);
+    attr_set = true;
   }
+  dim3 grid((lq + 2 * kQ - 1) / (2 * kQ), heads, batch);
+  launch_pdl<true>(attn_fwd2_kernel, grid, kFwd2Threads, smem, stream, mq, mk, mv, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err("attention_fwd launch: %s", cudaGetErrorString(e));
     return B200PDM_ERR_CUDA;
   }
   g_launches++;
+#ifdef B200PDM_DIAG
   if (dbg_on) {
     long long hbuf[16];
     cudaStreamSynchronize(stream);
@@ -599,6 +394,7 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
     fprintf(stderr, "[attn dbg] Lq=%d Lk=%d nkv=%d | wg0: wait_s=%lld pass1=%lld wait_pv=%lld pass2=%lld | wg1: wait_s=%lld pass1=%lld "
             "wait_pv=%lld pass2=%lld\n", lq, lk, p.nkv, hbuf[0], hbuf[1], hbuf[2], hbuf[3], hbuf[8], hbuf[9], hbuf[10], hbuf[11]);
   }
+#endif
   return B200PDM_OK;
 }
 
@@ -617,7 +413,11 @@ struct AttnBwdParams {
   int B, H, Lq, Lk, nq;
   float scale, scale_log2;
   const float* lse;    // [B, H, Lq] (log2 domain)
-  long long* dbg;      // optional phase timers (diagnostics)
+#ifdef B200PDM_DIAG
+  long long* dbg;      // optional phase timers (`make diag`)
+#else
+  static constexpr long long* dbg = nullptr;
+#endif
   const float* delta;  // [B, H, Lq]
   float* dq_acc;       // fp32 [B*Lq, ld_dq], head h at columns [64h, 64h+64)
   int64_t ld_dq;
@@ -954,6 +754,7 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
   p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nq = (lq + kQ - 1) / kQ;
   p.scale = scale, p.scale_log2 = scale * 1.4426950408889634f;
   p.lse = lse, p.delta = delta, p.dq_acc = dq_acc, p.ld_dq = ld_acc;
+#ifdef B200PDM_DIAG
   static long long* bdbg = nullptr;
   static int bdbg_on = -1;
   if (bdbg_on < 0) bdbg_on = getenv("B200PDM_ATTN_DBG") ? 1 : 0;
@@ -962,15 +763,21 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
     cudaMemsetAsync(bdbg, 0, 16 * sizeof(long long), stream);
   }
   p.dbg = bdbg_on ? bdbg : nullptr;
+#endif
   p.dk = reinterpret_cast<bf16*>(dk), p.ld_dk = lddk, p.dv = reinterpret_cast<bf16*>(dv), p.ld_dv = lddv;
   CUtensorMap mdq;
   rc = make_map_f32_3d(&mdq, dq_acc, (uint64_t)ld_acc, (uint64_t)lq, (uint64_t)batch, (uint64_t)ld_acc, kQ);
   if (rc) return rc;
   const size_t smem = 12 * kTileBytes + 256;
-  cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_err("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    return B200PDM_ERR_CUDA;
+  cudaError_t e;
+  static bool attr_set = false;   // once, not per launch (graph capture)
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_err("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return B200PDM_ERR_CUDA;
+    }
+    attr_set = true;
   }
   dim3 grid((lk + kKV - 1) / kKV, heads, batch);
   launch_pdl<true>(attn_bwd_kernel, grid, kBwdThreads, smem, stream, mq, mk, mv, mdo, mdq, p);
@@ -987,7 +794,8 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
                                                             cols8);
   e = cudaGetLastError();
   if (e != cudaSuccess) return B200PDM_ERR_CUDA;
-  g_launches += 4;
+  g_launches += 3;
+#ifdef B200PDM_DIAG
   if (bdbg_on) {
     long long hbuf[16];
     cudaStreamSynchronize(stream);
@@ -995,5 +803,6 @@ extern "C" int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, 
     fprintf(stderr, "[attn bwd dbg] Lq=%d Lk=%d nq=%d | wait_s=%lld softmax=%lld wait_dq=%lld drain_dq=%lld\n", lq, lk, p.nq, hbuf[0],
             hbuf[1], hbuf[2], hbuf[3]);
   }
+#endif
   return B200PDM_OK;
 }

@@ -58,7 +58,7 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ d, int64_t ldd, const 
   }
 }
 
-// ---------------------------------------------------------------- softmax (unfused attention path)
+// ---------------------------------------------------------------- row softmax (frozen encoders: head dims other than 64)
 // one block per row; fp32 scores in, bf16 probabilities out. p = softmax(scale * s).
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf16* __restrict__ p, int64_t ldp, int cols,
                                    float scale) {
@@ -75,21 +75,6 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf1
   sum = block_sum(sum, red);
   const float inv = 1.f / sum;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) pr[c] = __float2bfloat16(__expf((sr[c] - mx) * scale) * inv);
-}
-// ds = scale * p * (dp - sum_j dp_j p_j)
-__global__ void softmax_bwd_kernel(const float* __restrict__ dp, int64_t lddp, const bf16* __restrict__ p, int64_t ldp,
-                                   bf16* __restrict__ ds, int64_t ldds, int cols, float scale) {
-  pdl_trigger();   // PDL: successors may start their prologue while this grid runs
-  __shared__ float red[32];
-  const int64_t row = blockIdx.x;
-  const float* dr = dp + row * lddp;
-  const bf16* pr = p + row * ldp;
-  bf16* sr = ds + row * ldds;
-  float dot = 0.f;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) dot += dr[c] * __bfloat162float(pr[c]);
-  dot = block_sum(dot, red);
-  for (int c = threadIdx.x; c < cols; c += blockDim.x)
-    sr[c] = __float2bfloat16(scale * __bfloat162float(pr[c]) * (dr[c] - dot));
 }
 
 // ---------------------------------------------------------------- column sums (bias gradients)
@@ -435,15 +420,6 @@ int b200pdm_softmax_fwd(const float* s, int64_t lds, void* p, int64_t ldp, int64
   if (rows <= 0) return B200PDM_OK;
   int threads = cols >= 1024 ? 256 : 128;
   launch_pdl(softmax_fwd_kernel, (unsigned)rows, threads, 0, STREAM, s, lds, BF(p), ldp, cols, scale);
-  B200_CHECK_LAUNCH();
-  g_launches++;
-  return B200PDM_OK;
-}
-int b200pdm_softmax_bwd(const float* dp, int64_t lddp, const void* p, int64_t ldp, void* ds, int64_t ldds, int64_t rows,
-                        int cols, float scale, b200pdm_stream_t stream) {
-  if (rows <= 0) return B200PDM_OK;
-  int threads = cols >= 1024 ? 256 : 128;
-  launch_pdl(softmax_bwd_kernel, (unsigned)rows, threads, 0, STREAM, dp, lddp, CBF(p), ldp, BF(ds), ldds, cols, scale);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

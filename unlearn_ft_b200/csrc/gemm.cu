@@ -159,6 +159,7 @@ struct GemmDev {
   int n_per_group;   // valid output cols per N-group
   int n_groups;      // 1, or taps for conv wgrad
   int64_t out_group_stride;
+  int64_t out_split_stride;   // elements between the per-split partial-sum slabs (deterministic split-K), else 0
   int tiles_m, tiles_n_per_group, Z, splits;
   int kblocks, kb_per_split;
   int k_taps;        // conv fprop/dgrad: K runs over (channel block, tap), taps innermost; else 1
@@ -181,8 +182,13 @@ struct GemmDev {
   int64_t ldr, rbs1, rbs2;
   float alpha;
   int accumulate;
-  long long* dbg;  // optional per-role wait-cycle counters (diagnostics)
-  int dbg_mode;    // diagnostics only (B200PDM_GEMM_DBGMODE): 1 = quarter of the MMAs, 2 = no A loads, 4 = no B loads
+#ifdef B200PDM_DIAG   // `make diag` -> libb200pdm_diag.so (tools/diag_gemm_*.py); the product library carries none of this
+  long long* dbg;  // optional per-role wait-cycle counters
+  int dbg_mode;    // B200PDM_GEMM_DBGMODE: 1 = quarter of the MMAs, 2 = no A loads, 4 = no B loads, 8/128 = epilogue cuts
+#else
+  static constexpr long long* dbg = nullptr;
+  static constexpr int dbg_mode = 0;
+#endif
   int epi_groups;  // epilogue warpgroups: group g takes every epi_groups-th 32-column chunk of a tile
 };
 
@@ -221,6 +227,12 @@ __device__ __forceinline__ void tap_offsets(int taps, int tap, int flip, int* kh
   *kh = h, *kw = w;
 }
 
+#ifndef B200PDM_DIAG
+#define DBG_WAIT(slot, stmt) \
+  do {                       \
+    stmt;                    \
+  } while (0)
+#else
 #define DBG_WAIT(slot, stmt)                                              \
   do {                                                                    \
     if (p.dbg && blockIdx.x == 0) {                                       \
@@ -233,6 +245,7 @@ __device__ __forceinline__ void tap_offsets(int taps, int tap, int flip, int* kh
       stmt;                                                               \
     }                                                                     \
   } while (0)
+#endif
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
@@ -572,7 +585,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       auto aligned_to = [&](int bytes) {   // every chunk start of every row is `bytes`-aligned
         return ((reinterpret_cast<uintptr_t>(p.out) % bytes) == 0) && ((p.ldo * out_el) % bytes == 0) &&
                ((p.obs1 * out_el) % bytes == 0) && ((p.obs2 * out_el) % bytes == 0) &&
-               ((p.out_group_stride * out_el) % bytes == 0) && ((p.block_n * out_el) % bytes == 0);
+               ((p.out_group_stride * out_el) % bytes == 0) && ((p.out_split_stride * out_el) % bytes == 0) &&
+               ((p.block_n * out_el) % bytes == 0);
       };
       const bool out_v32 = aligned_to(32), out_v16 = aligned_to(16);
       const bool res_v32 = p.residual && ((reinterpret_cast<uintptr_t>(p.residual) & 31) == 0) && (p.ldr % 16 == 0) &&
@@ -595,7 +609,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const int row = m_tile * kBlockM + q * 32 + lane;      // own row (TMEM lane)
           const bool row_ok = row < p.M;
           const int64_t out_off =
-              tc.z1 * p.obs1 + tc.z2 * p.obs2 + tc.grp * p.out_group_stride + static_cast<int64_t>(row) * p.ldo + col_base;
+              tc.z1 * p.obs1 + tc.z2 * p.obs2 + tc.grp * p.out_group_stride + tc.split * p.out_split_stride +
+              static_cast<int64_t>(row) * p.ldo + col_base;
           const bf16* res_row = (p.residual && row_ok)
                                     ? p.residual + tc.z1 * p.rbs1 + tc.z2 * p.rbs2 + static_cast<int64_t>(row) * p.ldr + col_base
                                     : nullptr;
@@ -944,35 +959,13 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
   return B200PDM_ERR_ARG;
 }
 
-// Library-owned fp32 scratch for split-K partial sums (lazily grown; the only device allocation the library makes).
-// One buffer per "lane" (b200pdm_set_lane): the trainer enqueues the frozen teacher's forward on a second stream next to the
-// student's, and two split-K GEMMs in flight at once must not share partial sums.  Lanes are a host-side notion (the
-// enqueueing thread switches lane together with the stream), so the same buffers are used eagerly and under stream
-// capture -- nothing is allocated while a graph is being captured, the eager warm-up steps have sized every lane.
-constexpr int kMaxLanes = 4;
-static int g_lane = 0;
-static float* scratch_f32(size_t elems, cudaStream_t stream) {
-  static float* buf[kMaxLanes] = {};
-  static size_t cap[kMaxLanes] = {};
-  const int l = g_lane;
-  if (elems > cap[l]) {
-    if (buf[l]) {
-      cudaStreamSynchronize(stream);
-      cudaFree(buf[l]);
-    }
-    size_t want = elems < (8u << 20) ? (8u << 20) : elems;
-    if (cudaMalloc(&buf[l], want * sizeof(float)) != cudaSuccess) {
-      buf[l] = nullptr, cap[l] = 0;
-      set_err("split-K scratch allocation failed");
-      return nullptr;
-    }
-    cap[l] = want;
-  }
-  if (cudaMemsetAsync(buf[l], 0, elems * sizeof(float), stream) != cudaSuccess) return nullptr;
-  return buf[l];
-}
-
-__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldws, void* __restrict__ out, int out_fp32,
+// Split-K of a NON-accumulating output (forward / dgrad GEMMs of the 8x8 / 16x16 levels, where one wave would leave most SMs
+// idle): split s writes its partial tile with plain stores into its own fp32 slab of the CALLER's workspace
+// (b200pdm_*_workspace() bytes), and one finalize pass adds the slabs in split order, applies bias / time-embedding /
+// residual and converts.  No atomics, no memset, nothing allocated here: bit-identical from run to run, and safe under
+// CUDA-graph capture and with any number of streams (round 1 kept a library-owned, lazily re-allocated scratch per "lane").
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldws, int splits, int64_t slab,
+                                       void* __restrict__ out, int out_fp32,
                                        int64_t ldo, const float* __restrict__ bias, const float* __restrict__ rowbias,
                                        int64_t ld_rowbias, int rows_per_group, const bf16* __restrict__ residual,
                                        int64_t ldr, int64_t M, int N) {
@@ -982,7 +975,11 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldw
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / nq;
     const int n0 = (int)(i - m * nq) * 4;
-    const float4 a = *reinterpret_cast<const float4*>(ws + m * ldws + n0);
+    float4 a = *reinterpret_cast<const float4*>(ws + m * ldws + n0);
+    for (int sp = 1; sp < splits; ++sp) {   // fixed order: deterministic
+      const float4 b = *reinterpret_cast<const float4*>(ws + sp * slab + m * ldws + n0);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    }
     float f[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1000,11 +997,12 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int64_t ldw
   }
 }
 
-static int launch_finalize(const b200pdm_gemm_desc* d, const float* ws, int64_t ldws, cudaStream_t stream) {
+static int launch_finalize(const b200pdm_gemm_desc* d, const float* ws, int64_t ldws, int splits, int64_t slab,
+                           cudaStream_t stream) {
   const int64_t total = d->M * ((d->N + 3) / 4);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl(splitk_finalize_kernel, (int)blocks, 256, 0, stream, ws, ldws, d->out, d->out_fp32, d->ldo, d->bias, d->rowbias,
+  launch_pdl(splitk_finalize_kernel, (int)blocks, 256, 0, stream, ws, ldws, splits, slab, d->out, d->out_fp32, d->ldo, d->bias, d->rowbias,
                                                          d->ld_rowbias, d->rows_per_group > 0 ? d->rows_per_group : 1,
                                                          reinterpret_cast<const bf16*>(d->residual), d->ldr, d->M,
                                                          (int)d->N);
@@ -1012,7 +1010,7 @@ static int launch_finalize(const b200pdm_gemm_desc* d, const float* ws, int64_t 
     set_err("split-K finalize launch failed");
     return B200PDM_ERR_CUDA;
   }
-  g_launches += 2;
+  g_launches++;
   return B200PDM_OK;
 }
 
@@ -1029,74 +1027,102 @@ static int trace_on() {
   return on;
 }
 
-static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream);
-static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
+// Shape of the tile problem a descriptor poses + the plan chosen for it (shared by the launch and the workspace query, so
+// both see the same split decision).
+struct Shaped {
+  bool a_mn, b_mn, acc_out;
+  int Z1, Z2, n_groups, n_per_group, tiles_m, Z, kblocks;
+  Plan plan;
+  int64_t ldws, slab;   // split-K slabs: row pitch / elements per slab (0 when the plan needs no workspace)
+};
+static int shape_and_plan(const b200pdm_gemm_desc* d, bool have_workspace, Shaped* s, bool slab_pass = false) {
+  s->a_mn = d->a.mode == B200PDM_OP_MN2D;
+  s->b_mn = d->b.mode == B200PDM_OP_MN2D || d->b.mode == B200PDM_OP_CONV_WT || d->b.mode == B200PDM_OP_CONV_ACT_MN;
+  s->Z1 = d->Z1 > 0 ? d->Z1 : 1, s->Z2 = d->Z2 > 0 ? d->Z2 : 1;
+  s->n_groups = 1, s->n_per_group = static_cast<int>(d->N);
+  if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {   // conv wgrad: one N group per tap
+    s->n_groups = d->b.taps > 0 ? d->b.taps : 1;
+    s->n_per_group = d->b.channels;
+  }
+  s->tiles_m = cdiv(d->M, kBlockM);
+  s->Z = s->Z1 * s->Z2;
+  if (d->a.mode == B200PDM_OP_CONV_ACT) {
+    const int taps = d->a.taps > 0 ? d->a.taps : 1;
+    s->kblocks = taps * cdiv(d->a.channels, 64);
+  } else if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {
+    s->kblocks = cdiv((int64_t)d->b.batch * d->b.h_out * d->b.w_out, 64);
+  } else {
+    s->kblocks = cdiv(d->K, 64);
+  }
+  if (s->kblocks <= 0 || d->M <= 0 || d->N <= 0) {
+    set_err("gemm: empty problem");
+    return B200PDM_ERR_ARG;
+  }
+  s->acc_out = d->out_fp32 && d->accumulate;
+  const bool slabs_ok = have_workspace && !s->acc_out && s->Z == 1 && s->n_groups == 1 &&
+                        (int64_t)d->M * d->N * 4 <= (64ll << 20);
+  if (d->splits > 1 && (s->acc_out || slab_pass))   // split factor fixed by the caller (accumulating outputs) / the slab pass
+    s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, false, false, d->block_n, d->splits);
+  else
+    s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, s->acc_out || slabs_ok,
+                        !s->acc_out, d->block_n);
+  if (s->plan.bn <= 0) {
+    set_err("gemm: no valid tile plan (bad block_n?)");
+    return B200PDM_ERR_ARG;
+  }
+  s->ldws = s->slab = 0;
+  if (s->plan.splits > 1 && !s->acc_out && !slab_pass) {
+    s->ldws = (d->N + 7) / 8 * 8;
+    s->slab = d->M * s->ldws;
+  }
+  return B200PDM_OK;
+}
+
+static size_t gemm_workspace_bytes(const b200pdm_gemm_desc* d) {
+  Shaped s;
+  if (!d || shape_and_plan(d, true, &s) != B200PDM_OK) return 0;
+  return (size_t)s.slab * s.plan.splits * sizeof(float);
+}
+
+static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                       int64_t split_stride = 0);
+static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                       int64_t split_stride) {
   if (!d || !d->a.ptr || !d->b.ptr || !d->out) {
     set_err("gemm: null pointer");
     return B200PDM_ERR_ARG;
   }
-  const bool a_mn = d->a.mode == B200PDM_OP_MN2D;
-  const bool b_mn = d->b.mode == B200PDM_OP_MN2D || d->b.mode == B200PDM_OP_CONV_WT ||
-                    d->b.mode == B200PDM_OP_CONV_ACT_MN;
-  const int Z1 = d->Z1 > 0 ? d->Z1 : 1, Z2 = d->Z2 > 0 ? d->Z2 : 1;
+  Shaped sh;
+  int rc0 = shape_and_plan(d, workspace != nullptr, &sh, split_stride != 0);
+  if (rc0) return rc0;
+  const bool a_mn = sh.a_mn, b_mn = sh.b_mn, acc_out = sh.acc_out;
+  const int Z1 = sh.Z1, Z2 = sh.Z2, kblocks = sh.kblocks;
+  const Plan plan = sh.plan;
 
   GemmDev p;
   memset(&p, 0, sizeof(p));
-  // N grouping (conv wgrad: one group per tap)
-  p.n_groups = 1;
-  p.n_per_group = static_cast<int>(d->N);
-  p.out_group_stride = 0;
-  if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {
-    p.n_groups = d->b.taps > 0 ? d->b.taps : 1;
-    p.n_per_group = d->b.channels;
-    p.out_group_stride = d->ldo / p.n_groups;  // dW row = [taps][I_ld]
-  }
+  p.n_groups = sh.n_groups;
+  p.n_per_group = sh.n_per_group;
+  p.out_group_stride = d->b.mode == B200PDM_OP_CONV_ACT_MN ? d->ldo / p.n_groups : 0;  // dW row = [taps][I_ld]
+  p.out_split_stride = split_stride;
   p.M = static_cast<int>(d->M);
-  p.tiles_m = cdiv(d->M, kBlockM);
-  p.Z = Z1 * Z2;
-
-  // K blocks
-  int kblocks;
-  if (d->a.mode == B200PDM_OP_CONV_ACT) {
-    int taps = d->a.taps > 0 ? d->a.taps : 1;
-    kblocks = taps * cdiv(d->a.channels, 64);
-  } else if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {
-    kblocks = cdiv((int64_t)d->b.batch * d->b.h_out * d->b.w_out, 64);
-  } else {
-    kblocks = cdiv(d->K, 64);
-  }
-  if (kblocks <= 0) {
-    set_err("gemm: empty K");
-    return B200PDM_ERR_ARG;
-  }
+  p.tiles_m = sh.tiles_m;
+  p.Z = sh.Z;
   p.kblocks = kblocks;
 
-  // ---- tile plan (block_n, split-K, pair mode)
-  const bool acc_out = d->out_fp32 && d->accumulate;
-  const bool scratch_ok = !acc_out && p.Z == 1 && p.n_groups == 1 && (int64_t)d->M * d->N * 4 <= (64ll << 20);
-  Plan plan;
-  if (d->splits > 1) {   // caller fixed the split factor
-    plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, false, false, d->block_n, d->splits);
-  } else {
-    plan = plan_gemm(p.n_per_group, p.n_groups, b_mn, p.tiles_m, p.Z, kblocks, acc_out || scratch_ok, !acc_out,
-                     d->block_n);
-  }
-  if (plan.bn <= 0) {
-    set_err("gemm: no valid tile plan (bad block_n?)");
-    return B200PDM_ERR_ARG;
-  }
-  if (plan.splits > 1 && !acc_out) {
-    // split-K of a bf16/fp32 (non-accumulating) output: partial sums go to an fp32 scratch through vector atomics,
-    // then one finalize pass applies bias / time-embedding / residual and converts.
-    const int64_t ldws = (d->N + 3) / 4 * 4;
-    float* ws = scratch_f32((size_t)d->M * ldws, stream);
-    if (!ws) return B200PDM_ERR_CUDA;
+  if (plan.splits > 1 && !acc_out && split_stride == 0) {
+    const size_t need = (size_t)sh.slab * plan.splits * sizeof(float);
+    if (ws_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 31)) {
+      set_err("gemm: workspace smaller than b200pdm_*_workspace() asked for, or not 32-byte aligned");
+      return B200PDM_ERR_ARG;
+    }
+    float* ws = reinterpret_cast<float*>(workspace);
     b200pdm_gemm_desc d2 = *d;
-    d2.out = ws, d2.out_fp32 = 1, d2.ldo = ldws, d2.accumulate = 1, d2.splits = plan.splits, d2.block_n = plan.bn;
+    d2.out = ws, d2.out_fp32 = 1, d2.ldo = sh.ldws, d2.accumulate = 0, d2.splits = plan.splits, d2.block_n = plan.bn;
     d2.bias = nullptr, d2.rowbias = nullptr, d2.residual = nullptr;
-    int rc2 = launch_gemm(&d2, stream);
+    int rc2 = launch_gemm(&d2, nullptr, 0, stream, sh.slab);
     if (rc2) return rc2;
-    return launch_finalize(d, ws, ldws, stream);
+    return launch_finalize(d, ws, sh.ldws, plan.splits, sh.slab, stream);
   }
   int block_n = plan.bn;
   p.block_n = block_n;
@@ -1187,6 +1213,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
   p.rbs2 = d->rbs2;
   p.alpha = d->alpha;
   p.accumulate = d->accumulate;
+#ifdef B200PDM_DIAG
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
   if (dbg_on < 0) dbg_on = getenv("B200PDM_GEMM_DBG") ? 1 : 0;
@@ -1195,12 +1222,15 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
     cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(long long), stream);
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
+#endif
   const size_t smem = (size_t)fixed_bytes + (size_t)stages * stage_bytes;
   const int threads = 64 + 128 * p.epi_groups;
+#ifdef B200PDM_DIAG
   {
-    const char* e = getenv("B200PDM_GEMM_DBGMODE");   // diagnostics, re-read every launch so a script can toggle it
+    const char* e = getenv("B200PDM_GEMM_DBGMODE");   // re-read every launch so a script can toggle it
     p.dbg_mode = e ? atoi(e) : 0;
   }
+#endif
 
   const long total_tiles = (long)p.tiles_m_super * p.tiles_n_per_group * p.n_groups * p.Z * p.splits;  // per cluster
   const int max_clusters = num_sms() / cluster;
@@ -1263,6 +1293,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
       snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d msub=%d split=%d tiles=%ld grid=%d stages=%d cl=%d",
                d->a.mode, d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.m_sub, p.splits,
                total_tiles, grid, stages, cluster);
+#ifdef B200PDM_DIAG
       if (p.dbg) {
         long long h[16];
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1272,6 +1303,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, cudaStream_t stream) {
                 "cta0 lifetime=%lld ns, kernel (events)=%.1f us\n", key, h[4], h[0], h[1], h[2], h[3], h[5], h[6], h[7], tiles_cta0,
                 p.kb_per_split, h[8], h[9], ms * 1e3);
       }
+#endif
       TraceRow& r = g_trace[key];
       r.count++, r.ms += ms;
       r.flops += 2.0 * (double)d->M * p.n_per_group * p.n_groups * kk * p.Z;
@@ -1321,11 +1353,6 @@ int b200pdm_gemm_plan(int64_t n, int n_groups, int b_mn, int tiles_m, int Z, int
   out[5] = (int)tiles, out[6] = 148 / cs;
   return B200PDM_OK;
 }
-int b200pdm_set_lane(int lane) {
-  if (lane < 0 || lane >= kMaxLanes) return B200PDM_ERR_ARG;
-  g_lane = lane;
-  return B200PDM_OK;
-}
 
 int b200pdm_gemm_trace_dump(const char* path) {
   FILE* f = fopen(path, "w");
@@ -1339,34 +1366,90 @@ int b200pdm_gemm_trace_dump(const char* path) {
   return B200PDM_OK;
 }
 
-int b200pdm_gemm(const b200pdm_gemm_desc* desc, b200pdm_stream_t stream) {
-  return launch_gemm(desc, reinterpret_cast<cudaStream_t>(stream));
+size_t b200pdm_gemm_workspace(const b200pdm_gemm_desc* desc) { return gemm_workspace_bytes(desc); }
+
+int b200pdm_gemm(const b200pdm_gemm_desc* desc, void* workspace, size_t ws_bytes, b200pdm_stream_t stream) {
+  return launch_gemm(desc, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int b200pdm_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const void* residual,
-                       int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M, int64_t N, int64_t K,
-                       b200pdm_stream_t stream) {
-  b200pdm_gemm_desc d;
+}  // extern "C"
+
+// Descriptor builders shared by each entry point and its *_workspace twin (pointers may be null in the query).
+static void desc_linear_fwd(b200pdm_gemm_desc& d, const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
+                            const void* residual, int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M, int64_t N,
+                            int64_t K) {
   memset(&d, 0, sizeof(d));
   d.a.mode = B200PDM_OP_K2D, d.a.ptr = x, d.a.ld = ldx;
   d.b.mode = B200PDM_OP_K2D, d.b.ptr = w, d.b.ld = ldw;
   d.M = M, d.N = N, d.K = K, d.Z1 = 1, d.Z2 = 1;
   d.out = out, d.out_fp32 = out_fp32, d.ldo = ldo;
   d.bias = bias, d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
-  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
 }
-
-int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual, int64_t ldr,
-                         void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, b200pdm_stream_t stream) {
+static void desc_linear_dgrad(b200pdm_gemm_desc& d, const void* dy, int64_t lddy, const void* w, int64_t ldw,
+                              const void* residual, int64_t ldr, void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K) {
   // dx[M,K] = dy[M,N] . w[N,K]: reduction over N; B(n'=k, k'=n) = w[n][k] is MN-major.
-  b200pdm_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.a.mode = B200PDM_OP_K2D, d.a.ptr = dy, d.a.ld = lddy;
   d.b.mode = B200PDM_OP_MN2D, d.b.ptr = w, d.b.ld = ldw;
   d.M = M, d.N = K, d.K = N, d.Z1 = 1, d.Z2 = 1;
   d.out = dx, d.out_fp32 = 0, d.ldo = lddx;
   d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
-  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+}
+static void desc_conv_fwd(b200pdm_gemm_desc& d, const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias,
+                          const float* rowbias, int64_t ld_rowbias, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                          int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride) {
+  const int h_out = h_in / stride, w_out = w_in / stride;
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = x, d.a.ld = ldx;
+  d.a.batch = batch, d.a.h_in = h_in, d.a.w_in = w_in, d.a.channels = c_in;
+  d.a.h_out = h_out, d.a.w_out = w_out, d.a.stride = stride, d.a.taps = ksize * ksize;
+  d.b.mode = B200PDM_OP_CONV_W, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
+  d.b.taps = ksize * ksize;
+  d.M = (int64_t)batch * h_out * w_out, d.N = c_out, d.K = (int64_t)ksize * ksize * c_in, d.Z1 = 1, d.Z2 = 1;
+  d.out = out, d.out_fp32 = 0, d.ldo = ldo;
+  d.bias = bias, d.rowbias = rowbias, d.ld_rowbias = ld_rowbias, d.rows_per_group = h_out * w_out;
+  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
+}
+static void desc_conv_dgrad(b200pdm_gemm_desc& d, const void* dy, int64_t lddy, const void* w, int64_t w_ild,
+                            const void* residual, int64_t ldr, void* dx, int64_t lddx, int batch, int h, int w_sp, int c_in,
+                            int c_out, int ksize) {
+  memset(&d, 0, sizeof(d));
+  d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = dy, d.a.ld = lddy;
+  d.a.batch = batch, d.a.h_in = h, d.a.w_in = w_sp, d.a.channels = c_out;
+  d.a.h_out = h, d.a.w_out = w_sp, d.a.stride = 1, d.a.taps = ksize * ksize, d.a.flip = 1;
+  d.b.mode = B200PDM_OP_CONV_WT, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
+  d.b.taps = ksize * ksize;
+  d.M = (int64_t)batch * h * w_sp, d.N = c_in, d.K = (int64_t)ksize * ksize * c_out, d.Z1 = 1, d.Z2 = 1;
+  d.out = dx, d.out_fp32 = 0, d.ldo = lddx;
+  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
+}
+
+extern "C" {
+
+size_t b200pdm_linear_fwd_workspace(int64_t M, int64_t N, int64_t K, int out_fp32) {
+  b200pdm_gemm_desc d;
+  desc_linear_fwd(d, nullptr, K, nullptr, K, nullptr, nullptr, 0, nullptr, N, out_fp32, M, N, K);
+  return gemm_workspace_bytes(&d);
+}
+int b200pdm_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const void* residual,
+                       int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M, int64_t N, int64_t K, void* workspace,
+                       size_t ws_bytes, b200pdm_stream_t stream) {
+  b200pdm_gemm_desc d;
+  desc_linear_fwd(d, x, ldx, w, ldw, bias, residual, ldr, out, ldo, out_fp32, M, N, K);
+  return launch_gemm(&d, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t b200pdm_linear_dgrad_workspace(int64_t M, int64_t N, int64_t K) {
+  b200pdm_gemm_desc d;
+  desc_linear_dgrad(d, nullptr, N, nullptr, K, nullptr, 0, nullptr, K, M, N, K);
+  return gemm_workspace_bytes(&d);
+}
+int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual, int64_t ldr,
+                         void* dx, int64_t lddx, int64_t M, int64_t N, int64_t K, void* workspace, size_t ws_bytes,
+                         b200pdm_stream_t stream) {
+  b200pdm_gemm_desc d;
+  desc_linear_dgrad(d, dy, lddy, w, ldw, residual, ldr, dx, lddx, M, N, K);
+  return launch_gemm(&d, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw, int64_t M,
@@ -1378,49 +1461,46 @@ int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ld
   d.b.mode = B200PDM_OP_MN2D, d.b.ptr = x, d.b.ld = ldx;
   d.M = N, d.N = K, d.K = M, d.Z1 = 1, d.Z2 = 1;
   d.out = dw, d.out_fp32 = 1, d.ldo = lddw, d.alpha = 1.f, d.accumulate = 1;
-  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm(&d, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t b200pdm_conv_fwd_workspace(int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride) {
+  if ((ksize != 3 && ksize != 1) || (stride != 1 && stride != 2)) return 0;
+  b200pdm_gemm_desc d;
+  desc_conv_fwd(d, nullptr, c_in, nullptr, c_in, nullptr, nullptr, 0, nullptr, 0, nullptr, c_out, batch, h_in, w_in, c_in, c_out,
+                ksize, stride);
+  return gemm_workspace_bytes(&d);
+}
 int b200pdm_conv_fwd(const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias, const float* rowbias,
                      int64_t ld_rowbias, const void* residual, int64_t ldr, void* out, int64_t ldo, int batch, int h_in,
-                     int w_in, int c_in, int c_out, int ksize, int stride, b200pdm_stream_t stream) {
+                     int w_in, int c_in, int c_out, int ksize, int stride, void* workspace, size_t ws_bytes,
+                     b200pdm_stream_t stream) {
   if ((ksize != 3 && ksize != 1) || (stride != 1 && stride != 2)) {
     set_err("conv_fwd: unsupported ksize/stride");
     return B200PDM_ERR_UNSUPPORTED;
   }
-  const int h_out = h_in / stride, w_out = w_in / stride;
   b200pdm_gemm_desc d;
-  memset(&d, 0, sizeof(d));
-  d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = x, d.a.ld = ldx;
-  d.a.batch = batch, d.a.h_in = h_in, d.a.w_in = w_in, d.a.channels = c_in;
-  d.a.h_out = h_out, d.a.w_out = w_out, d.a.stride = stride, d.a.taps = ksize * ksize;
-  d.b.mode = B200PDM_OP_CONV_W, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
-  d.b.taps = ksize * ksize;
-  d.M = (int64_t)batch * h_out * w_out, d.N = c_out, d.K = (int64_t)ksize * ksize * c_in, d.Z1 = 1, d.Z2 = 1;
-  d.out = out, d.out_fp32 = 0, d.ldo = ldo;
-  d.bias = bias, d.rowbias = rowbias, d.ld_rowbias = ld_rowbias, d.rows_per_group = h_out * w_out;
-  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
-  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+  desc_conv_fwd(d, x, ldx, w, w_ild, bias, rowbias, ld_rowbias, residual, ldr, out, ldo, batch, h_in, w_in, c_in, c_out, ksize,
+                stride);
+  return launch_gemm(&d, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
+size_t b200pdm_conv_dgrad_workspace(int batch, int h, int w_sp, int c_in, int c_out, int ksize) {
+  if (ksize != 3 && ksize != 1) return 0;
+  b200pdm_gemm_desc d;
+  desc_conv_dgrad(d, nullptr, c_out, nullptr, c_in, nullptr, 0, nullptr, c_in, batch, h, w_sp, c_in, c_out, ksize);
+  return gemm_workspace_bytes(&d);
+}
 int b200pdm_conv_dgrad(const void* dy, int64_t lddy, const void* w, int64_t w_ild, const void* residual, int64_t ldr,
-                       void* dx, int64_t lddx, int batch, int h, int w_sp, int c_in, int c_out, int ksize,
-                       b200pdm_stream_t stream) {
+                       void* dx, int64_t lddx, int batch, int h, int w_sp, int c_in, int c_out, int ksize, void* workspace,
+                       size_t ws_bytes, b200pdm_stream_t stream) {
   if (ksize != 3 && ksize != 1) {
     set_err("conv_dgrad: unsupported ksize");
     return B200PDM_ERR_UNSUPPORTED;
   }
   b200pdm_gemm_desc d;
-  memset(&d, 0, sizeof(d));
-  d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = dy, d.a.ld = lddy;
-  d.a.batch = batch, d.a.h_in = h, d.a.w_in = w_sp, d.a.channels = c_out;
-  d.a.h_out = h, d.a.w_out = w_sp, d.a.stride = 1, d.a.taps = ksize * ksize, d.a.flip = 1;
-  d.b.mode = B200PDM_OP_CONV_WT, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
-  d.b.taps = ksize * ksize;
-  d.M = (int64_t)batch * h * w_sp, d.N = c_in, d.K = (int64_t)ksize * ksize * c_out, d.Z1 = 1, d.Z2 = 1;
-  d.out = dx, d.out_fp32 = 0, d.ldo = lddx;
-  d.residual = residual, d.ldr = ldr, d.alpha = 1.f;
-  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+  desc_conv_dgrad(d, dy, lddy, w, w_ild, residual, ldr, dx, lddx, batch, h, w_sp, c_in, c_out, ksize);
+  return launch_gemm(&d, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t w_ild, int batch,
@@ -1440,7 +1520,7 @@ int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx,
   d.b.h_out = h_out, d.b.w_out = w_out, d.b.stride = stride, d.b.taps = taps;
   d.M = c_out, d.N = (int64_t)taps * c_in, d.K = pixels, d.Z1 = 1, d.Z2 = 1;
   d.out = dw, d.out_fp32 = 1, d.ldo = (int64_t)taps * w_ild, d.alpha = 1.f, d.accumulate = 1;
-  return launch_gemm(&d, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm(&d, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

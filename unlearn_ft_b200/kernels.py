@@ -37,6 +37,20 @@ def alloc2d(rows: int, cols: int, device=None, dtype=BF16, zero: bool = False) -
     return buf[:, :cols] if ld != cols else buf
 
 
+_WS_BYTES = {}
+
+
+def _workspace(key, query, device):
+    """(tensor | None, bytes): caller-owned scratch for a GEMM-class call, sized by the library's *_workspace() twin (cached per
+    shape).  It comes from torch's stream-ordered allocator, so inside a CUDA-graph capture it lives in the graph's pool."""
+    n = _WS_BYTES.get(key)
+    if n is None:
+        n = _WS_BYTES[key] = int(query())
+    if n == 0:
+        return None, 0
+    return torch.empty(n, device=device, dtype=torch.uint8), n
+
+
 def _chk2d(t: torch.Tensor, name: str, dtype=BF16):
     if t.dim() != 2 or t.dtype != dtype or t.stride(1) != 1 or not t.is_cuda:
         raise ValueError(f"{name}: expected a 2-D {dtype} CUDA tensor with unit inner stride, got {tuple(t.shape)} "
@@ -57,9 +71,12 @@ def linear_fwd(x, w, bias=None, residual=None, out=None, out_fp32=False):
         out = alloc2d(M, N, x.device, F32 if out_fp32 else BF16)
     if residual is not None:
         _chk2d(residual, "residual")
-    check(_lib.lib().b200pdm_linear_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
-                                        _ptr(residual), residual.stride(0) if residual is not None else 0,
-                                        out.data_ptr(), out.stride(0), int(out.dtype == F32), M, N, K, _stream()),
+    L = _lib.lib()
+    ws, nws = _workspace(("lf", M, N, K, out.dtype == F32),
+                         lambda: L.b200pdm_linear_fwd_workspace(M, N, K, int(out.dtype == F32)), x.device)
+    check(L.b200pdm_linear_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                               _ptr(residual), residual.stride(0) if residual is not None else 0,
+                               out.data_ptr(), out.stride(0), int(out.dtype == F32), M, N, K, _ptr(ws), nws, _stream()),
           "linear_fwd")
     return out
 
@@ -71,9 +88,11 @@ def linear_dgrad(dy, w, residual=None, out=None):
     K = w.shape[1]
     if out is None:
         out = alloc2d(M, K, dy.device)
-    check(_lib.lib().b200pdm_linear_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), _ptr(residual),
-                                          residual.stride(0) if residual is not None else 0, out.data_ptr(),
-                                          out.stride(0), M, N, K, _stream()), "linear_dgrad")
+    L = _lib.lib()
+    ws, nws = _workspace(("ld", M, N, K), lambda: L.b200pdm_linear_dgrad_workspace(M, N, K), dy.device)
+    check(L.b200pdm_linear_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), _ptr(residual),
+                                 residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                                 out.stride(0), M, N, K, _ptr(ws), nws, _stream()), "linear_dgrad")
     return out
 
 
@@ -95,10 +114,13 @@ def conv_fwd(x, w, B, H, W, c_out, ksize=3, stride=1, bias=None, rowbias=None, r
     if out is None:
         out = alloc2d(B * Ho * Wo, c_out, x.device)
     ild = w.stride(1) if w.dim() == 3 else w.stride(0)
-    check(_lib.lib().b200pdm_conv_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), ild, _ptr(bias), _ptr(rowbias),
-                                      rowbias.stride(0) if rowbias is not None else 0, _ptr(residual),
-                                      residual.stride(0) if residual is not None else 0, out.data_ptr(),
-                                      out.stride(0), B, H, W, c_in, c_out, ksize, stride, _stream()), "conv_fwd")
+    L = _lib.lib()
+    ws, nws = _workspace(("cf", B, H, W, c_in, c_out, ksize, stride),
+                         lambda: L.b200pdm_conv_fwd_workspace(B, H, W, c_in, c_out, ksize, stride), x.device)
+    check(L.b200pdm_conv_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), ild, _ptr(bias), _ptr(rowbias),
+                             rowbias.stride(0) if rowbias is not None else 0, _ptr(residual),
+                             residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                             out.stride(0), B, H, W, c_in, c_out, ksize, stride, _ptr(ws), nws, _stream()), "conv_fwd")
     return out
 
 
@@ -109,9 +131,12 @@ def conv_dgrad(dy, w, B, H, W, c_in, ksize=3, residual=None, out=None):
     if out is None:
         out = alloc2d(B * H * W, c_in, dy.device)
     ild = w.stride(1) if w.dim() == 3 else w.stride(0)
-    check(_lib.lib().b200pdm_conv_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), ild, _ptr(residual),
-                                        residual.stride(0) if residual is not None else 0, out.data_ptr(),
-                                        out.stride(0), B, H, W, c_in, c_out, ksize, _stream()), "conv_dgrad")
+    L = _lib.lib()
+    ws, nws = _workspace(("cd", B, H, W, c_in, c_out, ksize),
+                         lambda: L.b200pdm_conv_dgrad_workspace(B, H, W, c_in, c_out, ksize), dy.device)
+    check(L.b200pdm_conv_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), ild, _ptr(residual),
+                               residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                               out.stride(0), B, H, W, c_in, c_out, ksize, _ptr(ws), nws, _stream()), "conv_dgrad")
     return out
 
 
@@ -125,8 +150,11 @@ def conv_wgrad(dy, x, dw, B, H, W, ksize=3, stride=1):
     return dw
 
 
-def gemm(desc: GemmDesc):
-    check(_lib.lib().b200pdm_gemm(C.byref(desc), _stream()), "gemm")
+def gemm(desc: GemmDesc, device=None):
+    L = _lib.lib()
+    n = int(L.b200pdm_gemm_workspace(C.byref(desc)))
+    ws = torch.empty(n, device=device or "cuda", dtype=torch.uint8) if n else None
+    check(L.b200pdm_gemm(C.byref(desc), _ptr(ws), n, _stream()), "gemm")
 
 
 def bmm(a, b, out, *, a_mn=False, b_mn=False, M, N, K, Z1=1, Z2=1, a_ld, a_bs=(0, 0), b_ld, b_bs=(0, 0), o_ld,
@@ -138,7 +166,7 @@ def bmm(a, b, out, *, a_mn=False, b_mn=False, M, N, K, Z1=1, Z2=1, a_ld, a_bs=(0
     d.M, d.N, d.K, d.Z1, d.Z2 = M, N, K, Z1, Z2
     d.out, d.out_fp32, d.ldo, d.obs1, d.obs2 = out.data_ptr(), int(out.dtype == F32), o_ld, o_bs[0], o_bs[1]
     d.alpha = alpha
-    gemm(d)
+    gemm(d, out.device)
     return out
 
 
@@ -221,12 +249,6 @@ def softmax_fwd(s, p, rows, cols, scale):
     check(_lib.lib().b200pdm_softmax_fwd(s.data_ptr(), s.stride(-2), p.data_ptr(), p.stride(-2), rows, cols, scale,
                                          _stream()), "softmax_fwd")
     return p
-
-
-def softmax_bwd(dp, p, ds, rows, cols, scale):
-    check(_lib.lib().b200pdm_softmax_bwd(dp.data_ptr(), dp.stride(-2), p.data_ptr(), p.stride(-2), ds.data_ptr(),
-                                         ds.stride(-2), rows, cols, scale, _stream()), "softmax_bwd")
-    return ds
 
 
 def attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=None, want_lse=False):

@@ -128,6 +128,11 @@ class ResnetBlock2DWidthGated(nn.Module):
         g = torch.tensor(self.keep_groups, dtype=torch.long)
         return (g[:, None] * self.group_dim + torch.arange(self.group_dim)[None, :]).reshape(-1)
 
+    def prune(self):
+        """Reference blocks.py:435-475 / :647-702.  Modules here exist only in pruned form (the model-level `prune()` creates
+        them that way), so the reference's per-module call has nothing left to do."""
+        return self
+
     def run(self, x, temb_act, B, H, W, need_bwd):
         """x: [B*H*W, C_in]; temb_act = SiLU(emb) bf16 [B, 1280]. Returns (y, bwd) with bwd(dy) -> (dx, d_temb_act)."""
         if self.dropped:
@@ -204,6 +209,10 @@ class GatedAttention(nn.Module):
         self.to_out = nn.ModuleList([PLinear(inner, query_dim, bias=True), nn.Identity()])
         self.pruned = True
 
+    def prune(self):
+        """Reference blocks.py:163-196: already in pruned form (see ResnetBlock2DWidthGated.prune)."""
+        return self
+
     def _fused(self, names):
         """One [sum N, K] bf16 weight (and fp32 grad) view over parameters that are adjacent in the arena."""
         mods = [getattr(self, n) for n in names]
@@ -274,6 +283,10 @@ class FeedForwardWidthGated(nn.Module):
         self.inner = inner
         self.net = nn.ModuleList([GEGLUGated(dim, inner), nn.Identity(), PLinear(inner, dim)])
 
+    def prune(self):
+        """Reference blocks.py:131-138 (+ GEGLUGated.prune_gate :62-76): already in pruned form."""
+        return self
+
     def keep_units(self) -> torch.Tensor:
         g = torch.tensor(self.keep_groups, dtype=torch.long)
         return (g[:, None] * self.group_dim + torch.arange(self.group_dim)[None, :]).reshape(-1)
@@ -334,6 +347,10 @@ class Transformer2DModelWidthGated(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlockWidthGated(
             in_channels, cross_attention_dim, keep1, keep2, keep_ff, num_attention_heads, ff_gate_width)])
         self.proj_out = PLinear(in_channels, in_channels)
+
+    def prune_module(self):
+        """Reference blocks.py:1324-1334 (depth-dropped transformer -> Identity): already applied at construction."""
+        return self
 
     def run(self, x, ctx2d, B, H, W, Lctx, need_bwd):
         if self.dropped:                                                                # blocks.py:1134-1138

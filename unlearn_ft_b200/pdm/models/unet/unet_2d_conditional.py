@@ -120,7 +120,13 @@ class UNet2DConditionModelGated(nn.Module):
         if arch_vector is None:
             arch_vector = torch.ones(1, n_total)
         self.arch_vector = arch_vector.detach().float().cpu().clone()
-        self._build(cfg)
+        self._pending_arch = None
+        self._materialise(device, trainable, seed)
+        self.eval()
+
+    def _materialise(self, device, trainable, seed):
+        """Blocks at the widths `self.arch_vector` prescribes + their flat parameter arena."""
+        self._build(self._config)
         self.arena = ParamArena(self, device, trainable=trainable, seed=seed)
         anchor = self.arena.master if trainable else None
         if trainable:
@@ -128,7 +134,6 @@ class UNet2DConditionModelGated(nn.Module):
         for blk in list(self.down_blocks) + [self.mid_block] + list(self.up_blocks):
             blk._anchor = anchor
         self._anchor = anchor
-        self.eval()
 
     # ------------------------------------------------------------------------------------------------ construction
     def _build(self, cfg):
@@ -213,6 +218,50 @@ class UNet2DConditionModelGated(nn.Module):
     # ------------------------------------------------------------------------------------------------ reference API
     def get_structure(self):
         return self.structure
+
+    def is_pruned(self) -> bool:
+        return bool((self.arch_vector < 0.5).any())
+
+    def set_structure(self, arch_vectors):
+        """Reference :1367-1415 -- first half of its two-phase API (build full -> set_structure -> prune).  `arch_vectors` is
+        what `HyperStructure.transform_arch_vector(arch_vector, model.get_structure())` returns ({'width': [T[1, w], ...],
+        'depth': [T[1, 1], ...]}, consumed block by block in get_structure() order) or the flat [1, 1620] vector itself.
+        The gate values are recorded; `prune()` applies them.  (Runtime multiplicative gates on an un-pruned network, the
+        pruning phase's mode, are SURVEY section 8f-4.)"""
+        if torch.is_tensor(arch_vectors):
+            flat = arch_vectors.detach().float().cpu().reshape(1, -1).clone()
+        else:
+            widths, depths = list(arch_vectors["width"]), list(arch_vectors["depth"])
+            want_w = [w for s in self.structure["width"] for w in s]
+            if [int(t.shape[-1]) for t in widths] != want_w:
+                raise ValueError("set_structure: width vectors do not match get_structure()")
+            if len(depths) != sum(d for s in self.structure["depth"] for d in s):
+                raise ValueError("set_structure: depth vectors do not match get_structure()")
+            flat = torch.cat([t.detach().float().cpu().reshape(1, -1) for t in widths + depths], dim=1)
+        if flat.shape != self.arch_vector.shape:
+            raise ValueError(f"set_structure: expected {tuple(self.arch_vector.shape)} gate values, got {tuple(flat.shape)}")
+        self._pending_arch = flat
+
+    @torch.no_grad()
+    def prune(self):
+        """Second half of the reference's two-phase API: its `for m in model.modules(): m.prune()` / `m.prune_module()` pass
+        (:2455-2461; per-module bodies blocks.py:62-76,131-138,163-196,435-475,647-702,1324-1334).  Here it is one
+        operation on the model: the blocks are re-created at the widths the recorded gates keep and every weight is
+        selected out of the current full-width tensors with the reference's boolean-mask (ascending index) selections.
+        Idempotent once applied, so the reference's own module loop -- which reaches this method first (the root module)
+        and then the leaf modules' no-op `prune()` -- can be run unchanged."""
+        if self._pending_arch is None:
+            return self
+        if self.is_pruned():
+            raise RuntimeError("prune(): this network is already pruned (the reference prunes a full-width model once)")
+        full_sd = {k: v.detach().clone() for k, v in self.state_dict().items()}
+        device, trainable = self.arena.device, self.arena.trainable
+        self.arch_vector, self._pending_arch = self._pending_arch, None
+        for name in ("conv_in", "time_embedding", "down_blocks", "mid_block", "up_blocks", "conv_norm_out", "conv_out"):
+            delattr(self, name)
+        self._materialise(device, trainable, None)
+        self.load_unpruned_state_dict(full_sd)
+        return self
 
     @property
     def device(self):

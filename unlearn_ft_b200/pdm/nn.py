@@ -273,7 +273,7 @@ def side_branch(*operands):
     _Side.open_.add(main)
     _Side.inside = True
     try:
-        with torch.cuda.stream(side), _lib.lane(_lib.lane.current + 2):
+        with torch.cuda.stream(side):
             yield
     finally:
         _Side.inside = False
@@ -367,53 +367,6 @@ def attention(q, k, v, B, heads, Lq, Lk, need_bwd, out=None):
         K.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, heads, Lq, Lk, scale)
 
     return o, bwd
-
-
-def attention_unfused(q, k, v, B, heads, Lq, Lk, need_bwd, out=None):
-    """First-version attention kept for A/B checks: batched QK^T (fp32 scores) -> row softmax -> PV on the GEMM core."""
-    D = 64
-    scale = D ** -0.5
-    Lkp = K.round8(Lk)
-    dev = q.device
-    ldq, ldk, ldv = q.stride(0), k.stride(0), v.stride(0)
-    s = torch.empty(B * heads * Lq * Lkp, device=dev, dtype=F32)
-    K.bmm(q, k, s, M=Lq, N=Lk, K=D, Z1=heads, Z2=B, a_ld=ldq, a_bs=(D, Lq * ldq), b_ld=ldk, b_bs=(D, Lk * ldk),
-          o_ld=Lkp, o_bs=(Lq * Lkp, heads * Lq * Lkp))
-    p = torch.empty(B * heads * Lq * Lkp, device=dev, dtype=BF16)
-    K.softmax_fwd(s.view(-1, Lkp), p.view(-1, Lkp), B * heads * Lq, Lk, scale)
-    del s
-    if out is None:
-        out = K.alloc2d(B * Lq, heads * D, dev)
-    K.bmm(p, v, out, b_mn=True, M=Lq, N=D, K=Lk, Z1=heads, Z2=B, a_ld=Lkp, a_bs=(Lq * Lkp, heads * Lq * Lkp),
-          b_ld=ldv, b_bs=(D, Lk * ldv), o_ld=out.stride(0), o_bs=(D, Lq * out.stride(0)))
-    if not need_bwd:
-        return out, None
-
-    def bwd(do, dq, dk, dv):
-        """do: [B*Lq, heads*64]; dq/dk/dv: output views (pitches arbitrary) or None to skip."""
-        ldo = do.stride(0)
-        pbs = (Lq * Lkp, heads * Lq * Lkp)
-        # dV = P^T dO   (A = P MN-major: m' = key, k' = query ; B = dO MN-major: n' = d, k' = query)
-        if dv is not None:
-            K.bmm(p, do, dv, a_mn=True, b_mn=True, M=Lk, N=D, K=Lq, Z1=heads, Z2=B, a_ld=Lkp, a_bs=pbs, b_ld=ldo,
-                  b_bs=(D, Lq * ldo), o_ld=dv.stride(0), o_bs=(D, Lk * dv.stride(0)))
-        # dP = dO V^T  (fp32)
-        dp = torch.empty(B * heads * Lq * Lkp, device=dev, dtype=F32)
-        K.bmm(do, v, dp, M=Lq, N=Lk, K=D, Z1=heads, Z2=B, a_ld=ldo, a_bs=(D, Lq * ldo), b_ld=ldv, b_bs=(D, Lk * ldv),
-              o_ld=Lkp, o_bs=pbs)
-        ds = torch.empty(B * heads * Lq * Lkp, device=dev, dtype=BF16)  # pad columns are never read (map dims)
-        K.softmax_bwd(dp.view(-1, Lkp), p.view(-1, Lkp), ds.view(-1, Lkp), B * heads * Lq, Lk, scale)
-        del dp
-        # dQ = dS K   (B = K MN-major: n' = d, k' = key)
-        if dq is not None:
-            K.bmm(ds, k, dq, b_mn=True, M=Lq, N=D, K=Lk, Z1=heads, Z2=B, a_ld=Lkp, a_bs=pbs, b_ld=ldk,
-                  b_bs=(D, Lk * ldk), o_ld=dq.stride(0), o_bs=(D, Lq * dq.stride(0)))
-        # dK = dS^T Q  (A = dS MN-major, B = Q MN-major)
-        if dk is not None:
-            K.bmm(ds, q, dk, a_mn=True, b_mn=True, M=Lk, N=D, K=Lq, Z1=heads, Z2=B, a_ld=Lkp, a_bs=pbs, b_ld=ldq,
-                  b_bs=(D, Lq * ldq), o_ld=dk.stride(0), o_bs=(D, Lk * dk.stride(0)))
-
-    return out, bwd
 
 
 def concat_channels(a, b):

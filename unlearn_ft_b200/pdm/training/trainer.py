@@ -402,7 +402,8 @@ class UnetFineTuner:
     """Hot path of reference `UnetFineTuner` (trainer.py:2116-2488) on synthetic inputs."""
 
     def __init__(self, student: UNet2DConditionModelPruned, teacher: UNet2DConditionModel, lr=1e-6, betas=(0.9, 0.999),
-                 eps=1e-8, weight_decay=0.0, warmup_steps=250, w_diff=1.0, w_kd=2.0, w_block=0.1, snr_gamma=5.0):
+                 eps=1e-8, weight_decay=0.0, warmup_steps=250, w_diff=1.0, w_kd=2.0, w_block=0.1, snr_gamma=5.0,
+                 process_group=None):
         self.student, self.teacher = student, teacher
         self.device = student.device
         self.noise_scheduler = NoiseScheduler(self.device)
@@ -413,7 +414,7 @@ class UnetFineTuner:
         cast_block_act_hooks(student, self.block_act_student)                     # trainer.py:2303-2306
         if teacher is not None:
             cast_block_act_hooks(teacher, self.block_act_teacher)
-        self.reducer = GradReducer(student)
+        self.reducer = GradReducer(student, group=process_group)   # default group = all ranks (the DDP wrap of the reference)
         # second stream for the teacher's forward (env B200PDM_SERIAL_TEACHER=1: A/B measurement of the serial order)
         self.teacher_stream = (torch.cuda.Stream() if (teacher is not None and torch.cuda.is_available()
                                                        and not os.environ.get("B200PDM_SERIAL_TEACHER")) else None)
@@ -428,10 +429,26 @@ class UnetFineTuner:
         g = self.snr_gamma * torch.ones_like(timesteps)
         return (torch.stack([snr, g], dim=1).min(dim=1)[0] / snr).float().contiguous()
 
+    def _diffusion_inputs(self, batch):
+        """Latents, noise and timesteps of a step.  The reference draws the last two inside `step()`
+        (`torch.randn_like(latents)`, trainer.py:2409; `torch.randint(0, num_train_timesteps, (bsz,))`, :2421): a batch
+        without 'noise' / 'timesteps' gets exactly that (torch's global CUDA generator, or `self.generator` if set);
+        parity tests and the CUDA-graph step pass them in so that both sides of a comparison see the same draw."""
+        latents = batch["latents"]
+        gen = getattr(self, "generator", None)
+        noise = batch.get("noise")
+        if noise is None:
+            noise = torch.randn(latents.shape, device=latents.device, dtype=latents.dtype, generator=gen)
+        timesteps = batch.get("timesteps")
+        if timesteps is None:
+            timesteps = torch.randint(0, self.noise_scheduler.config.num_train_timesteps, (latents.shape[0],),
+                                      device=latents.device, generator=gen).long()
+        return latents, noise, timesteps
+
     def step(self, batch):
         """trainer.py:2403-2488.  batch: {'latents' [B,4,h,w] (stands in for vae.encode(...)*0.18215), 'noise',
         'timesteps', 'prompt_embeds' [B,77,1024]} -- the synthetic-input contract of SURVEY.md section 8d."""
-        latents, noise, timesteps = batch["latents"], batch["noise"], batch["timesteps"]
+        latents, noise, timesteps = self._diffusion_inputs(batch)
         ehs = batch["prompt_embeds"]
         noisy, target = self.noise_scheduler.add_noise_and_velocity(latents, noise, timesteps)
         teacher_pred = None
@@ -443,7 +460,7 @@ class UnetFineTuner:
             # leave idle.  Joined before the loss, which is the first consumer of the teacher's prediction and features.
             cur = torch.cuda.current_stream()
             ts.wait_stream(cur)
-            with torch.cuda.stream(ts), _lib.lane(1), torch.no_grad():
+            with torch.cuda.stream(ts), torch.no_grad():
                 teacher_pred = self.teacher(noisy, timesteps, ehs).sample
         elif need_teacher:
             with torch.no_grad():
@@ -625,14 +642,13 @@ class BilevelUnetFineTuner(UnetFineTuner):
     def upper_step(self, batch):
         """trainer.py:2904-3001 with the shipped weights (diffusion 0 / distillation 1 / block 0):
         loss = mse(student(x_t, c), 2*eps_T(x_t, empty) - eps_T(x_t, c))  (:2996-2998)."""
-        latents, noise, timesteps = batch["latents"], batch["noise"], batch["timesteps"]
+        latents, noise, timesteps = self._diffusion_inputs(batch)
         ehs, empty = batch["prompt_embeds"], batch["empty_prompt_embeds"]
         noisy, _ = self.noise_scheduler.add_noise_and_velocity(latents, noise, timesteps)
         ts = self.teacher_stream
         if ts is not None:                                                        # teacher x2 next to the student (see step())
             ts.wait_stream(torch.cuda.current_stream())
-        with (torch.cuda.stream(ts) if ts is not None else contextlib.nullcontext()), \
-                (_lib.lane(1) if ts is not None else contextlib.nullcontext()), torch.no_grad():
+        with (torch.cuda.stream(ts) if ts is not None else contextlib.nullcontext()), torch.no_grad():
             cond = self.teacher(noisy, timesteps, ehs).sample                     # :2951
             uncond = self.teacher(noisy, timesteps, empty).sample                 # :2953
         pred = self.student(noisy, timesteps, ehs).sample                         # :2957
