@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--ratio", type=float, default=0.55)
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip the stock-torch (cuDNN / cuBLAS / SDPA / fused AdamW) run of the oracle on the same GPU")
     ap.add_argument("--no-graph", action="store_true", help="single GPU: time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--sampling", action="store_true",
                     help="BASELINE config 5 instead of the default config 2: forward-only CFG sampling loop (U-Net only), "
@@ -196,6 +198,71 @@ def gemm_roofline(torch, K, batch, latent):
     ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
     flops = 2.0 * B * H * W * Co * 9 * Ci
     return flops / (ms * 1e-3) / 1e12, ms, f"conv3x3 {Ci}->{Co} @ {H}x{W} batch {B} (implicit GEMM M={B*H*W} N={Co} K={9*Ci})"
+
+
+def attention_roofline(torch, K, batch, peaks):
+    """Second tensor-class kernel: the fused tcgen05 attention forward at the step's dominant attention shape (teacher
+    self-attention at 64x64: 5 heads, L = 4096, head_dim 64), timed alone with CUDA events.  FLOPs = 4 B h L^2 64."""
+    B, H, L = batch, 5, 4096
+    q, k, v = (K.alloc2d(B * L, H * 64).normal_() for _ in range(3))
+    out = K.alloc2d(B * L, H * 64)
+    for _ in range(3):
+        K.attention_fwd(q, k, v, B, H, L, L, 0.125, out=out)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for e0, e1 in ev:
+        e0.record()
+        K.attention_fwd(q, k, v, B, H, L, L, 0.125, out=out)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    tf = 4.0 * B * H * L * L * 64 / (ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops", 1590.0)
+    return {"bound": "tensor", "kernel": "b200::attn_fwd2_kernel (tcgen05 flash-style attention forward)",
+            "shape": f"batch {B}, {H} heads, Lq = Lk = {L}, head_dim 64", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+            "frac": tf / peak, "ms_per_launch": ms, "traffic": None}
+
+
+def gemm_class_roofline(torch, _lib, one_eager_step, peaks):
+    """Launch-weighted roofline of the whole GEMM class (every tcgen05 GEMM / implicit-GEMM conv launch of ONE step, forward
+    and backward, teacher and student): sum of algorithmic FLOPs (2 M N K) / sum of per-launch CUDA-event times, measured
+    live by the library's per-launch trace (serialised launches, so launch gaps are included: a lower bound)."""
+    import ctypes as C
+    L = _lib.lib()
+    L.b200pdm_gemm_trace_enable(1)
+    try:
+        one_eager_step()
+        torch.cuda.synchronize()
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        L.b200pdm_gemm_trace_totals(C.byref(ms), C.byref(fl), C.byref(n))
+    finally:
+        L.b200pdm_gemm_trace_enable(0)
+    if ms.value <= 0:
+        return None
+    tf = fl.value / (ms.value * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops", 1590.0)
+    return {"bound": "tensor", "kernel": "b200::gemm_kernel, all launches of one step (launch-weighted)", "achieved": tf,
+            "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "gemm_ms_per_step": ms.value, "gemm_launches_per_step": n.value,
+            "gemm_tflop_per_step": fl.value / 1e12, "traffic": None,
+            "how": "per-launch CUDA events on the launching stream, launches serialised (one eager step after the timed region)"}
+
+
+def library_baseline_run(args):
+    """SURVEY section 8d 'library' reference point, driver-visible: the oracle (torch restatement of the reference step) on
+    the SAME GPU through stock torch ops (cuDNN / cuBLAS / SDPA / fused torch AdamW, bf16 autocast, eager), in a
+    subprocess after the timed region (tests/library_baseline.py).  Not the product path; never part of `value`."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "library_baseline.py"), "--batch", str(args.batch),
+                            "--ratio", str(args.ratio), "--steps", "3", "--warmup", "2"], capture_output=True, text=True,
+                           timeout=600, cwd=ROOT)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"value": None, "note": f"failed rc={r.returncode}: {r.stderr[-300:]}"}
+        d = json.loads(line[-1])
+        return {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "kind": "torch-library oracle on the same GPU",
+                "what": d["what"], "steps": 3, "warmup": 2, "torch": d["torch"], "cudnn": d["cudnn"]}
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "note": f"failed: {e!r}"}
 
 
 def adamw_roofline(torch, K, student):
@@ -352,12 +419,21 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        res = cpu_reference_run(args.ratio, args.latent, max(1, min(args.steps, 3)), min(args.warmup, 1))
+        # a "step" of this arm = one batch-1 training step of the same workload (bounded sample: ~2 s of CPU work each); the
+        # requested K / W are honoured up to a 60-step total so the run stays within a few minutes, and the line reports
+        # what actually ran
+        k_run = max(1, min(args.steps, 40))
+        w_run = max(0, min(args.warmup, 60 - k_run, 5))
+        res = cpu_reference_run(args.ratio, args.latent, k_run, w_run)
+        ref_workload = (f"bounded sample of: {workload} -- here ONE sample per step (batch 1), fp32, CPU: "
+                        f"{res['cores']} host threads, oracle restatement of the reference step")
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "steps": k_run, "warmup": w_run, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                "config": {"workload": workload, "note": "reference CPU path = oracle restatement (diffusers not "
-                           "installable offline); timed steps capped at 3, warm-up at 1 to bound the run"},
+                "config": {"workload": ref_workload, "batch_per_step": 1, "requested_steps": args.steps,
+                           "requested_warmup": args.warmup,
+                           "note": "reference CPU path = oracle restatement (the reference itself needs diffusers, not "
+                                   "installable offline)"},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -525,6 +601,11 @@ def main():
         pass
     tf, conv_ms, conv_desc = gemm_roofline(torch, K, B, L)
     hbm = adamw_roofline(torch, K, student)
+    attn_rf = attention_roofline(torch, K, B, peaks)
+    gemm_class = None
+    if world == 1:      # (an eager step on rank 0 alone would wait for the other ranks' all-reduces)
+        tuner.release_cuda_graph()
+        gemm_class = gemm_class_roofline(torch, _lib, lambda: train_step(0, dev_batches, dev_upper), peaks)
     peak_burst = peaks.get("bf16_tflops", 1590.0)
     step_tf = STEP_TFLOP_PER_SAMPLE.get(round(args.ratio, 2), 2.196) * B / (ms_total / args.steps * 1e-3) if ms_total else 0
     if args.bilevel:   # upper step = 2 teacher fwd + student fwd + bwd = 2*0.804 + 3*fwd_s TFLOP/sample
@@ -547,9 +628,9 @@ def main():
         "roofline_hbm": hbm,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full
-                     # capture profiles/r1_ncu_full_conv960x170_v9.txt (algorithmic bytes: 151.0 MB; the 22 MB output mostly stays in L2)
-                     "traffic": 138.97e6, "traffic_unit": "bytes/launch", "algorithmic_bytes": 151.0e6,
+                     # not measurable from inside the process: the per-round `ncu --set full` capture of this launch is
+                     # committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum) and cited in DESIGN.md
+                     "traffic": None, "algorithmic_bytes": 2.0 * (B * L * L * 960 + 170 * 9 * 960 + B * L * L * 170),
                      "kernel": "b200::gemm_kernel<0,0,true> (tcgen05 cta_group::2 implicit-GEMM conv)",
                      "shape": conv_desc,
                      "ms_per_launch": conv_ms,
@@ -557,6 +638,8 @@ def main():
                      if peaks else "fallback 1590 TFLOP/s, of fallback",
                      "step_algorithmic_tflops": step_tf,
                      "step_frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", 1400.0)},
+        "roofline_step": gemm_class,
+        "roofline_attention": attn_rf,
     }
     if args.bilevel:
         line["config"]["cycle"] = (f"{freq} lower + 1 upper step per cycle, {args.steps // freq} cycle(s) timed; value counts the "
@@ -569,6 +652,8 @@ def main():
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e!r}"}
+    if not args.no_library_baseline and world == 1 and not args.bilevel:
+        line["library_baseline"] = library_baseline_run(args)
     emit(line)
     shutdown()
 

@@ -74,6 +74,9 @@ typedef struct {
   int taps;                        /* 9 (3x3, pad 1) or 1                                                  */
   int flip;                        /* 1: use tap (2-kh, 2-kw) for the shift (dgrad)                        */
   int out_channels;                /* W modes: O                                                           */
+  int no_pad;                      /* ACT modes: 1 = no leading zero padding (window starts AT the pixel; trailing
+                                      out-of-bounds taps still read zeros): diffusers Downsample2D(padding=0), which pads
+                                      (0, 1, 0, 1) and convolves with stride 2.  0 = the usual one-pixel "same" padding  */
 } b200pdm_operand;
 
 typedef struct {
@@ -93,11 +96,19 @@ typedef struct {
   int accumulate;           /* fp32 out only: out += ... (vector atomic adds; split-K allowed)             */
   int splits;               /* accumulate only: fixed split-K factor, 0/1 = planner's choice               */
   int block_n;              /* 0 = choose                                                                  */
+  int geglu;                /* 1: fused GEGLU epilogue.  b = K-major [2N, K] (value rows, then gate rows), bias [2N];
+                               out[M, N] (bf16) = (acc_v + bias_v) * gelu_erf(acc_g + bias_g); no rowbias / residual  */
+  void* aux;                /* geglu: optional bf16 [M, 2N] pre-activations (value | gate), pitch ld_aux, or NULL  */
+  int64_t ld_aux;
 } b200pdm_gemm_desc;
 
 /* Diagnostics: with B200PDM_GEMM_TRACE=1 in the environment every GEMM launch is timed (serialising); this writes the
  * per-shape table (tab separated) to `path` (host string) and clears it. */
 int b200pdm_gemm_trace_dump(const char* path);
+/* The same switch at run time (clears the table when turned on), and the table's totals: summed per-launch CUDA-event time
+ * (ms), algorithmic FLOPs (2 M N K) and launch count -- bench.py's launch-weighted GEMM-class roofline. */
+int b200pdm_gemm_trace_enable(int on);
+int b200pdm_gemm_trace_totals(double* ms, double* flops, int64_t* launches);
 /* Generic launch.  Non-accumulating outputs of small-M problems may be split along K: every split writes its partial tile
  * into its own fp32 slab of `workspace`, a finalize kernel adds the slabs in split order (deterministic) and applies the
  * epilogue.  b200pdm_gemm_workspace() = bytes that plan needs (0 when the planner does not split). */
@@ -112,6 +123,13 @@ size_t b200pdm_linear_fwd_workspace(int64_t M, int64_t N, int64_t K, int out_fp3
 int b200pdm_linear_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias,
                        const void* residual, int64_t ldr, void* out, int64_t ldo, int out_fp32, int64_t M,
                        int64_t N, int64_t K, void* workspace, size_t ws_bytes, b200pdm_stream_t stream);
+/* GEGLU feed-forward input projection with the activation fused into the GEMM epilogue (GEGLUGated.forward,
+ * pdm/models/unet/blocks.py:44-59: `hidden, gate = proj(x).chunk(2, -1); hidden * gelu(gate)`):
+ *   out[M, F] = (x . w[:F]^T + bias[:F]) * gelu_erf(x . w[F:]^T + bias[F:])          w: [2F, K], bias: [2F]
+ * pre (optional, bf16 [M, 2F], pitch ldp): the two pre-activations, saved for b200pdm_geglu_bwd; without it (frozen teacher,
+ * sampling) the projection's 2F-wide output never reaches HBM.                                               */
+int b200pdm_linear_geglu_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out, int64_t ldo,
+                             void* pre, int64_t ldp, int64_t M, int64_t F, int64_t K, b200pdm_stream_t stream);
 /* dx[M,K] = dy[M,N] . w[N,K] (+ residual[M,K]); autograd backward of the call sites above.                 */
 size_t b200pdm_linear_dgrad_workspace(int64_t M, int64_t N, int64_t K);
 int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ldw, const void* residual,
@@ -130,6 +148,12 @@ int b200pdm_conv_fwd(const void* x, int64_t ldx, const void* w, int64_t w_ild, c
                      const float* rowbias, int64_t ld_rowbias, const void* residual, int64_t ldr, void* out,
                      int64_t ldo, int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride,
                      void* workspace, size_t ws_bytes, b200pdm_stream_t stream);
+/* Same, 3x3, with the window anchored at the pixel instead of one before it:
+ *   out[b,ho,wo,:] = sum_tap x[b, ho*s+kh, wo*s+kw, :] . w[:, tap, :]^T + bias      (zeros beyond the right / bottom edge)
+ * = F.pad(x, (0, 1, 0, 1)) followed by a padding-0 convolution: the VAE encoder's Downsample2D (SURVEY 8f-2,
+ * pdm/training/trainer.py:2405).  Forward only (the VAE is frozen).                                           */
+int b200pdm_conv_fwd_nopad(const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias, void* out, int64_t ldo,
+                           int batch, int h_in, int w_in, int c_in, int c_out, int stride, b200pdm_stream_t stream);
 /* dx[b,h,w,:Cin] = sum_tap dy[b, h+1-kh, w+1-kw, :Cout] . w[:, tap, :Cin] (+ residual)  (stride 1 only).    */
 size_t b200pdm_conv_dgrad_workspace(int batch, int h, int w_sp, int c_in, int c_out, int ksize);
 int b200pdm_conv_dgrad(const void* dy, int64_t lddy, const void* w, int64_t w_ild, const void* residual,
@@ -185,6 +209,21 @@ int b200pdm_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk
                           const void* out, int64_t ldo, const void* dout, int64_t lddo, const float* lse, void* dq,
                           int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* workspace, int batch,
                           int heads, int lq, int lk, float scale, b200pdm_stream_t stream);
+/* Fused attention forward with an optional causal mask (query i attends keys <= i): the CLIP text encoder of the
+ * step-front producers (pdm/utils/data_utils.py:155-191 -> transformers CLIPTextModel).          */
+int b200pdm_attention_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                             void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk, float scale,
+                             int causal, b200pdm_stream_t stream);
+/* erf-GELU over a [rows, C] bf16 matrix (CLIP text MLP).                                                    */
+int b200pdm_gelu(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int C, b200pdm_stream_t stream);
+/* CLIPTextEmbeddings: out[b*L + l, :] = token_embedding[ids[b, l], :] + position_embedding[l, :] (fp32 tables, bf16 out). */
+int b200pdm_clip_embed(const int64_t* ids, const float* token_embedding, const float* position_embedding, void* out,
+                       int64_t ldo, int64_t rows, int seq_len, int C, int vocab, b200pdm_stream_t stream);
+/* vae.encode(x).latent_dist.sample() * scaling_factor (pdm/training/trainer.py:2405-2406; diffusers
+ * DiagonalGaussianDistribution): moments = NHWC bf16 [B*hw, 2*Cz] (mean | logvar, logvar clamped to [-30, 20]);
+ * latents (NCHW fp32) = (mean + exp(logvar / 2) * eps) * scaling_factor; eps NCHW fp32 or NULL (mode); mean_out optional. */
+int b200pdm_vae_sample(const void* moments, int64_t ldm, const float* eps, float* latents, float* mean_out, int batch,
+                       int latent_channels, int hw, float scaling_factor, b200pdm_stream_t stream);
 /* Column sums: out[n] += sum_m x[m, n]  (bias gradients).                                                   */
 int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream);
 /* Per-sample column sums: out[r / rows_per_group, n] += x[r, n]  (gradient of the time-embedding broadcast add,

@@ -174,3 +174,25 @@ def test_two_phase_prune_api_matches_direct_construction():
     with pytest.raises(RuntimeError):
         model.set_structure(av)
         model.prune()                                                # pruning twice is an error, as in the reference
+
+
+def test_encoder_state_dict_keys_match_their_dependencies():
+    """The frozen step-front producers carry the state-dict keys and shapes of the dependency classes the reference loads
+    (transformers CLIPTextModel with the SD-2.1 text config; diffusers AutoencoderKL encoder + quant_conv as restated in
+    oracle/vae_restated.py), so real checkpoints load by key."""
+    import torch
+    from transformers import CLIPTextConfig
+    from transformers import CLIPTextModel as HF
+
+    from oracle.vae_restated import AutoencoderKLEncoder
+    from unlearn_ft_b200.pdm.models import AutoencoderKL, CLIPTextModel
+    cfg = CLIPTextConfig(vocab_size=49408, hidden_size=1024, intermediate_size=4096, num_hidden_layers=23, num_attention_heads=16,
+                         max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5, projection_dim=512)
+    with torch.device("meta"):
+        hf = HF(cfg)
+        vo = AutoencoderKLEncoder()
+    mine = CLIPTextModel(device="meta", seed=None)
+    assert {k: tuple(v.shape) for k, v in hf.state_dict().items()} == {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    vae = AutoencoderKL(device="meta", seed=None)
+    assert {k: tuple(v.shape) for k, v in vo.state_dict().items()} == {k: tuple(v.shape) for k, v in vae.state_dict().items()}
+    assert sum(p.numel() for p in vae.parameters()) == 34_163_664

@@ -208,3 +208,28 @@ def test_flash_attention_bwd(B, H, Lq, Lk):
     for name, mine, r in (("dq", dq, qh.grad), ("dk", dk, kh.grad), ("dv", dv, vh.grad)):
         L = r.shape[2]
         assert rel_err(mine, r.transpose(1, 2).reshape(B * L, H * D)) < 3e-2, name
+
+
+@pytest.mark.parametrize("M,Fh,Kd", [(4096, 680, 320), (8192, 1280, 320), (1024, 2720, 1280), (300, 40, 64), (16384, 1360, 640)])
+def test_linear_geglu_fused_epilogue(M, Fh, Kd):
+    """GEGLUGated.forward (reference blocks.py:44-59) as one GEMM with the activation in the epilogue: against torch fp32 on
+    bf16-exact inputs, against the unfused path (linear_fwd + geglu_fwd), and the saved pre-activations against linear_fwd."""
+    import torch.nn.functional as F
+    k = _k()
+    g = torch.Generator(device="cuda").manual_seed(M + Fh)
+    x = k.alloc2d(M, Kd)
+    x.copy_(torch.randn(M, Kd, device="cuda", generator=g))
+    w = (torch.randn(2 * Fh, Kd, device="cuda", generator=g) / Kd ** 0.5).bfloat16()
+    b = torch.randn(2 * Fh, device="cuda", generator=g) * 0.1
+    ref_p = x.float() @ w.float().t() + b
+    h, gt = ref_p.chunk(2, -1)
+    ref = h * F.gelu(gt)
+    y0, none = k.linear_geglu_fwd(x, w, b, save_pre=False)          # frozen-model form: nothing but [M, F] is written
+    assert none is None and y0.shape == (M, Fh)
+    assert rel_err(y0, ref) < 1e-2
+    y1, pre = k.linear_geglu_fwd(x, w, b, save_pre=True)            # trainable form: pre-activations saved for geglu_bwd
+    p_unfused = k.linear_fwd(x, w, bias=b)
+    assert torch.equal(pre, p_unfused)                               # same GEMM, same rounding
+    assert rel_err(y1, ref) < 1e-2
+    y_unfused = k.geglu_fwd(p_unfused)
+    assert rel_err(y1, y_unfused.float()) < 4e-3                     # (erf by A&S 7.1.26 vs erff: at most an ulp of bf16)

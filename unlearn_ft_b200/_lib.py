@@ -27,6 +27,7 @@ class Operand(C.Structure):
         ("mode", i32), ("ptr", c_p), ("ld", i64), ("bs1", i64), ("bs2", i64),
         ("batch", i32), ("h_in", i32), ("w_in", i32), ("channels", i32),
         ("h_out", i32), ("w_out", i32), ("stride", i32), ("taps", i32), ("flip", i32), ("out_channels", i32),
+        ("no_pad", i32),
     ]
 
 
@@ -39,6 +40,7 @@ class GemmDesc(C.Structure):
         ("bias", c_p), ("rowbias", c_p), ("ld_rowbias", i64), ("rows_per_group", i32),
         ("residual", c_p), ("ldr", i64), ("rbs1", i64), ("rbs2", i64),
         ("alpha", f32), ("accumulate", i32), ("splits", i32), ("block_n", i32),
+        ("geglu", i32), ("aux", c_p), ("ld_aux", i64),
     ]
 
 
@@ -57,15 +59,19 @@ _SIGS = {
     "b200pdm_launch_count": [],
     "b200pdm_gemm_plan": [i64, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int)],
     "b200pdm_gemm_trace_dump": [C.c_char_p],
+    "b200pdm_gemm_trace_enable": [i32],
+    "b200pdm_gemm_trace_totals": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)],
     "b200pdm_gemm_workspace": [C.POINTER(GemmDesc)],
     "b200pdm_gemm": [C.POINTER(GemmDesc), c_p, sz, c_p],
     "b200pdm_linear_fwd_workspace": [i64, i64, i64, i32],
     "b200pdm_linear_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i32, i64, i64, i64, c_p, sz, c_p],
+    "b200pdm_linear_geglu_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, i64, i64, i64, c_p],
     "b200pdm_linear_dgrad_workspace": [i64, i64, i64],
     "b200pdm_linear_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i64, i64, i64, c_p, sz, c_p],
     "b200pdm_linear_wgrad": [c_p, i64, c_p, i64, c_p, i64, i64, i64, i64, c_p],
     "b200pdm_conv_fwd_workspace": [i32, i32, i32, i32, i32, i32, i32],
     "b200pdm_conv_fwd": [c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p, sz, c_p],
+    "b200pdm_conv_fwd_nopad": [c_p, i64, c_p, i64, c_p, c_p, i64, i32, i32, i32, i32, i32, i32, c_p],
     "b200pdm_conv_dgrad_workspace": [i32, i32, i32, i32, i32, i32],
     "b200pdm_conv_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, c_p, sz, c_p],
     "b200pdm_conv_wgrad": [c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p],
@@ -79,6 +85,10 @@ _SIGS = {
     "b200pdm_attention_fwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i32, i32, i32, i32, f32, c_p],
     "b200pdm_attention_bwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, c_p,
                               i32, i32, i32, i32, f32, c_p],
+    "b200pdm_attention_fwd_ex": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i32, i32, i32, i32, f32, i32, c_p],
+    "b200pdm_gelu": [c_p, i64, c_p, i64, i64, i32, c_p],
+    "b200pdm_clip_embed": [c_p, c_p, c_p, c_p, i64, i64, i32, i32, i32, c_p],
+    "b200pdm_vae_sample": [c_p, i64, c_p, c_p, c_p, i32, i32, i32, f32, c_p],
     "b200pdm_colsum": [c_p, i64, c_p, i64, i32, c_p],
     "b200pdm_colsum_grouped": [c_p, i64, c_p, i64, i64, i32, i32, c_p],
     "b200pdm_cast_f32_to_bf16": [c_p, c_p, i64, c_p],

@@ -40,6 +40,7 @@ struct AttnFwdParams {
   bf16* out;
   int64_t ldo;
   float* lse;  // [B, H, Lq] log2-domain log-sum-exp (may be null)
+  int causal;  // 1: query i attends keys <= i (CLIP text encoder); masked per row in the ragged path
 #ifdef B200PDM_DIAG
   long long* dbg;  // optional phase timers of CTA 0 / warp 2 (`make diag`)
 #else
@@ -189,7 +190,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int sw = r & 7;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < p.nkv; ++j) {
-      const int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
+      int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
+      if (p.causal) valid = min(valid, q0 + t * kQ + r - j * kKV + 1);   // ... that this row may attend (can be <= 0)
       const bool prof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 64 || threadIdx.x == 192);
       const int pslot = (threadIdx.x == 64) ? 0 : 8;
       long long tp0 = prof ? clock64() : 0;
@@ -216,7 +218,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         }
       }
-      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+      float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+      if (valid <= 0) m_tile = (j == 0) ? 0.f : m;      // (causal: nothing to attend in this block -- all its p are 0)
       if (j == 0) {
         m = m_tile;
       } else {
@@ -337,9 +340,17 @@ static int make_qkv_map(CUtensorMap* map, const void* ptr, int64_t ld, int B, in
 
 using namespace b200;
 
+extern "C" int b200pdm_attention_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                        void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk,
+                                        float scale, int causal, b200pdm_stream_t stream_);
 extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                      void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk,
                                      float scale, b200pdm_stream_t stream_) {
+  return b200pdm_attention_fwd_ex(q, ldq, k, ldk, v, ldv, out, ldo, lse, batch, heads, lq, lk, scale, 0, stream_);
+}
+extern "C" int b200pdm_attention_fwd_ex(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                        void* out, int64_t ldo, float* lse, int batch, int heads, int lq, int lk,
+                                        float scale, int causal, b200pdm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!q || !k || !v || !out || batch <= 0 || heads <= 0 || lq <= 0 || lk <= 0) return B200PDM_ERR_ARG;
   if (ldo % 8 || (reinterpret_cast<uintptr_t>(out) & 15)) {
@@ -357,6 +368,7 @@ extern "C" int b200pdm_attention_fwd(const void* q, int64_t ldq, const void* k, 
   p.B = batch, p.H = heads, p.Lq = lq, p.Lk = lk, p.nkv = (lk + kKV - 1) / kKV;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<bf16*>(out), p.ldo = ldo, p.lse = lse;
+  p.causal = causal ? 1 : 0;
 #ifdef B200PDM_DIAG
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;

@@ -446,6 +446,20 @@ __device__ __forceinline__ float silu_grad_f(float x) {
   return s * (1.f + x * (1.f - s));
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU for the fused GEMM epilogue, where instruction count matters: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7
+// absolute, i.e. fp32-exact for what is rounded to bf16 next): one reciprocal, one exponential, a degree-5 Horner chain.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float erf_abs = fmaf(-poly * t, e, 1.f);          // erf(|x| / sqrt 2)
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float gelu_erf_grad_f(float x) {
   const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);

@@ -58,6 +58,59 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ d, int64_t ldd, const 
   }
 }
 
+// ---------------------------------------------------------------- step-front producers (frozen encoders)
+// erf-GELU over a [rows, C] bf16 matrix (CLIP text MLP: transformers CLIPMLP, hidden_act "gelu").
+__global__ void gelu_kernel(const bf16* __restrict__ x, int64_t ldx, bf16* __restrict__ y, int64_t ldy, int64_t rows, int cvec) {
+  pdl_trigger();
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cvec;
+    const int c0 = (int)(i - r * cvec) * 8;
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + r * ldx + c0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
+    *reinterpret_cast<bf16x8*>(y + r * ldy + c0) = pack8(v);
+  }
+}
+// CLIPTextEmbeddings: out[b*L + l, :] = token_embedding[ids[b, l], :] + position_embedding[l, :]   (fp32 tables, bf16 out)
+__global__ void clip_embed_kernel(const long long* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                                  bf16* __restrict__ out, int64_t ldo, int64_t rows, int L, int C, int vocab) {
+  pdl_trigger();
+  const int cvec = C >> 2;
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cvec;
+    const int c0 = (int)(i - r * cvec) * 4;
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float4 a = *reinterpret_cast<const float4*>(tok + id * C + c0);
+    const float4 b = *reinterpret_cast<const float4*>(pos + (r % L) * (int64_t)C + c0);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a.x + b.x, a.y + b.y), hi = __floats2bfloat162_rn(a.z + b.z, a.w + b.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo), pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + r * ldo + c0) = pk;
+  }
+}
+// AutoencoderKL.encode(...).latent_dist.sample() * scaling_factor (diffusers DiagonalGaussianDistribution): moments = NHWC
+// bf16 [B*hw, 2*Cz] (mean | logvar); latents NCHW fp32 = (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps) * scale.
+__global__ void vae_sample_kernel(const bf16* __restrict__ mom, int64_t ldm, const float* __restrict__ eps, float* __restrict__ z,
+                                  float* __restrict__ mean_out, int B, int Cz, int hw, float scale) {
+  pdl_trigger();
+  const int64_t total = (int64_t)B * Cz * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw);
+    const int c = (int)((i / hw) % Cz);
+    const int b = (int)(i / ((int64_t)hw * Cz));
+    const bf16* m = mom + ((int64_t)b * hw + p) * ldm;
+    const float mu = __bfloat162float(m[c]);
+    const float lv = fminf(fmaxf(__bfloat162float(m[Cz + c]), -30.f), 20.f);
+    const float sd = __expf(0.5f * lv);
+    z[i] = (mu + sd * (eps ? eps[i] : 0.f)) * scale;
+    if (mean_out) mean_out[i] = mu;
+  }
+}
+
 // ---------------------------------------------------------------- row softmax (frozen encoders: head dims other than 64)
 // one block per row; fp32 scores in, bf16 probabilities out. p = softmax(scale * s).
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf16* __restrict__ p, int64_t ldp, int cols,
@@ -411,6 +464,31 @@ int b200pdm_geglu_bwd(const void* dout, int64_t lddo, const void* proj, int64_t 
   const int fvec = F / 8;
   launch_pdl(geglu_bwd_kernel, grid_for(rows * fvec, 256), 256, 0, STREAM, CBF(dout), lddo, CBF(proj), ldp, BF(dproj), lddp, rows,
                                                                   F, fvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_gelu(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int C, b200pdm_stream_t stream) {
+  if (C % 8 || ldx % 8 || ldy % 8) return B200PDM_ERR_UNSUPPORTED;
+  launch_pdl(gelu_kernel, grid_for(rows * (C / 8), 256), 256, 0, STREAM, CBF(x), ldx, BF(y), ldy, rows, C / 8);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_clip_embed(const int64_t* ids, const float* token_embedding, const float* position_embedding, void* out,
+                       int64_t ldo, int64_t rows, int seq_len, int C, int vocab, b200pdm_stream_t stream) {
+  if (!ids || !token_embedding || !position_embedding || !out || C % 4 || ldo % 4 || seq_len <= 0) return B200PDM_ERR_ARG;
+  launch_pdl(clip_embed_kernel, grid_for(rows * (C / 4), 256), 256, 0, STREAM, reinterpret_cast<const long long*>(ids),
+             token_embedding, position_embedding, BF(out), ldo, rows, seq_len, C, vocab);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_vae_sample(const void* moments, int64_t ldm, const float* eps, float* latents, float* mean_out, int batch,
+                       int latent_channels, int hw, float scaling_factor, b200pdm_stream_t stream) {
+  if (!moments || !latents || batch <= 0 || latent_channels <= 0 || hw <= 0) return B200PDM_ERR_ARG;
+  launch_pdl(vae_sample_kernel, grid_for((int64_t)batch * latent_channels * hw, 256), 256, 0, STREAM, CBF(moments), ldm, eps,
+             latents, mean_out, batch, latent_channels, hw, scaling_factor);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

@@ -150,6 +150,7 @@ struct OpDev {
   int Wo, HoWo;  // output grid (pixel decomposition)
   int stride;
   int flip;
+  int pad;       // leading zero padding of the convolution window (1 = "same" 3x3; 0 = diffusers Downsample2D(padding=0))
   FastDiv fd_Wo, fd_HoWo;
 };
 
@@ -190,6 +191,11 @@ struct GemmDev {
   static constexpr int dbg_mode = 0;
 #endif
   int epi_groups;  // epilogue warpgroups: group g takes every epi_groups-th 32-column chunk of a tile
+  // fused GEGLU epilogue (B = [2F, K] projection weight): a tile's accumulator holds the VALUE columns of bh = block_n / 2
+  // hidden units in [0, bh) and their GATE columns in [bh, 2 bh); out[:, f] = value * gelu_erf(gate)
+  int geglu_F;     // F (0 = off)
+  bf16* aux;       // optional [M, 2F] pre-activations (value | gate) saved for the backward pass
+  int64_t ld_aux;
 };
 
 // Where a tile sits: decoded once per tile by each role.
@@ -283,7 +289,7 @@ __device__ __forceinline__ ACursor make_a_cursor(const OpDev& op, const TileCoor
     const int rem = pix0 - n0 * op.HoWo;
     const int h0 = fdiv(rem, op.fd_Wo);
     const int w0 = rem - h0 * op.Wo;
-    c.c1 = w0 * op.stride - 1, c.c2 = h0 * op.stride - 1, c.c3 = n0;
+    c.c1 = w0 * op.stride - op.pad, c.c2 = h0 * op.stride - op.pad, c.c3 = n0;
   } else {
     c.c1 = m_tile * kBlockM, c.c2 = tc.z1, c.c3 = tc.z2;
   }
@@ -321,7 +327,16 @@ struct BCursor {
 template <bool PAIR>
 __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, uint8_t* dst, uint64_t* bar,
                                        const BCursor& c, const TileCoord& tc, int block_n, int kb, int cb, int tap,
-                                       int cluster, int rank) {
+                                       int cluster, int rank, int geglu_F = 0) {
+  if (geglu_F) {   // K-major [2F, K] weight: value rows [n0, n0 + bh) and gate rows [F + n0, F + n0 + bh), bh = block_n / 2
+    if (PAIR) {    // cta_group::2 splits B along N: CTA 0 supplies the value half, CTA 1 the gate half
+      tma_load_4d_2sm(dst, map, bar, kb * kBlockK, c.n0 + rank * geglu_F, tc.z1, tc.z2);
+    } else {
+      tma_load_4d(dst, map, bar, kb * kBlockK, c.n0, tc.z1, tc.z2);
+      tma_load_4d(dst + (block_n / 2) * 128, map, bar, kb * kBlockK, c.n0 + geglu_F, tc.z1, tc.z2);
+    }
+    return;
+  }
   const int parts = PAIR ? 2 : cluster;
   const uint16_t mask = static_cast<uint16_t>((1u << cluster) - 1);
   const int rows = block_n / parts;            // K-major slice
@@ -372,7 +387,7 @@ __device__ __forceinline__ void load_b(const OpDev& op, const CUtensorMap* map, 
       const int rem = pix0 - b0 * op.HoWo;
       const int h0 = fdiv(rem, op.fd_Wo);
       const int w0 = rem - h0 * op.Wo;
-      const int cw = w0 * op.stride + c.kw - 1, ch = h0 * op.stride + c.kh - 1;
+      const int cw = w0 * op.stride + c.kw - op.pad, ch = h0 * op.stride + c.kh - op.pad;
       for (int j = 0; j < atoms; ++j) {
         if (PAIR)
           tma_load_4d_2sm(dst + j * kAtomBytes, map, bar, c.n0 + 64 * (j0 + j), cw, ch, b0);
@@ -469,7 +484,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const ACursor ac0 = make_a_cursor(p.a, tc, tc.m_tile);
         const ACursor ac1 = make_a_cursor(p.a, tc, tc.m_tile + cluster);   // second sub-tile of a tall tile
         BCursor bc;
-        bc.n0 = tc.nt * p.block_n;
+        bc.n0 = p.geglu_F ? tc.nt * (p.block_n / 2) : tc.nt * p.block_n;
         tap_offsets(p.b.taps, tc.grp, 0, &bc.kh, &bc.kw);
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
@@ -487,13 +502,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac0, kb, cb, tap);
                 if (p.m_sub == 2) load_a<PAIR>(p.a, &tma_a, a_dst + kStageABytes, &full_bar[stage], ac1, kb, cb, tap);
               }
-              if (b_bytes) load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank);
+              if (b_bytes) load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank, p.geglu_F);
             } else {
               // pair: both CTAs' loads complete_tx on the LEADER's full barrier, which expects the bytes of the whole pair
               if (!pair || rank == 0) mbar_expect_tx(&full_bar[stage], (pair ? 2 : 1) * tx_bytes);
               DBG_WAIT(6, load_a<PAIR>(p.a, &tma_a, a_dst, &full_bar[stage], ac0, kb, cb, tap);
                        if (p.m_sub == 2) load_a<PAIR>(p.a, &tma_a, a_dst + kStageABytes, &full_bar[stage], ac1, kb, cb, tap);
-                       load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank));
+                       load_b<PAIR>(p.b, &tma_b, b_dst, &full_bar[stage], bc, tc, p.block_n, kb, cb, tap, mcast, rank, p.geglu_F));
             }
           }
           if (++tap == p.k_taps) tap = 0, ++cb;
@@ -600,6 +615,95 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t unit = 0;   // accumulator units drained so far (slot = unit & 1, phase = (unit >> 1) & 1)
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
+        if (p.geglu_F) {
+          // ---------------- fused GEGLU epilogue (see GemmDev::geglu_F) ----------------
+          const int bh = p.block_n >> 1;
+          const int f_base = tc.nt * bh;
+          const int n_f = min(bh, p.geglu_F - f_base);           // valid hidden units of this tile
+          for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
+            const int acc = unit & 1;
+            const uint32_t acc_phase = (unit >> 1) & 1;
+            const int row = (tc.m_tile + sub * cluster) * kBlockM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            {   // bias of the tile's accumulator columns -> this warp's smem slice (value half, then gate half)
+              float b8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = lane * 8 + j;
+                const int cf = c < bh ? c : c - bh;
+                b8[j] = (p.bias && c < p.block_n && cf < n_f) ? __ldg(p.bias + f_base + cf + (c < bh ? 0 : p.geglu_F)) : 0.f;
+              }
+              __syncwarp();
+              sts128(cb_s + lane * 32, __float_as_uint(b8[0]), __float_as_uint(b8[1]), __float_as_uint(b8[2]), __float_as_uint(b8[3]));
+              sts128(cb_s + lane * 32 + 16, __float_as_uint(b8[4]), __float_as_uint(b8[5]), __float_as_uint(b8[6]), __float_as_uint(b8[7]));
+              __syncwarp();
+            }
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+            bf16* o_row = reinterpret_cast<bf16*>(p.out) + static_cast<int64_t>(row) * p.ldo + f_base;
+            bf16* a_row = p.aux ? p.aux + static_cast<int64_t>(row) * p.ld_aux + f_base : nullptr;
+            const bool o16 = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.ldo % 8 == 0);
+            const bool a16 = p.aux && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux % 8 == 0) && (p.geglu_F % 8 == 0);
+            auto store32 = [&](bf16* dst, const float* f, int nv, bool vec16) {
+              if (nv == 32 && vec16) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                  uint32_t pk[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 2 * j], f[g4 * 8 + 2 * j + 1]);
+                    pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                  }
+                  *reinterpret_cast<uint4*>(dst + g4 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) dst[j] = __float2bfloat16(f[j]);
+              }
+            };
+            for (int c0 = wg * 32; c0 < n_f; c0 += 32 * p.epi_groups) {
+              const int nv = min(32, n_f - c0);
+              uint32_t vh[32], vg[32];
+              tmem_ld_32x32(taddr + c0, vh);
+              tmem_ld_32x32(taddr + bh + c0, vg);
+              tmem_ld_wait();
+              float h[32], gt[32];
+#pragma unroll
+              for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 bh4 = lds128f(cb_s + (c0 + g4 * 4) * 4), bg4 = lds128f(cb_s + (bh + c0 + g4 * 4) * 4);
+                h[4 * g4] = __uint_as_float(vh[4 * g4]) + bh4.x, h[4 * g4 + 1] = __uint_as_float(vh[4 * g4 + 1]) + bh4.y;
+                h[4 * g4 + 2] = __uint_as_float(vh[4 * g4 + 2]) + bh4.z, h[4 * g4 + 3] = __uint_as_float(vh[4 * g4 + 3]) + bh4.w;
+                gt[4 * g4] = __uint_as_float(vg[4 * g4]) + bg4.x, gt[4 * g4 + 1] = __uint_as_float(vg[4 * g4 + 1]) + bg4.y;
+                gt[4 * g4 + 2] = __uint_as_float(vg[4 * g4 + 2]) + bg4.z, gt[4 * g4 + 3] = __uint_as_float(vg[4 * g4 + 3]) + bg4.w;
+              }
+              if (!row_ok) continue;
+              if (a_row) {   // pre-activations for the backward pass, rounded exactly as the unfused path stored them
+                store32(a_row + c0, h, nv, a16);
+                store32(a_row + p.geglu_F + c0, gt, nv, a16);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {   // ... and the product is formed from the ROUNDED values, like geglu_fwd did
+                  h[j] = __bfloat162float(__float2bfloat16(h[j]));
+                  gt[j] = __bfloat162float(__float2bfloat16(gt[j]));
+                }
+              }
+              float y[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) y[j] = h[j] * gelu_erf_fast(gt[j]);
+              store32(o_row + c0, y, nv, o16);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (pair && rank != 0)
+                mbar_arrive_remote(&tempty_bar[acc], 0);
+              else
+                mbar_arrive(&tempty_bar[acc]);
+            }
+          }
+          continue;
+        }
         const int col_base = tc.nt * p.block_n;                // within the N group
         const int n_cols = min(p.block_n, p.n_per_group - col_base);   // valid columns of this tile
         for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
@@ -617,6 +721,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const float* rb_row = (p.rowbias && !rb_uniform && row_ok)
                                     ? p.rowbias + static_cast<int64_t>(fdiv(row, p.fd_rows_per_group)) * p.ld_rowbias + col_base
                                     : nullptr;
+          // The residual operand of the NEXT unit is pulled into L2 now (one 128-byte line per prefetch, this lane's row):
+          // its loads sit on the unit's critical path -- on the small-K projections (K <= 1280: epilogue-bound, the
+          // accumulator is ready before the previous unit has drained) every chunk otherwise exposes an HBM round trip.
+          if (p.residual && wg == 0) {
+            int nt_t = t, nt_sub = sub + 1;
+            if (nt_sub == p.m_sub) nt_t = t + tile_step, nt_sub = 0;
+            if (nt_t < total_tiles) {
+              const TileCoord nc = (nt_t == t) ? tc : decode_tile(p, nt_t, tiles_per_split, tiles_n, cluster, rank);
+              const int nrow = (nc.m_tile + nt_sub * cluster) * kBlockM + q * 32 + lane;
+              if (nrow < p.M) {
+                const int ncol = nc.nt * p.block_n;
+                const int ncols = min(p.block_n, p.n_per_group - ncol);
+                const char* r0 = reinterpret_cast<const char*>(p.residual + nc.z1 * p.rbs1 + nc.z2 * p.rbs2 +
+                                                               static_cast<int64_t>(nrow) * p.ldr + ncol);
+                const char* r1 = r0 + ncols * 2;
+                for (const char* a = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(r0) & ~uintptr_t(127)); a < r1; a += 128)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+              }
+            }
+          }
           if (use_cb) {
             const int row_w = m_tile * kBlockM + q * 32;   // first row of the warp
             const float* rbw = (rb_uniform && row_w < p.M)
@@ -847,13 +971,13 @@ struct Plan {
   double cost = 1e30;
 };
 static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, int kblocks, bool can_split,
-                      bool split_needs_finalize, int fixed_bn, int fixed_splits = 0) {
+                      bool split_needs_finalize, int fixed_bn, int fixed_splits = 0, int bn_step = 0) {
   static int env_msub = -1;
   if (env_msub < 0) {
     const char* e = getenv("B200PDM_MSUB");
     env_msub = e ? atoi(e) : 0;
   }
-  const int g = b_mn ? 64 : 16;
+  const int g = bn_step > 0 ? bn_step : (b_mn ? 64 : 16);   // (fused GEGLU: halves of 32-column chunks -> steps of 64)
   const int n_pad = static_cast<int>((n + g - 1) / g * g);
   static const int split_cands[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
   Plan best;
@@ -902,6 +1026,7 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
   dev->taps = op.taps > 0 ? op.taps : 1;
   dev->stride = op.stride > 0 ? op.stride : 1;
   dev->flip = op.flip;
+  dev->pad = op.no_pad ? 0 : 1;
   const int rows = is_a ? kBlockM : block_n / cluster;   // K-major B: each CTA loads (and multicasts) its slice
   uint64_t dims[5], str[5];
   uint32_t box[5], es[5] = {1, 1, 1, 1, 1};
@@ -1021,10 +1146,10 @@ struct TraceRow {
   double ms = 0, flops = 0;
 };
 static std::map<std::string, TraceRow> g_trace;
+static int g_trace_on = -1;
 static int trace_on() {
-  static int on = -1;
-  if (on < 0) on = getenv("B200PDM_GEMM_TRACE") ? 1 : 0;
-  return on;
+  if (g_trace_on < 0) g_trace_on = getenv("B200PDM_GEMM_TRACE") ? 1 : 0;
+  return g_trace_on;
 }
 
 // Shape of the tile problem a descriptor poses + the plan chosen for it (shared by the launch and the workspace query, so
@@ -1039,7 +1164,7 @@ static int shape_and_plan(const b200pdm_gemm_desc* d, bool have_workspace, Shape
   s->a_mn = d->a.mode == B200PDM_OP_MN2D;
   s->b_mn = d->b.mode == B200PDM_OP_MN2D || d->b.mode == B200PDM_OP_CONV_WT || d->b.mode == B200PDM_OP_CONV_ACT_MN;
   s->Z1 = d->Z1 > 0 ? d->Z1 : 1, s->Z2 = d->Z2 > 0 ? d->Z2 : 1;
-  s->n_groups = 1, s->n_per_group = static_cast<int>(d->N);
+  s->n_groups = 1, s->n_per_group = static_cast<int>(d->geglu ? 2 * d->N : d->N);   // GEGLU: value + gate columns
   if (d->b.mode == B200PDM_OP_CONV_ACT_MN) {   // conv wgrad: one N group per tap
     s->n_groups = d->b.taps > 0 ? d->b.taps : 1;
     s->n_per_group = d->b.channels;
@@ -1061,7 +1186,9 @@ static int shape_and_plan(const b200pdm_gemm_desc* d, bool have_workspace, Shape
   s->acc_out = d->out_fp32 && d->accumulate;
   const bool slabs_ok = have_workspace && !s->acc_out && s->Z == 1 && s->n_groups == 1 &&
                         (int64_t)d->M * d->N * 4 <= (64ll << 20);
-  if (d->splits > 1 && (s->acc_out || slab_pass))   // split factor fixed by the caller (accumulating outputs) / the slab pass
+  if (d->geglu)   // one tile = bh value + bh gate columns of the same hidden units; never split along K
+    s->plan = plan_gemm(s->n_per_group, 1, false, s->tiles_m, s->Z, s->kblocks, false, false, d->block_n, 0, 64);
+  else if (d->splits > 1 && (s->acc_out || slab_pass))   // split factor fixed by the caller (accumulating outputs) / the slab pass
     s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, false, false, d->block_n, d->splits);
   else
     s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, s->acc_out || slabs_ok,
@@ -1069,6 +1196,13 @@ static int shape_and_plan(const b200pdm_gemm_desc* d, bool have_workspace, Shape
   if (s->plan.bn <= 0) {
     set_err("gemm: no valid tile plan (bad block_n?)");
     return B200PDM_ERR_ARG;
+  }
+  {   // normalise the split factor to what the kernel will really run (ceil division can leave the last splits empty): the
+      // slab count the finalize pass adds up must equal the number of slabs that get written
+    int sp = s->plan.splits > s->kblocks ? s->kblocks : s->plan.splits;
+    if (sp < 1) sp = 1;
+    const int per = cdiv(s->kblocks, sp);
+    s->plan.splits = cdiv(s->kblocks, per);
   }
   s->ldws = s->slab = 0;
   if (s->plan.splits > 1 && !s->acc_out && !slab_pass) {
@@ -1090,6 +1224,11 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
                        int64_t split_stride) {
   if (!d || !d->a.ptr || !d->b.ptr || !d->out) {
     set_err("gemm: null pointer");
+    return B200PDM_ERR_ARG;
+  }
+  if (d->geglu && (d->a.mode != B200PDM_OP_K2D || d->b.mode != B200PDM_OP_K2D || d->out_fp32 || d->rowbias || d->residual ||
+                   d->accumulate || (d->Z1 > 1) || (d->Z2 > 1))) {
+    set_err("gemm: the fused GEGLU epilogue takes plain K-major operands, a bf16 output and an optional bias only");
     return B200PDM_ERR_ARG;
   }
   Shaped sh;
@@ -1156,7 +1295,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
   CUtensorMap map_a, map_b;
   int rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2);
   if (rc) return rc;
-  rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->N, d->K, Z1, Z2, cluster);
+  // (GEGLU: the weight has 2F rows and is always fetched in half-tile boxes, one for the value and one for the gate rows)
+  rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->geglu ? 2 * d->N : d->N, d->K, Z1, Z2, d->geglu ? 2 : cluster);
   if (rc) return rc;
 
   {
@@ -1213,6 +1353,9 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
   p.rbs2 = d->rbs2;
   p.alpha = d->alpha;
   p.accumulate = d->accumulate;
+  p.geglu_F = d->geglu ? static_cast<int>(d->N) : 0;
+  p.aux = reinterpret_cast<bf16*>(d->aux);
+  p.ld_aux = d->ld_aux;
 #ifdef B200PDM_DIAG
   static long long* dbg_buf = nullptr;
   static int dbg_on = -1;
@@ -1354,6 +1497,20 @@ int b200pdm_gemm_plan(int64_t n, int n_groups, int b_mn, int tiles_m, int Z, int
   return B200PDM_OK;
 }
 
+int b200pdm_gemm_trace_enable(int on) {
+  g_trace_on = on ? 1 : 0;
+  if (on) g_trace.clear();
+  return B200PDM_OK;
+}
+int b200pdm_gemm_trace_totals(double* ms, double* flops, int64_t* launches) {
+  double m = 0, f = 0;
+  int64_t n = 0;
+  for (auto& kv : g_trace) m += kv.second.ms, f += kv.second.flops, n += kv.second.count;
+  if (ms) *ms = m;
+  if (flops) *flops = f;
+  if (launches) *launches = n;
+  return B200PDM_OK;
+}
 int b200pdm_gemm_trace_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) return B200PDM_ERR_ARG;
@@ -1397,12 +1554,12 @@ static void desc_linear_dgrad(b200pdm_gemm_desc& d, const void* dy, int64_t lddy
 }
 static void desc_conv_fwd(b200pdm_gemm_desc& d, const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias,
                           const float* rowbias, int64_t ld_rowbias, const void* residual, int64_t ldr, void* out, int64_t ldo,
-                          int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride) {
+                          int batch, int h_in, int w_in, int c_in, int c_out, int ksize, int stride, int no_pad = 0) {
   const int h_out = h_in / stride, w_out = w_in / stride;
   memset(&d, 0, sizeof(d));
   d.a.mode = B200PDM_OP_CONV_ACT, d.a.ptr = x, d.a.ld = ldx;
   d.a.batch = batch, d.a.h_in = h_in, d.a.w_in = w_in, d.a.channels = c_in;
-  d.a.h_out = h_out, d.a.w_out = w_out, d.a.stride = stride, d.a.taps = ksize * ksize;
+  d.a.h_out = h_out, d.a.w_out = w_out, d.a.stride = stride, d.a.taps = ksize * ksize, d.a.no_pad = no_pad;
   d.b.mode = B200PDM_OP_CONV_W, d.b.ptr = w, d.b.ld = w_ild, d.b.channels = c_in, d.b.out_channels = c_out;
   d.b.taps = ksize * ksize;
   d.M = (int64_t)batch * h_out * w_out, d.N = c_out, d.K = (int64_t)ksize * ksize * c_in, d.Z1 = 1, d.Z2 = 1;
@@ -1452,6 +1609,14 @@ int b200pdm_linear_dgrad(const void* dy, int64_t lddy, const void* w, int64_t ld
   return launch_gemm(&d, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int b200pdm_linear_geglu_fwd(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* out, int64_t ldo,
+                             void* pre, int64_t ldp, int64_t M, int64_t F, int64_t K, b200pdm_stream_t stream) {
+  b200pdm_gemm_desc d;
+  desc_linear_fwd(d, x, ldx, w, ldw, bias, nullptr, 0, out, ldo, 0, M, F, K);
+  d.geglu = 1, d.aux = pre, d.ld_aux = ldp;
+  return launch_gemm(&d, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int b200pdm_linear_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw, int64_t M,
                          int64_t N, int64_t K, b200pdm_stream_t stream) {
   // dw[N,K] += dy[M,N]^T . x[M,K]: reduction over M; A(m'=n, k'=m) = dy[m][n] MN-major, B(n'=k, k'=m) = x[m][k] MN-major.
@@ -1483,6 +1648,14 @@ int b200pdm_conv_fwd(const void* x, int64_t ldx, const void* w, int64_t w_ild, c
   desc_conv_fwd(d, x, ldx, w, w_ild, bias, rowbias, ld_rowbias, residual, ldr, out, ldo, batch, h_in, w_in, c_in, c_out, ksize,
                 stride);
   return launch_gemm(&d, workspace, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b200pdm_conv_fwd_nopad(const void* x, int64_t ldx, const void* w, int64_t w_ild, const float* bias, void* out, int64_t ldo,
+                           int batch, int h_in, int w_in, int c_in, int c_out, int stride, b200pdm_stream_t stream) {
+  if (stride != 1 && stride != 2) return B200PDM_ERR_UNSUPPORTED;
+  b200pdm_gemm_desc d;
+  desc_conv_fwd(d, x, ldx, w, w_ild, bias, nullptr, 0, nullptr, 0, out, ldo, batch, h_in, w_in, c_in, c_out, 3, stride, 1);
+  return launch_gemm(&d, nullptr, 0, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t b200pdm_conv_dgrad_workspace(int batch, int h, int w_sp, int c_in, int c_out, int ksize) {

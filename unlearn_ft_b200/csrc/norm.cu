@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256, (MAXV <= 2 ? 2 : 1))
 ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const bf16* __restrict__ res, int64_t ldr, bf16* __restrict__ dx, int64_t lddx, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block) {
+              float* __restrict__ dbeta, int64_t rows, int C, int rows_per_block, int vec_red) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   extern __shared__ float sh[];  // dgamma[C], dbeta[C]
   float* sdg = sh;
@@ -450,9 +450,23 @@ ln_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict_
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&dgamma[i], sdg[i]);
-    atomicAdd(&dbeta[i], sdb[i]);
+  // block partials -> global.  One 128-bit reduction per four channels (C % 8 == 0): with one resident wave of blocks this is
+  // C / 2 vector atomics per block instead of the 2 C scalar ones per block over two waves that made the C = 1280 backward
+  // atomics-bound (round 1: 758 k scalar atomics on 2560 addresses for a 31 MB problem, 0.18 of HBM bandwidth).
+  if (vec_red) {
+    for (int i = threadIdx.x * 4; i < C; i += blockDim.x * 4) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + i), "f"(sdg[i]), "f"(sdg[i + 1]), "f"(sdg[i + 2]),
+                   "f"(sdg[i + 3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + i), "f"(sdb[i]), "f"(sdb[i + 1]), "f"(sdb[i + 2]),
+                   "f"(sdb[i + 3])
+                   : "memory");
+    }
+  } else {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(&dgamma[i], sdg[i]);
+      atomicAdd(&dbeta[i], sdb[i]);
+    }
   }
 }
 
@@ -602,9 +616,10 @@ int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
     set_err("layernorm_bwd: C must be a multiple of 8 and <= 1280", "");
     return B200PDM_ERR_UNSUPPORTED;
   }
-  int blocks = 148 * (C <= 512 ? 2 : 1) * 2;   // two waves of the resident blocks
+  int blocks = 148 * (C <= 512 ? 2 : 1);       // one resident wave (launch bounds: 2 blocks / SM up to C = 512, else 1)
   int rows_per_block = (int)((rows + blocks - 1) / blocks);
   if (rows_per_block < 8) rows_per_block = 8;
+  const int vec_red = ((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0;
   blocks = (int)((rows + rows_per_block - 1) / rows_per_block);
   const size_t sh = sizeof(float) * 2 * C;
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
@@ -614,13 +629,13 @@ int b200pdm_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   if (residual && ldr % 8) return B200PDM_ERR_UNSUPPORTED;
   if (C <= 8 * 32 * 2)
     launch_pdl(ln_bwd_kernel<2, 2>, blocks, 256, sh, stream, dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
-                                                    dbeta, rows, C, rows_per_block);
+                                                    dbeta, rows, C, rows_per_block, vec_red);
   else if (C <= 8 * 32 * 3)
     launch_pdl(ln_bwd_kernel<3, 1>, blocks, 256, sh, stream, dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
-                                                    dbeta, rows, C, rows_per_block);
+                                                    dbeta, rows, C, rows_per_block, vec_red);
   else
     launch_pdl(ln_bwd_kernel<5, 1>, blocks, 256, sh, stream, dyb, lddy, xb, ldx, gamma, mean, rstd, rb, ldr, dxb, lddx, dgamma,
-                                                    dbeta, rows, C, rows_per_block);
+                                                    dbeta, rows, C, rows_per_block, vec_red);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

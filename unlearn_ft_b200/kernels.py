@@ -81,6 +81,24 @@ def linear_fwd(x, w, bias=None, residual=None, out=None, out_fp32=False):
     return out
 
 
+def linear_geglu_fwd(x, w, bias, save_pre=False, out=None):
+    """GEGLU input projection with the activation in the GEMM epilogue (blocks.py:44-59): w [2F, K], bias [2F] ->
+    (out [M, F], pre [M, 2F] | None).  `pre` = the (value | gate) pre-activations geglu_bwd needs; None for frozen models."""
+    _chk2d(x, "x"), _chk2d(w, "w")
+    M, K = x.shape
+    F2 = w.shape[0]
+    if w.shape[1] != K or F2 % 2:
+        raise ValueError(f"linear_geglu_fwd: bad weight shape {tuple(w.shape)} for x {tuple(x.shape)}")
+    Fh = F2 // 2
+    if out is None:
+        out = alloc2d(M, Fh, x.device)
+    pre = alloc2d(M, F2, x.device) if save_pre else None
+    check(_lib.lib().b200pdm_linear_geglu_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), out.data_ptr(),
+                                              out.stride(0), _ptr(pre), pre.stride(0) if pre is not None else 0, M, Fh, K,
+                                              _stream()), "linear_geglu_fwd")
+    return out, pre
+
+
 def linear_dgrad(dy, w, residual=None, out=None):
     """dx[M,K] = dy[M,N] @ w[N,K] (+ residual)."""
     _chk2d(dy, "dy"), _chk2d(w, "w")
@@ -121,6 +139,20 @@ def conv_fwd(x, w, B, H, W, c_out, ksize=3, stride=1, bias=None, rowbias=None, r
                              rowbias.stride(0) if rowbias is not None else 0, _ptr(residual),
                              residual.stride(0) if residual is not None else 0, out.data_ptr(),
                              out.stride(0), B, H, W, c_in, c_out, ksize, stride, _ptr(ws), nws, _stream()), "conv_fwd")
+    return out
+
+
+def conv_fwd_nopad(x, w, B, H, W, c_out, stride=2, bias=None, out=None):
+    """3x3 convolution whose window starts AT the pixel (zeros beyond the right / bottom edge): F.pad(x, (0, 1, 0, 1)) +
+    padding-0 conv = diffusers Downsample2D(padding=0) of the VAE encoder.  Forward only."""
+    _chk2d(x, "x")
+    c_in = x.shape[1]
+    Ho, Wo = H // stride, W // stride
+    if out is None:
+        out = alloc2d(B * Ho * Wo, c_out, x.device)
+    ild = w.stride(1) if w.dim() == 3 else w.stride(0)
+    check(_lib.lib().b200pdm_conv_fwd_nopad(x.data_ptr(), x.stride(0), w.data_ptr(), ild, _ptr(bias), out.data_ptr(),
+                                            out.stride(0), B, H, W, c_in, c_out, stride, _stream()), "conv_fwd_nopad")
     return out
 
 
@@ -251,15 +283,45 @@ def softmax_fwd(s, p, rows, cols, scale):
     return p
 
 
-def attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=None, want_lse=False):
-    """Fused attention forward (head_dim 64). q: [B*Lq, >=heads*64] view, k/v: [B*Lk, ...] views."""
+def attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=None, want_lse=False, causal=False):
+    """Fused attention forward (head_dim 64). q: [B*Lq, >=heads*64] view, k/v: [B*Lk, ...] views.  causal: query i attends
+    keys <= i (CLIP text encoder)."""
     if out is None:
         out = alloc2d(B * Lq, heads * 64, q.device)
     lse = torch.empty(B * heads * Lq, device=q.device, dtype=F32) if want_lse else None
-    check(_lib.lib().b200pdm_attention_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
-                                           v.stride(0), out.data_ptr(), out.stride(0), _ptr(lse), B, heads, Lq, Lk,
-                                           scale, _stream()), "attention_fwd")
+    check(_lib.lib().b200pdm_attention_fwd_ex(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                              v.stride(0), out.data_ptr(), out.stride(0), _ptr(lse), B, heads, Lq, Lk,
+                                              scale, int(causal), _stream()), "attention_fwd")
     return out, lse
+
+
+def gelu(x, out=None):
+    _chk2d(x, "x")
+    if out is None:
+        out = alloc2d(x.shape[0], x.shape[1], x.device)
+    check(_lib.lib().b200pdm_gelu(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], _stream()),
+          "gelu")
+    return out
+
+
+def clip_embed(ids, token_embedding, position_embedding):
+    """ids int64 [B, L]; fp32 tables [vocab, C], [>= L, C] -> bf16 [B*L, C]."""
+    B, L = ids.shape
+    vocab, Cn = token_embedding.shape
+    ids = ids.to(torch.int64).contiguous()
+    out = alloc2d(B * L, Cn, ids.device)
+    check(_lib.lib().b200pdm_clip_embed(ids.data_ptr(), token_embedding.data_ptr(), position_embedding.data_ptr(), out.data_ptr(),
+                                        out.stride(0), B * L, L, Cn, vocab, _stream()), "clip_embed")
+    return out
+
+
+def vae_sample(moments, B, hw, latent_channels, scaling_factor, eps=None, want_mean=False):
+    """moments bf16 [B*hw, 2*Cz] -> latents fp32 [B, Cz, hw] (flat spatial), optional mean."""
+    z = torch.empty(B, latent_channels, hw, device=moments.device, dtype=F32)
+    mean = torch.empty_like(z) if want_mean else None
+    check(_lib.lib().b200pdm_vae_sample(moments.data_ptr(), moments.stride(0), _ptr(eps), z.data_ptr(), _ptr(mean), B,
+                                        latent_channels, hw, float(scaling_factor), _stream()), "vae_sample")
+    return z, mean
 
 
 def attention_bwd(q, k, v, out, dout, lse, dq, dk, dv, B, heads, Lq, Lk, scale):

@@ -292,12 +292,11 @@ class FeedForwardWidthGated(nn.Module):
         return (g[:, None] * self.group_dim + torch.arange(self.group_dim)[None, :]).reshape(-1)
 
     def run(self, x, residual, need_bwd):
-        p, b_p = bnn.linear(x, self.net[0].proj, need_bwd)                              # blocks.py:49
-        gl, b_g = bnn.geglu(p, need_bwd)                                                # blocks.py:54-59
+        gl, b_pg = bnn.linear_geglu(x, self.net[0].proj, need_bwd)                      # blocks.py:49,54-59 in one GEMM
         y, b_2 = bnn.linear(gl, self.net[2], need_bwd, residual=residual)
         if not need_bwd:
             return y, None
-        return y, (lambda dy: b_p(b_g(b_2(dy))))
+        return y, (lambda dy: b_pg(b_2(dy)))
 
 
 class BasicTransformerBlockWidthGated(nn.Module):

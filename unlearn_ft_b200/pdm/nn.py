@@ -343,6 +343,24 @@ def conv(x, m: PConv2d, B, H, W, need_bwd, rowbias=None, residual=None):
     return y, bwd
 
 
+def linear_geglu(x, m: PLinear, need_bwd):
+    """GEGLUGated.forward (blocks.py:44-59) as ONE GEMM: y = (x W_v^T + b_v) * gelu_erf(x W_g^T + b_g) with the activation in
+    the epilogue.  Frozen models never write the 2F-wide projection; trainable ones save it (bf16) for the backward pass:
+    bwd(dy) -> dx through geglu_bwd (d value | d gate) and the projection's dgrad / wgrad / bias column sum."""
+    y, pre = K.linear_geglu_fwd(x, m.w16, m.bias, save_pre=need_bwd)
+    if not need_bwd:
+        return y, None
+
+    def bwd(dy):
+        dp = K.geglu_bwd(dy, pre)
+        with wgrad_branch(dp, x):
+            K.linear_wgrad(dp, x, m.gw)
+            K.colsum(dp, m.bias.grad)
+        return K.linear_dgrad(dp, m.w16)
+
+    return y, bwd
+
+
 def geglu(p, need_bwd):
     y = K.geglu_fwd(p)
     if not need_bwd:

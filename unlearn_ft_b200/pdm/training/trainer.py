@@ -54,6 +54,20 @@ class NoiseScheduler:
         return self.add_noise_and_velocity(latents, noise, timesteps)[1]
 
 
+def encode_prompt(tokenizer, text_encoder, prompt=None, max_sequence_length=77, device=None, text_input_ids=None):
+    """Reference pdm/utils/data_utils.py:155-191 (non-pooled branch).  The tokenizer is a host-side string operation outside the
+    hot path (and its vocabulary files are not available offline): pass `text_input_ids` [B, 77] (the reference supports
+    exactly this when `tokenizer is None`), or a tokenizer object with the transformers call signature."""
+    if tokenizer is not None:
+        prompt = [prompt] if isinstance(prompt, str) else prompt
+        text_input_ids = tokenizer(prompt, padding="max_length", max_length=max_sequence_length, truncation=True,
+                                   return_tensors="pt").input_ids
+    elif text_input_ids is None:
+        raise ValueError("text_input_ids must be provided when the tokenizer is not specified")
+    dev = device or text_encoder.device
+    return text_encoder(text_input_ids.to(dev))[0].to(dtype=text_encoder.dtype)
+
+
 def cast_block_act_hooks(unet, store: dict):
     """Reference trainer.py:557-572."""
     handles = []
@@ -403,8 +417,11 @@ class UnetFineTuner:
 
     def __init__(self, student: UNet2DConditionModelPruned, teacher: UNet2DConditionModel, lr=1e-6, betas=(0.9, 0.999),
                  eps=1e-8, weight_decay=0.0, warmup_steps=250, w_diff=1.0, w_kd=2.0, w_block=0.1, snr_gamma=5.0,
-                 process_group=None):
+                 process_group=None, vae=None, text_encoder=None):
         self.student, self.teacher = student, teacher
+        # frozen step-front producers (reference trainer.py:2126-2144): optional -- the synthetic-input contract of SURVEY 8d
+        # feeds 'latents' / 'prompt_embeds' directly; with them the reference's own batch keys are accepted (see step())
+        self.vae, self.text_encoder = vae, text_encoder
         self.device = student.device
         self.noise_scheduler = NoiseScheduler(self.device)
         self.w_diff, self.w_kd, self.w_block, self.snr_gamma = w_diff, w_kd, w_block, snr_gamma
@@ -434,8 +451,14 @@ class UnetFineTuner:
         (`torch.randn_like(latents)`, trainer.py:2409; `torch.randint(0, num_train_timesteps, (bsz,))`, :2421): a batch
         without 'noise' / 'timesteps' gets exactly that (torch's global CUDA generator, or `self.generator` if set);
         parity tests and the CUDA-graph step pass them in so that both sides of a comparison see the same draw."""
-        latents = batch["latents"]
         gen = getattr(self, "generator", None)
+        latents = batch.get("latents")
+        if latents is None:
+            # reference batch contract: latents = vae.encode(batch["pixel_values"]).latent_dist.sample() * scaling_factor
+            # (trainer.py:2405-2406), through the B200 VAE encoder (pdm/models/encoders.py)
+            if self.vae is None:
+                raise KeyError("batch has no 'latents' and the tuner was built without a vae to encode batch['pixel_values']")
+            latents = self.vae.encode_latents(batch["pixel_values"], generator=gen, noise=batch.get("vae_noise"))
         noise = batch.get("noise")
         if noise is None:
             noise = torch.randn(latents.shape, device=latents.device, dtype=latents.dtype, generator=gen)
@@ -445,11 +468,21 @@ class UnetFineTuner:
                                       device=latents.device, generator=gen).long()
         return latents, noise, timesteps
 
+    def _prompt_embeds(self, batch, key="prompt_embeds", ids_key="input_ids"):
+        """Text states of a step: given, or produced from token ids by the frozen text encoder exactly as the reference's dataset
+        transform does (`text_encoder(input_ids)[0]`, pdm/utils/data_utils.py:155-191)."""
+        ehs = batch.get(key)
+        if ehs is None:
+            if self.text_encoder is None:
+                raise KeyError(f"batch has no '{key}' and the tuner was built without a text_encoder to encode batch['{ids_key}']")
+            ehs = encode_prompt(None, self.text_encoder, text_input_ids=batch[ids_key])
+        return ehs
+
     def step(self, batch):
         """trainer.py:2403-2488.  batch: {'latents' [B,4,h,w] (stands in for vae.encode(...)*0.18215), 'noise',
         'timesteps', 'prompt_embeds' [B,77,1024]} -- the synthetic-input contract of SURVEY.md section 8d."""
         latents, noise, timesteps = self._diffusion_inputs(batch)
-        ehs = batch["prompt_embeds"]
+        ehs = self._prompt_embeds(batch)
         noisy, target = self.noise_scheduler.add_noise_and_velocity(latents, noise, timesteps)
         teacher_pred = None
         need_teacher = self.w_block > 0 or self.w_kd > 0
@@ -643,7 +676,8 @@ class BilevelUnetFineTuner(UnetFineTuner):
         """trainer.py:2904-3001 with the shipped weights (diffusion 0 / distillation 1 / block 0):
         loss = mse(student(x_t, c), 2*eps_T(x_t, empty) - eps_T(x_t, c))  (:2996-2998)."""
         latents, noise, timesteps = self._diffusion_inputs(batch)
-        ehs, empty = batch["prompt_embeds"], batch["empty_prompt_embeds"]
+        ehs = self._prompt_embeds(batch)
+        empty = self._prompt_embeds(batch, "empty_prompt_embeds", "empty_input_ids")
         noisy, _ = self.noise_scheduler.add_noise_and_velocity(latents, noise, timesteps)
         ts = self.teacher_stream
         if ts is not None:                                                        # teacher x2 next to the student (see step())
