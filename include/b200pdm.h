@@ -224,6 +224,22 @@ int b200pdm_clip_embed(const int64_t* ids, const float* token_embedding, const f
  * latents (NCHW fp32) = (mean + exp(logvar / 2) * eps) * scaling_factor; eps NCHW fp32 or NULL (mode); mean_out optional. */
 int b200pdm_vae_sample(const void* moments, int64_t ldm, const float* eps, float* latents, float* mean_out, int batch,
                        int latent_channels, int hw, float scaling_factor, b200pdm_stream_t stream);
+/* Runtime gates of the UN-PRUNED network (the pruning phase's mode).  Width gates (pdm/models/gates.py:15-28,
+ * 56-62; applied at blocks.py:56-58,267-272,343-348): y[r, c] = x[r, c] * gate[(r / rows_per_sample) % gate_batch][(c % period)
+ * / group_size] -- gate is fp32 [gate_batch, widths] with row pitch ldg (per-sample architectures, or one shared row), `period`
+ * lets q|k|v or value|gate column blocks share one gate row.  gate_grad accumulates d gate += sum dy * x over the gated
+ * elements (the gradient the hypernetwork is trained with, trainer.py:1159-1321); dx is gate_scale applied to dy.          */
+int b200pdm_gate_scale(const void* x, int64_t ldx, const float* gate, int ldg, void* y, int64_t ldy, int64_t rows, int C,
+                       int rows_per_sample, int period, int group_size, int gate_batch, b200pdm_stream_t stream);
+int b200pdm_gate_grad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dgate, int ldg, int64_t rows, int C,
+                      int rows_per_sample, int period, int group_size, int gate_batch, b200pdm_stream_t stream);
+/* Depth gate (gates.py:43-49; blocks.py:582-587,1241-1244): y = (1 - m) * inp + m * out with m = gate[b % gate_batch], and
+ * its backward: d_inp = (1 - m) dy, d_out = m dy, dgate[b % gate_batch] += sum dy * (out - inp)  (dgate may be NULL).     */
+int b200pdm_depth_blend(const void* inp, int64_t ldi, const void* out, int64_t ldo, const float* gate, void* y, int64_t ldy,
+                        int64_t rows, int C, int rows_per_sample, int gate_batch, b200pdm_stream_t stream);
+int b200pdm_depth_blend_bwd(const void* dy, int64_t lddy, const void* inp, int64_t ldi, const void* out, int64_t ldo,
+                            const float* gate, void* d_inp, int64_t ldgi, void* d_out, int64_t ldgo, float* dgate, int64_t rows,
+                            int C, int rows_per_sample, int gate_batch, b200pdm_stream_t stream);
 /* Column sums: out[n] += sum_m x[m, n]  (bias gradients).                                                   */
 int b200pdm_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, b200pdm_stream_t stream);
 /* Per-sample column sums: out[r / rows_per_group, n] += x[r, n]  (gradient of the time-embedding broadcast add,

@@ -86,6 +86,10 @@ _SIGS = {
     "b200pdm_attention_bwd": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, c_p,
                               i32, i32, i32, i32, f32, c_p],
     "b200pdm_attention_fwd_ex": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, c_p, i32, i32, i32, i32, f32, i32, c_p],
+    "b200pdm_gate_scale": [c_p, i64, c_p, i32, c_p, i64, i64, i32, i32, i32, i32, i32, c_p],
+    "b200pdm_gate_grad": [c_p, i64, c_p, i64, c_p, i32, i64, i32, i32, i32, i32, i32, c_p],
+    "b200pdm_depth_blend": [c_p, i64, c_p, i64, c_p, c_p, i64, i64, i32, i32, i32, c_p],
+    "b200pdm_depth_blend_bwd": [c_p, i64, c_p, i64, c_p, i64, c_p, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, c_p],
     "b200pdm_gelu": [c_p, i64, c_p, i64, i64, i32, c_p],
     "b200pdm_clip_embed": [c_p, c_p, c_p, c_p, i64, i64, i32, i32, i32, c_p],
     "b200pdm_vae_sample": [c_p, i64, c_p, c_p, c_p, i32, i32, i32, f32, c_p],

@@ -111,6 +111,100 @@ __global__ void vae_sample_kernel(const bf16* __restrict__ mom, int64_t ldm, con
   }
 }
 
+// ---------------------------------------------------------------- runtime gates of the un-pruned network
+// Width gate (pdm/models/gates.py:15-28 VirtualGate / :56-62 LinearWidthGate): y[r, c] = x[r, c] * gate[b(r) % Bg][g(c)], with
+// b(r) = r / rows_per_sample and g(c) = (c % period) / group_size (period: q|k|v or value|gate column blocks share one gate).
+__global__ void gate_scale_kernel(const bf16* __restrict__ x, int64_t ldx, const float* __restrict__ gate, int ldg,
+                                  bf16* __restrict__ y, int64_t ldy, int64_t rows, int C, int rows_per_sample, int period,
+                                  int group_size, int Bg) {
+  pdl_trigger();
+  const int cvec = (C + 7) >> 3;
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cvec;
+    const int c0 = (int)(i - r * cvec) * 8;
+    const float* g = gate + (int64_t)((r / rows_per_sample) % Bg) * ldg;
+    if (c0 + 8 <= C) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + r * ldx + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= g[((c0 + j) % period) / group_size];
+      *reinterpret_cast<bf16x8*>(y + r * ldy + c0) = pack8(v);
+    } else {
+      for (int c = c0; c < C; ++c) y[r * ldy + c] = __float2bfloat16(__bfloat162float(x[r * ldx + c]) * g[(c % period) / group_size]);
+    }
+  }
+}
+// d gate[bg][g] += sum over the rows of the samples b = bg (mod Bg) and the columns of group g of dy[r, c] * x[r, c].
+// grid (column chunks of 256, samples); block 256: thread = one column, loop over the sample's rows, then one atomic per column.
+__global__ void gate_grad_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
+                                 float* __restrict__ dgate, int ldg, int C, int rows_per_sample, int period, int group_size,
+                                 int Bg, int row_slices) {
+  pdl_trigger();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  const int per = (rows_per_sample + row_slices - 1) / row_slices;
+  const int r0 = blockIdx.z * per, r1 = min(rows_per_sample, r0 + per);
+  const int64_t base = (int64_t)b * rows_per_sample;
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r)
+    acc += __bfloat162float(dy[(base + r) * lddy + c]) * __bfloat162float(x[(base + r) * ldx + c]);
+  atomicAdd(dgate + (int64_t)(b % Bg) * ldg + (c % period) / group_size, acc);
+}
+// Depth gate (pdm/models/gates.py:43-49): y = (1 - m_b) * inp + m_b * out, m = gate[b % Bg].
+__global__ void depth_blend_kernel(const bf16* __restrict__ inp, int64_t ldi, const bf16* __restrict__ out, int64_t ldo,
+                                   const float* __restrict__ gate, bf16* __restrict__ y, int64_t ldy, int64_t rows, int C,
+                                   int rows_per_sample, int Bg) {
+  pdl_trigger();
+  const int cvec = C >> 3;
+  const int64_t total = rows * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cvec;
+    const int c0 = (int)(i - r * cvec) * 8;
+    const float m = gate[(r / rows_per_sample) % Bg];
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(inp + r * ldi + c0), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(out + r * ldo + c0), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (1.f - m) * a[j] + m * b[j];
+    *reinterpret_cast<bf16x8*>(y + r * ldy + c0) = pack8(a);
+  }
+}
+// backward: d_inp = (1 - m) dy, d_out = m dy, d m[b % Bg] += sum dy * (out - inp)
+__global__ void depth_blend_bwd_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ inp, int64_t ldi,
+                                       const bf16* __restrict__ out, int64_t ldo, const float* __restrict__ gate,
+                                       bf16* __restrict__ d_inp, int64_t ldgi, bf16* __restrict__ d_out, int64_t ldgo,
+                                       float* __restrict__ dgate, int C, int rows_per_sample, int Bg, int row_slices) {
+  pdl_trigger();
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const float m = gate[b % Bg];
+  const int cvec = C >> 3;
+  const int per = (rows_per_sample + row_slices - 1) / row_slices;
+  const int r0 = blockIdx.x * per, r1 = min(rows_per_sample, r0 + per);
+  const int64_t base = (int64_t)b * rows_per_sample;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)r0 * cvec + threadIdx.x; i < (int64_t)r1 * cvec; i += blockDim.x) {
+    const int64_t r = base + i / cvec;
+    const int c0 = (int)(i % cvec) * 8;
+    float g[8], a[8], o[8], gi[8], go[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dy + r * lddy + c0), g);
+    unpack8(*reinterpret_cast<const bf16x8*>(inp + r * ldi + c0), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(out + r * ldo + c0), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc += g[j] * (o[j] - a[j]);
+      gi[j] = (1.f - m) * g[j];
+      go[j] = m * g[j];
+    }
+    *reinterpret_cast<bf16x8*>(d_inp + r * ldgi + c0) = pack8(gi);
+    *reinterpret_cast<bf16x8*>(d_out + r * ldgo + c0) = pack8(go);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && dgate) atomicAdd(dgate + (b % Bg), acc);
+}
+
 // ---------------------------------------------------------------- row softmax (frozen encoders: head dims other than 64)
 // one block per row; fp32 scores in, bf16 probabilities out. p = softmax(scale * s).
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, int64_t lds, bf16* __restrict__ p, int64_t ldp, int cols,
@@ -464,6 +558,53 @@ int b200pdm_geglu_bwd(const void* dout, int64_t lddo, const void* proj, int64_t 
   const int fvec = F / 8;
   launch_pdl(geglu_bwd_kernel, grid_for(rows * fvec, 256), 256, 0, STREAM, CBF(dout), lddo, CBF(proj), ldp, BF(dproj), lddp, rows,
                                                                   F, fvec);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_gate_scale(const void* x, int64_t ldx, const float* gate, int ldg, void* y, int64_t ldy, int64_t rows, int C,
+                       int rows_per_sample, int period, int group_size, int gate_batch, b200pdm_stream_t stream) {
+  if (!x || !gate || !y || rows_per_sample <= 0 || period <= 0 || group_size <= 0 || gate_batch <= 0 || ldx % 8 || ldy % 8)
+    return B200PDM_ERR_ARG;
+  launch_pdl(gate_scale_kernel, grid_for(rows * ((C + 7) / 8), 256), 256, 0, STREAM, CBF(x), ldx, gate, ldg, BF(y), ldy, rows, C,
+             rows_per_sample, period, group_size, gate_batch);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_gate_grad(const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dgate, int ldg, int64_t rows, int C,
+                      int rows_per_sample, int period, int group_size, int gate_batch, b200pdm_stream_t stream) {
+  if (!dy || !x || !dgate || rows_per_sample <= 0 || rows % rows_per_sample || period <= 0 || group_size <= 0 || gate_batch <= 0)
+    return B200PDM_ERR_ARG;
+  const int B = (int)(rows / rows_per_sample);
+  int slices = rows_per_sample >= 1024 ? 8 : (rows_per_sample >= 128 ? 2 : 1);
+  dim3 grid((C + 255) / 256, B, slices);
+  launch_pdl(gate_grad_kernel, grid, 256, 0, STREAM, CBF(dy), lddy, CBF(x), ldx, dgate, ldg, C, rows_per_sample, period, group_size,
+             gate_batch, slices);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_depth_blend(const void* inp, int64_t ldi, const void* out, int64_t ldo, const float* gate, void* y, int64_t ldy,
+                        int64_t rows, int C, int rows_per_sample, int gate_batch, b200pdm_stream_t stream) {
+  if (!inp || !out || !gate || !y || C % 8 || ldi % 8 || ldo % 8 || ldy % 8 || rows_per_sample <= 0 || gate_batch <= 0)
+    return B200PDM_ERR_ARG;
+  launch_pdl(depth_blend_kernel, grid_for(rows * (C / 8), 256), 256, 0, STREAM, CBF(inp), ldi, CBF(out), ldo, gate, BF(y), ldy, rows, C,
+             rows_per_sample, gate_batch);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_depth_blend_bwd(const void* dy, int64_t lddy, const void* inp, int64_t ldi, const void* out, int64_t ldo,
+                            const float* gate, void* d_inp, int64_t ldgi, void* d_out, int64_t ldgo, float* dgate, int64_t rows,
+                            int C, int rows_per_sample, int gate_batch, b200pdm_stream_t stream) {
+  if (!dy || !inp || !out || !gate || !d_inp || !d_out || C % 8 || rows_per_sample <= 0 || rows % rows_per_sample || gate_batch <= 0)
+    return B200PDM_ERR_ARG;
+  const int B = (int)(rows / rows_per_sample);
+  const int slices = rows_per_sample >= 1024 ? 16 : (rows_per_sample >= 64 ? 4 : 1);
+  dim3 grid(slices, B);
+  launch_pdl(depth_blend_bwd_kernel, grid, 256, 0, STREAM, CBF(dy), lddy, CBF(inp), ldi, CBF(out), ldo, gate, BF(d_inp), ldgi,
+             BF(d_out), ldgo, dgate, C, rows_per_sample, gate_batch, slices);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

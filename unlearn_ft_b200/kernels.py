@@ -295,6 +295,42 @@ def attention_fwd(q, k, v, B, heads, Lq, Lk, scale, out=None, want_lse=False, ca
     return out, lse
 
 
+def gate_scale(x, gate, rows_per_sample, period, group_size, out=None):
+    """Width gate: y[r, c] = x[r, c] * gate[(r // rows_per_sample) % Bg][(c % period) // group_size]; gate fp32 [Bg, width] view."""
+    _chk2d(x, "x")
+    if out is None:
+        out = alloc2d(x.shape[0], x.shape[1], x.device)
+    check(_lib.lib().b200pdm_gate_scale(x.data_ptr(), x.stride(0), gate.data_ptr(), gate.stride(0), out.data_ptr(), out.stride(0),
+                                        x.shape[0], x.shape[1], rows_per_sample, period, group_size, gate.shape[0], _stream()),
+          "gate_scale")
+    return out
+
+
+def gate_grad(dy, x, dgate, rows_per_sample, period, group_size):
+    """dgate[bg, g] (fp32 view, accumulated) += sum dy * x over the elements gate[bg, g] multiplies."""
+    check(_lib.lib().b200pdm_gate_grad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dgate.data_ptr(), dgate.stride(0),
+                                       x.shape[0], x.shape[1], rows_per_sample, period, group_size, dgate.shape[0], _stream()),
+          "gate_grad")
+
+
+def depth_blend(inp, out_, gate, rows_per_sample):
+    """(1 - m) * inp + m * out_ per sample; gate fp32 [Bg] (contiguous)."""
+    y = alloc2d(inp.shape[0], inp.shape[1], inp.device)
+    check(_lib.lib().b200pdm_depth_blend(inp.data_ptr(), inp.stride(0), out_.data_ptr(), out_.stride(0), gate.data_ptr(),
+                                         y.data_ptr(), y.stride(0), inp.shape[0], inp.shape[1], rows_per_sample, gate.numel(),
+                                         _stream()), "depth_blend")
+    return y
+
+
+def depth_blend_bwd(dy, inp, out_, gate, dgate, rows_per_sample):
+    d_inp, d_out = alloc2d(inp.shape[0], inp.shape[1], inp.device), alloc2d(inp.shape[0], inp.shape[1], inp.device)
+    check(_lib.lib().b200pdm_depth_blend_bwd(dy.data_ptr(), dy.stride(0), inp.data_ptr(), inp.stride(0), out_.data_ptr(),
+                                             out_.stride(0), gate.data_ptr(), d_inp.data_ptr(), d_inp.stride(0), d_out.data_ptr(),
+                                             d_out.stride(0), _ptr(dgate), inp.shape[0], inp.shape[1], rows_per_sample,
+                                             gate.numel(), _stream()), "depth_blend_bwd")
+    return d_inp, d_out
+
+
 def gelu(x, out=None):
     _chk2d(x, "x")
     if out is None:

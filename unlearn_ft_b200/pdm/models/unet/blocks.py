@@ -67,6 +67,56 @@ def run_block(runner, anchor, *tensors, owner=None):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# runtime gates of the un-pruned network (reference gates.py + the `if not self.pruned:` branches of blocks.py)
+# ----------------------------------------------------------------------------------------------------------------
+class RuntimeGates:
+    """Gate values of one forward: `g` fp32 [Bg, n_gates] on the device (all width gates in get_structure() order, then the
+    depth gates -- the arch-vector layout of hypernet.py:101-126) and `dg`, the same-shaped accumulator of their gradients.
+    Gated modules hold the column range(s) they own (`gate_cols`, `depth_col`) and read / accumulate views of these."""
+
+    def __init__(self, g: torch.Tensor):
+        self.g = g.detach().to(F32).contiguous()
+        self.dg = torch.zeros_like(self.g)
+
+    def cols(self, rng):
+        return self.g[:, rng[0]:rng[0] + rng[1]], self.dg[:, rng[0]:rng[0] + rng[1]]
+
+
+def width_gate(x, rt: Optional[RuntimeGates], rng, rows_per_sample, period, group_size, need_bwd):
+    """y = x * gate (gates.py:15-28,56-62).  Returns (y, bwd) with bwd(dy) -> dx, accumulating d gate."""
+    if rt is None or rng is None:
+        return x, (lambda dy: dy)
+    g, dg = rt.cols(rng)
+    y = K.gate_scale(x, g, rows_per_sample, period, group_size)
+    if not need_bwd:
+        return y, None
+
+    def bwd(dy):
+        K.gate_grad(dy, x, dg, rows_per_sample, period, group_size)
+        return K.gate_scale(dy, g, rows_per_sample, period, group_size)
+
+    return y, bwd
+
+
+def depth_gate(inp, out, rt: Optional[RuntimeGates], col, rows_per_sample, need_bwd):
+    """(1 - m) * inp + m * out (gates.py:43-49).  bwd(dy) -> (d_inp, d_out), accumulating d m."""
+    if rt is None or col is None:
+        return out, None
+    g, dg = rt.g[:, col].contiguous(), rt.dg[:, col]
+    y = K.depth_blend(inp, out, g, rows_per_sample)
+    if not need_bwd:
+        return y, None
+
+    def bwd(dy):
+        tmp = torch.zeros_like(g)
+        d_inp, d_out = K.depth_blend_bwd(dy, inp, out, g, tmp, rows_per_sample)
+        dg.add_(tmp)                      # (column view of the accumulator is strided: one tiny add)
+        return d_inp, d_out
+
+    return y, bwd
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # leaf composites
 # ----------------------------------------------------------------------------------------------------------------
 class Downsample2D(nn.Module):
@@ -104,8 +154,10 @@ class ResnetBlock2DWidthGated(nn.Module):
     """
 
     def __init__(self, in_channels, out_channels, temb_channels, keep_groups: Sequence[int], eps=1e-5, groups=32,
-                 depth_gated=False, dropped=False, is_input_concatenated=False, skip_connection_dim=None):
+                 depth_gated=False, dropped=False, is_input_concatenated=False, skip_connection_dim=None, gate_cols=None,
+                 depth_col=None):
         super().__init__()
+        self.gate_cols, self.depth_col, self._rt = gate_cols, depth_col, None   # runtime gating (un-pruned mode), see RuntimeGates
         self.in_channels, self.out_channels = in_channels, out_channels
         self.depth_gated, self.dropped, self.pruned = depth_gated, dropped, True
         self.is_input_concatenated, self.skip_connection_dim = is_input_concatenated, skip_connection_dim
@@ -156,18 +208,29 @@ class ResnetBlock2DWidthGated(nn.Module):
         h1, b_n1 = bnn.gn(x, self.norm1, B, hw, True, need_bwd)                       # blocks.py:318-319
         bnn.side_join()
         h2, b_c1 = bnn.conv(h1, self.conv1, B, H, W, need_bwd, rowbias=t)               # blocks.py:332,339-341
+        rt = self._rt
+        h2, b_g = width_gate(h2, rt, self.gate_cols, hw, self.mid_channels, self.group_dim, need_bwd)   # blocks.py:343-346
         h3, b_n2 = bnn.gn(h2, self.norm2, B, hw, True, need_bwd)                       # blocks.py:348,371
         if self.conv_shortcut is not None:
             sc, b_sc = bnn.conv(x, self.conv_shortcut, B, H, W, need_bwd)               # blocks.py:376-377
         else:
             sc, b_sc = x, None
         y, b_c2 = bnn.conv(h3, self.conv2, B, H, W, need_bwd, residual=sc)              # blocks.py:374,379
+        b_d = None
+        if rt is not None and self.depth_gated and self.depth_col is not None:          # blocks.py:582-587
+            cin = x.shape[1]
+            keep = cin - self.skip_connection_dim if self.is_input_concatenated else cin
+            inp_h = x[:, :keep]
+            y, b_d = depth_gate(inp_h, y, rt, self.depth_col, hw, need_bwd)
         if not need_bwd:
             return y, None
 
         def bwd(dy):
+            d_inp = None
+            if b_d is not None:
+                d_inp, dy = b_d(dy)
             dh3, _ = b_c2(dy)
-            dh2 = b_n2(dh3)
+            dh2 = b_g(b_n2(dh3))
             dh1, dt = b_c1(dh2, want_rowbias=True)
             with bnn.side_branch(dt):     # time-embedding gradient chain: off the dgrad chain, joined at the block's end
                 dtemb = b_t(K.cast2d_f32_to_bf16(dt))
@@ -176,6 +239,8 @@ class ResnetBlock2DWidthGated(nn.Module):
             else:
                 dsc = dy
             dx = b_n1(dh1, residual=dsc)     # merges the shortcut-branch gradient in the GroupNorm-backward epilogue
+            if d_inp is not None:            # the depth gate's bypass branch: gradient of input[:, :keep]
+                K.add(dx[:, :d_inp.shape[1]], d_inp, out=dx[:, :d_inp.shape[1]])
             return dx, dtemb
 
         return y, bwd
@@ -193,8 +258,9 @@ class GatedAttention(nn.Module):
     """Pruned form of reference blocks.py:141-196 (+ processor :199-295): `heads` surviving 64-wide heads."""
 
     def __init__(self, query_dim, heads, dim_head=64, cross_attention_dim=None, keep_heads: Optional[Sequence[int]] = None,
-                 orig_heads: Optional[int] = None):
+                 orig_heads: Optional[int] = None, gate_cols=None):
         super().__init__()
+        self.gate_cols, self._rt = gate_cols, None
         if dim_head != 64:
             raise ValueError("the sm_100a attention path is specialised for head_dim 64 (SD-2.1)")
         self.heads, self.dim_head, self.query_dim = heads, dim_head, query_dim
@@ -231,15 +297,20 @@ class GatedAttention(nn.Module):
         """x: normalised tokens [B*L, C]; returns to_out(attn(x)) + residual and bwd(dy) -> dx (gradient w.r.t. x only;
         the residual branch is merged by the caller's LayerNorm backward)."""
         inner = self.heads * 64
+        rt = self._rt
+        b_gq = b_gkv = (lambda d: d)
         if not self.is_cross:
             w, g = self._fused(("to_q", "to_k", "to_v"))
             qkv, b_qkv = bnn.linear(x, self.to_q, need_bwd, w16=w, gw=g, bias=None)    # blocks.py:244,251-252
+            qkv, b_gq = width_gate(qkv, rt, self.gate_cols, L, inner, 64, need_bwd)    # blocks.py:267-272: head gate on q, k, v
             q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
             Lk = L
         else:
             q, b_q = bnn.linear(x, self.to_q, need_bwd)
+            q, b_gq = width_gate(q, rt, self.gate_cols, L, inner, 64, need_bwd)
             w, g = self._fused(("to_k", "to_v"))
             kv, b_kv = bnn.linear(ctx2d, self.to_k, need_bwd, w16=w, gw=g, bias=None)
+            kv, b_gkv = width_gate(kv, rt, self.gate_cols, Lctx, inner, 64, need_bwd)
             k, v = kv[:, :inner], kv[:, inner:]
             Lk = Lctx
         a, b_att = bnn.attention(q, k, v, B, self.heads, L, Lk, need_bwd)             # blocks.py:275-277
@@ -252,12 +323,12 @@ class GatedAttention(nn.Module):
             if not self.is_cross:
                 dqkv = K.alloc2d(B * L, 3 * inner, dy.device)
                 b_att(da, dqkv[:, :inner], dqkv[:, inner:2 * inner], dqkv[:, 2 * inner:])
-                return b_qkv(dqkv)
+                return b_qkv(b_gq(dqkv))
             dq = K.alloc2d(B * L, inner, dy.device)
             dkv = K.alloc2d(B * Lk, 2 * inner, dy.device)
             b_att(da, dq, dkv[:, :inner], dkv[:, inner:])
-            b_kv(dkv, need_dx=False)            # text-encoder context is frozen (trainer.py:2433)
-            return b_q(dq)
+            b_kv(b_gkv(dkv), need_dx=False)     # text-encoder context is frozen (trainer.py:2433)
+            return b_q(b_gq(dq))
 
         return y, bwd
 
@@ -274,8 +345,9 @@ class GEGLUGated(nn.Module):
 class FeedForwardWidthGated(nn.Module):
     """Pruned form of reference blocks.py:79-138: net = [GEGLU(proj), Dropout(0), Linear]."""
 
-    def __init__(self, dim, keep_groups: Sequence[int], gate_width=32, mult=4):
+    def __init__(self, dim, keep_groups: Sequence[int], gate_width=32, mult=4, gate_cols=None):
         super().__init__()
+        self.gate_cols, self._rt = gate_cols, None
         self.keep_groups = list(keep_groups)
         self.group_dim = dim * mult // gate_width
         self.inner_full = dim * mult
@@ -291,7 +363,16 @@ class FeedForwardWidthGated(nn.Module):
         g = torch.tensor(self.keep_groups, dtype=torch.long)
         return (g[:, None] * self.group_dim + torch.arange(self.group_dim)[None, :]).reshape(-1)
 
-    def run(self, x, residual, need_bwd):
+    def run(self, x, residual, need_bwd, rows_per_sample=None):
+        if self._rt is not None and self.gate_cols is not None:
+            # un-pruned mode: the gate sits BETWEEN the projection and the activation (blocks.py:54-58), on both halves
+            p, b_p = bnn.linear(x, self.net[0].proj, need_bwd)
+            p, b_gt = width_gate(p, self._rt, self.gate_cols, rows_per_sample, self.inner, self.group_dim, need_bwd)
+            gl, b_g = bnn.geglu(p, need_bwd)
+            y, b_2 = bnn.linear(gl, self.net[2], need_bwd, residual=residual)
+            if not need_bwd:
+                return y, None
+            return y, (lambda dy: b_p(b_gt(b_g(b_2(dy)))))
         gl, b_pg = bnn.linear_geglu(x, self.net[0].proj, need_bwd)                      # blocks.py:49,54-59 in one GEMM
         y, b_2 = bnn.linear(gl, self.net[2], need_bwd, residual=residual)
         if not need_bwd:
@@ -302,14 +383,14 @@ class FeedForwardWidthGated(nn.Module):
 class BasicTransformerBlockWidthGated(nn.Module):
     """Pruned form of reference blocks.py:705-868 (diffusers BasicTransformerBlock data flow)."""
 
-    def __init__(self, dim, cross_attention_dim, keep1, keep2, keep_ff, orig_heads, ff_gate_width=32):
+    def __init__(self, dim, cross_attention_dim, keep1, keep2, keep_ff, orig_heads, ff_gate_width=32, gate_cols=(None, None, None)):
         super().__init__()
         self.norm1 = PLayerNorm(dim)
-        self.attn1 = GatedAttention(dim, len(keep1), 64, None, keep1, orig_heads)
+        self.attn1 = GatedAttention(dim, len(keep1), 64, None, keep1, orig_heads, gate_cols=gate_cols[0])
         self.norm2 = PLayerNorm(dim)
-        self.attn2 = GatedAttention(dim, len(keep2), 64, cross_attention_dim, keep2, orig_heads)
+        self.attn2 = GatedAttention(dim, len(keep2), 64, cross_attention_dim, keep2, orig_heads, gate_cols=gate_cols[1])
         self.norm3 = PLayerNorm(dim)
-        self.ff = FeedForwardWidthGated(dim, keep_ff, ff_gate_width)
+        self.ff = FeedForwardWidthGated(dim, keep_ff, ff_gate_width, gate_cols=gate_cols[2])
 
     def run(self, x0, ctx2d, B, L, Lctx, need_bwd):
         n1, b_n1 = bnn.ln(x0, self.norm1, need_bwd)
@@ -317,7 +398,7 @@ class BasicTransformerBlockWidthGated(nn.Module):
         n2, b_n2 = bnn.ln(x1, self.norm2, need_bwd)
         x2, b_a2 = self.attn2.run(n2, x1, ctx2d, B, L, Lctx, need_bwd)
         n3, b_n3 = bnn.ln(x2, self.norm3, need_bwd)
-        x3, b_ff = self.ff.run(n3, x2, need_bwd)
+        x3, b_ff = self.ff.run(n3, x2, need_bwd, L)
         if not need_bwd:
             return x3, None
 
@@ -334,8 +415,9 @@ class Transformer2DModelWidthGated(nn.Module):
     """Pruned form of reference blocks.py:870-1003 / :1006-1334 (continuous input, use_linear_projection=True)."""
 
     def __init__(self, num_attention_heads, in_channels, cross_attention_dim, keep1, keep2, keep_ff, norm_num_groups=32,
-                 depth_gated=False, dropped=False, ff_gate_width=32):
+                 depth_gated=False, dropped=False, ff_gate_width=32, gate_cols=(None, None, None), depth_col=None):
         super().__init__()
+        self.depth_col, self._rt = depth_col, None
         self.in_channels = in_channels
         self.depth_gated, self.dropped, self.pruned = depth_gated, dropped, True
         if dropped:
@@ -344,7 +426,7 @@ class Transformer2DModelWidthGated(nn.Module):
         self.norm = PGroupNorm(norm_num_groups, in_channels, eps=1e-6)
         self.proj_in = PLinear(in_channels, in_channels)
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlockWidthGated(
-            in_channels, cross_attention_dim, keep1, keep2, keep_ff, num_attention_heads, ff_gate_width)])
+            in_channels, cross_attention_dim, keep1, keep2, keep_ff, num_attention_heads, ff_gate_width, gate_cols=gate_cols)])
         self.proj_out = PLinear(in_channels, in_channels)
 
     def prune_module(self):
@@ -359,9 +441,20 @@ class Transformer2DModelWidthGated(nn.Module):
         t0, b_pi = bnn.linear(n, self.proj_in, need_bwd)
         t1, b_tb = self.transformer_blocks[0].run(t0, ctx2d, B, L, Lctx, need_bwd)
         y, b_po = bnn.linear(t1, self.proj_out, need_bwd, residual=x)                   # + residual (blocks.py:1221-1228)
+        b_d = None
+        if self._rt is not None and self.depth_gated and self.depth_col is not None:    # blocks.py:1241-1244
+            y, b_d = depth_gate(x, y, self._rt, self.depth_col, L, need_bwd)
         if not need_bwd:
             return y, None
-        return y, (lambda dy: b_n(b_pi(b_tb(b_po(dy))), residual=dy))
+        if b_d is None:
+            return y, (lambda dy: b_n(b_pi(b_tb(b_po(dy))), residual=dy))
+
+        def bwd(dy):
+            d_inp, d_out = b_d(dy)
+            dx = b_n(b_pi(b_tb(b_po(d_out))), residual=d_out)
+            return K.add(dx, d_inp)
+
+        return y, bwd
 
 
 class Transformer2DModelWidthDepthGated(Transformer2DModelWidthGated):

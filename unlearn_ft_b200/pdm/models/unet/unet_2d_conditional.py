@@ -30,7 +30,7 @@ from ...nn import ParamArena, PConv2d, PGroupNorm, PLinear, as2d, to4d
 from ...utils.estimation_utils import keep_indices
 from ..hypernet import HyperStructure
 from .blocks import (CrossAttnDownBlock2DWidthHalfDepthGated, CrossAttnUpBlock2DWidthHalfDepthGated,
-                     DownBlock2DWidthHalfDepthGated, ResnetBlock2DWidthGated, Transformer2DModelWidthGated,
+                     DownBlock2DWidthHalfDepthGated, ResnetBlock2DWidthGated, RuntimeGates, Transformer2DModelWidthGated,
                      UNetMidBlock2DCrossAttnWidthGated, UpBlock2DWidthHalfDepthGated, run_block)
 
 BF16, F32 = torch.bfloat16, torch.float32
@@ -99,6 +99,23 @@ def structure_from_config(cfg: dict) -> Dict[str, list]:
     return {"width": width, "depth": depth}
 
 
+class _IndexOnOwnDevice(dict):
+    """state-dict view whose tensors accept host-built index tensors in index_select."""
+
+    class _T:
+        def __init__(self, t):
+            self.t = t
+
+        def index_select(self, dim, idx):
+            return self.t.index_select(dim, idx.to(self.t.device))
+
+    def __getitem__(self, k):
+        return self._T(dict.__getitem__(self, k))
+
+    def raw(self, k):
+        return dict.__getitem__(self, k)
+
+
 class UNet2DConditionModelGated(nn.Module):
     """See module docstring.  ``arch_vector=None`` builds the un-pruned network (all gates open)."""
 
@@ -121,6 +138,7 @@ class UNet2DConditionModelGated(nn.Module):
             arch_vector = torch.ones(1, n_total)
         self.arch_vector = arch_vector.detach().float().cpu().clone()
         self._pending_arch = None
+        self._gate_src = None
         self._materialise(device, trainable, seed)
         self.eval()
 
@@ -149,30 +167,39 @@ class UNet2DConditionModelGated(nn.Module):
         it_w, it_d = iter(wv), iter(dv)
         it_has_depth = iter(flat_depth)
 
+        # column of every gate inside the flat arch vector (all widths in get_structure() order, then the depth gates:
+        # hypernet.py:101-126) -- what a gated module reads at run time in the un-pruned mode (blocks.RuntimeGates)
+        n_width_total = sum(w for s_ in self.structure["width"] for w in s_)
+        cursor = {"w": 0, "d": n_width_total}
+
         def next_gate():
             w = next(it_w)
-            return keep_indices(w)
+            cols = (cursor["w"], int(w.shape[-1]))
+            cursor["w"] += int(w.shape[-1])
+            return keep_indices(w), cols
 
         def next_depth():
             has = next(it_has_depth)
             if not has:
-                return False, False
+                return False, False, None
             d = next(it_d)
-            return True, bool(float(d[0]) < 0.5)           # hard_concrete(depth) == 0 -> dropped (blocks.py:649)
+            col = cursor["d"]
+            cursor["d"] += 1
+            return True, bool(float(d[0]) < 0.5), col      # hard_concrete(depth) == 0 -> dropped (blocks.py:649)
 
         def make_layers(n_layers, cins, cout, has_attn, h, concat_skips=None):
             """Gates are consumed resnets-first then attentions, as in get_structure()/set_gate_structure()."""
             r_specs = [(next_gate(),) + next_depth() for _ in range(n_layers)]
             a_specs = [((next_gate(), next_gate(), next_gate()),) + next_depth() for _ in range(n_layers)] if has_attn else []
             resnets, atts = [], []
-            for i, (keep, dg, drop) in enumerate(r_specs):
+            for i, ((keep, cols), dg, drop, dcol) in enumerate(r_specs):
                 skip = concat_skips[i] if concat_skips is not None else None
                 resnets.append(ResnetBlock2DWidthGated(cins[i], cout, temb, keep, eps, G, depth_gated=dg, dropped=drop,
                                                        is_input_concatenated=concat_skips is not None,
-                                                       skip_connection_dim=skip if dg else None))
-            for (k1, k2, kf), dg, drop in a_specs:
+                                                       skip_connection_dim=skip if dg else None, gate_cols=cols, depth_col=dcol))
+            for ((k1, c1), (k2, c2), (kf, cf)), dg, drop, dcol in a_specs:
                 atts.append(Transformer2DModelWidthGated(h, cout, ctx, k1, k2, kf, G, depth_gated=dg, dropped=drop,
-                                                         ff_gate_width=ffw))
+                                                         ff_gate_width=ffw, gate_cols=(c1, c2, cf), depth_col=dcol))
             return resnets, atts
 
         self.conv_in = PConv2d(cfg["in_channels"], ch[0], 3)
@@ -188,14 +215,15 @@ class UNet2DConditionModelGated(nn.Module):
             else:
                 self.down_blocks.append(DownBlock2DWidthHalfDepthGated(resnets, out_c, not final))
         # mid block: resnets[0], resnets[1] gates, then the attention's (get_gate_structure order, blocks.py:2548-2565)
-        k_r0, k_r1 = next_gate(), next_gate()
+        (k_r0, c_r0), (k_r1, c_r1) = next_gate(), next_gate()
         next(it_has_depth), next(it_has_depth)
-        k_a = (next_gate(), next_gate(), next_gate())
+        (k_a1, c_a1), (k_a2, c_a2), (k_af, c_af) = next_gate(), next_gate(), next_gate()
         next(it_has_depth)
         c = ch[-1]
         self.mid_block = UNetMidBlock2DCrossAttnWidthGated(
-            [ResnetBlock2DWidthGated(c, c, temb, k_r0, eps, G), ResnetBlock2DWidthGated(c, c, temb, k_r1, eps, G)],
-            [Transformer2DModelWidthGated(heads[-1], c, ctx, *k_a, G, ff_gate_width=ffw)])
+            [ResnetBlock2DWidthGated(c, c, temb, k_r0, eps, G, gate_cols=c_r0),
+             ResnetBlock2DWidthGated(c, c, temb, k_r1, eps, G, gate_cols=c_r1)],
+            [Transformer2DModelWidthGated(heads[-1], c, ctx, k_a1, k_a2, k_af, G, ff_gate_width=ffw, gate_cols=(c_a1, c_a2, c_af))])
         self.up_blocks = nn.ModuleList()
         rch, rheads = list(reversed(ch)), list(reversed(heads))
         out_c = rch[0]
@@ -226,10 +254,10 @@ class UNet2DConditionModelGated(nn.Module):
         """Reference :1367-1415 -- first half of its two-phase API (build full -> set_structure -> prune).  `arch_vectors` is
         what `HyperStructure.transform_arch_vector(arch_vector, model.get_structure())` returns ({'width': [T[1, w], ...],
         'depth': [T[1, 1], ...]}, consumed block by block in get_structure() order) or the flat [1, 1620] vector itself.
-        The gate values are recorded; `prune()` applies them.  (Runtime multiplicative gates on an un-pruned network, the
-        pruning phase's mode, are SURVEY section 8f-4.)"""
+        The gate values are recorded; `prune()` materialises them, and until then a forward pass applies them as runtime
+        multiplicative gates (rows = 1, or one row per sample)."""
         if torch.is_tensor(arch_vectors):
-            flat = arch_vectors.detach().float().cpu().reshape(1, -1).clone()
+            live = arch_vectors if arch_vectors.dim() == 2 else arch_vectors.reshape(1, -1)
         else:
             widths, depths = list(arch_vectors["width"]), list(arch_vectors["depth"])
             want_w = [w for s in self.structure["width"] for w in s]
@@ -237,10 +265,15 @@ class UNet2DConditionModelGated(nn.Module):
                 raise ValueError("set_structure: width vectors do not match get_structure()")
             if len(depths) != sum(d for s in self.structure["depth"] for d in s):
                 raise ValueError("set_structure: depth vectors do not match get_structure()")
-            flat = torch.cat([t.detach().float().cpu().reshape(1, -1) for t in widths + depths], dim=1)
-        if flat.shape != self.arch_vector.shape:
-            raise ValueError(f"set_structure: expected {tuple(self.arch_vector.shape)} gate values, got {tuple(flat.shape)}")
-        self._pending_arch = flat
+            rows = widths[0].shape[0] if widths[0].dim() == 2 else 1
+            live = torch.cat([t.reshape(rows, -1) for t in widths + depths], dim=1)      # depth gates arrive 1-D (hypernet.py:124)
+        if live.shape[1] != self.arch_vector.shape[1]:
+            raise ValueError(f"set_structure: expected {self.arch_vector.shape[1]} gate values per row, got {tuple(live.shape)}")
+        self._pending_arch = live.detach().float().cpu().clone()
+        # Un-pruned ("gated") mode of the pruning phase: until prune() is called the recorded values act as
+        # MULTIPLICATIVE gates at run time -- per sample when one row per sample is given -- and a tensor that requires
+        # grad receives d loss / d gate (what the hypernetwork is trained with, trainer.py:1159-1321).
+        self._gate_src = live
 
     @torch.no_grad()
     def prune(self):
@@ -252,6 +285,9 @@ class UNet2DConditionModelGated(nn.Module):
         and then the leaf modules' no-op `prune()` -- can be run unchanged."""
         if self._pending_arch is None:
             return self
+        self._gate_src = None
+        if self._pending_arch.shape[0] != 1:
+            raise ValueError("prune(): one architecture (a [1, n] arch vector) can be materialised, got per-sample gates")
         if self.is_pruned():
             raise RuntimeError("prune(): this network is already pruned (the reference prunes a full-width model once)")
         full_sd = {k: v.detach().clone() for k, v in self.state_dict().items()}
@@ -358,6 +394,7 @@ class UNet2DConditionModelGated(nn.Module):
         prune() methods (ascending surviving indices; blocks.py:64-72,133-138,169-185,444-473). Bit-exact gathers."""
         own = dict(self.named_parameters())
         used = set()
+        full_sd = _IndexOnOwnDevice(full_sd)          # (index tensors are built on the host; the weights may live anywhere)
         for name, mod in self.named_modules():
             pre = name + "." if name else ""
             if isinstance(mod, ResnetBlock2DWidthGated) and not mod.dropped:
@@ -383,15 +420,16 @@ class UNet2DConditionModelGated(nn.Module):
                 used.update({pre + "net.0.proj.weight", pre + "net.0.proj.bias", pre + "net.2.weight"})
         for k, p in own.items():
             if k not in used:
-                p.copy_(full_sd[k])
+                p.copy_(full_sd.raw(k))
         self.arena.shadow_fresh = False
 
     # ------------------------------------------------------------------------------------------------ forward
-    def _stem(self, sample, timesteps):
+    def _stem(self, sample, timesteps, gate_in=None):
         B, _, H, W = sample.shape
         te = self.time_embedding
+        rt = getattr(self, "_rt_live", None)
 
-        def runner(need_bwd, sample_, t_):
+        def runner(need_bwd, sample_, t_, *gates_):
             x0 = K.nchw_f32_to_nhwc_bf16(sample_)
             h0, b_ci = bnn.conv(x0, self.conv_in, B, H, W, need_bwd)                          # reference :1616
             t_emb = K.timestep_embedding(t_, self.conv_in.out_channels)                        # reference :1514-1519
@@ -411,11 +449,14 @@ class UNet2DConditionModelGated(nn.Module):
                     d_a1 = b_l2(d_emb)
                     d_e1 = K.silu_bwd(d_a1, e1)
                     b_l1(d_e1, need_dx=False)
+                if gates_:                       # every gated module has accumulated its d gate by now
+                    return (None, None, rt.dg)
                 return (None, None)
 
             return outs, bwd
 
-        return run_block(runner, self._anchor, sample, timesteps, owner=(self, "_grad_ready_stem"))
+        extra = () if gate_in is None else (gate_in,)
+        return run_block(runner, self._anchor, sample, timesteps, *extra, owner=(self, "_grad_ready_stem"))
 
     @staticmethod
     @torch.no_grad()
@@ -460,13 +501,25 @@ class UNet2DConditionModelGated(nn.Module):
             for blk in list(self.down_blocks) + [self.mid_block] + list(self.up_blocks):
                 blk._anchor = anchor
             self._anchor = anchor
+        rt, gate_in = None, None
+        if self._gate_src is not None and not self.is_pruned():
+            # un-pruned mode: distribute this forward's gate values; their gradient comes back through the stem's node,
+            # the last one of the backward pass (every other block consumes the stem's outputs)
+            gate_in = self._gate_src.to(device=sample.device, dtype=F32)
+            if sample.shape[0] % gate_in.shape[0]:
+                raise ValueError("gate rows must divide the batch (gates.py:23-25 repeats them over the batch)")
+            rt = RuntimeGates(gate_in)
+        for m in self.modules():
+            if hasattr(m, "_rt"):
+                m._rt = rt
+        self._rt_live = rt
         timesteps = timestep
         if not torch.is_tensor(timesteps):
             timesteps = torch.tensor([timesteps], dtype=torch.int64, device=sample.device)
         elif timesteps.dim() == 0:
             timesteps = timesteps[None].to(sample.device)
         timesteps = timesteps.expand(sample.shape[0]).to(torch.int64).contiguous()
-        h, temb_act = self._stem(sample, timesteps)
+        h, temb_act = self._stem(sample, timesteps, gate_in)
         ctx2d = self._context(encoder_hidden_states)
         res = (h,)
         for blk in self.down_blocks:                                                            # reference :1631-1653
