@@ -168,14 +168,17 @@ int b200pdm_conv_wgrad(const void* dy, int64_t lddy, const void* x, int64_t ldx,
  * HBM-bound kernels
  * ------------------------------------------------------------------------------------------------------------ */
 /* GroupNorm (+ optional SiLU) over NHWC bf16.  groups*cpg == C.  Saves stats = per-(sample, channel) coefficient
- * tables scale/shift/rstd/mean*rstd (+2 scratch planes), fp32 [6][B][round8(C)].
+ * tables scale/shift/rstd/mean*rstd, fp32 [4][B][round8(C)].  scratch: b200pdm_groupnorm_scratch_floats() fp32 (per-slice
+ * partial sums, written with plain stores and added in slice order: the result does not depend on block scheduling).
  * Replaces norm1+nonlinearity / norm2+nonlinearity at blocks.py:318-319,348,371,519-520,549,572,
  * conv_norm_out+conv_act at unet_2d_conditional.py:1720-1722, and Transformer2DModel.norm (silu=0).        */
+size_t b200pdm_groupnorm_scratch_floats(int batch, int hw, int C);
 int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
-                          float* stats, int batch, int hw, int C, int groups, float eps, int silu,
+                          float* stats, float* scratch, int batch, int hw, int C, int groups, float eps, int silu,
                           b200pdm_stream_t stream);
 /* dx (+ optional residual: a second gradient stream merged in the same pass), and dgamma/dbeta += (fp32).
- * workspace: fp32 [4][batch][round8(C)].                                                                    */
+ * workspace: b200pdm_groupnorm_bwd_workspace_floats() fp32.                                                 */
+size_t b200pdm_groupnorm_bwd_workspace_floats(int batch, int hw, int C);
 int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
                           const float* beta, const float* stats, const void* residual, int64_t ldr, void* dx,
                           int64_t lddx, float* dgamma, float* dbeta, float* workspace, int batch, int hw, int C,

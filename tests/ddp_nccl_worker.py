@@ -44,32 +44,39 @@ def main():
     for mode in ("eager", "graph"):
         ddp = UnetFineTuner(student(), teacher, lr=1e-4, warmup_steps=0)
         assert ddp.reducer.world == world
-        ref = UnetFineTuner(student(), teacher, lr=1e-4, warmup_steps=0, process_group=solo)
-        assert ref.reducer.world == 1
+        local = UnetFineTuner(student(), teacher, lr=1e-4, warmup_steps=0, process_group=solo)   # same slice, no exchange
+        ref = UnetFineTuner(student(), teacher, lr=1e-4, warmup_steps=0, process_group=solo)     # the whole batch on one rank
+        assert ref.reducer.world == 1 and local.reducer.world == 1
         if mode == "graph":
             ddp.capture_cuda_graph(mine)
         l_ddp = torch.stack([v.detach().float() for v in ddp.train_step(mine)]).clone()
+        local.train_step(mine)
         l_ref = torch.stack([v.detach().float() for v in ref.train_step(glob)])
         dist.all_reduce(l_ddp, op=dist.ReduceOp.AVG)                  # mean over the global batch = mean of the rank means
         torch.cuda.synchronize()
-        # first-step AdamW moment = (1 - beta1) * averaged gradient: compares the exchanged gradient itself
+        # first-step AdamW moment = (1 - beta1) * gradient: compares the exchanged gradient itself
         m_ddp, m_ref = ddp.optimizer.exp_avg.double(), ref.optimizer.exp_avg.double()
+        m_avg = local.optimizer.exp_avg.clone()
+        dist.all_reduce(m_avg, op=dist.ReduceOp.AVG)                  # torch's own average of the ranks' local gradients
+        comm_err = ((m_ddp - m_avg.double()).norm() / m_avg.double().norm()).item()
         grad_err = ((m_ddp - m_ref).norm() / m_ref.norm()).item()
-        p_err = ((ddp.student.arena.master.detach().double() - ref.student.arena.master.detach().double()).norm()
-                 / (ref.student.arena.master.detach().double() - student().arena.master.detach().double()).norm()).item()
         loss_err = ((l_ddp - l_ref).abs() / l_ref.abs()).max().item()
         # every rank holds the same parameters afterwards
         chk = ddp.student.arena.master.detach().double().sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN), dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        results[mode] = (grad_err, p_err, loss_err, float(hi - lo))
-        print(f"[rank {rank}] {mode}: grad rel-L2 {grad_err:.2e}, update rel-L2 {p_err:.2e}, loss rel {loss_err:.2e}, "
-              f"replica spread {float(hi - lo):.1e}", flush=True)
+        results[mode] = (comm_err, grad_err, loss_err, float(hi - lo))
+        print(f"[rank {rank}] {mode}: exchanged gradient vs mean of local gradients rel-L2 {comm_err:.2e}; vs one rank on the "
+              f"concatenated batch: gradient rel-L2 {grad_err:.2e}, loss rel {loss_err:.2e}; replica spread {float(hi - lo):.1e}",
+              flush=True)
         ddp.release_cuda_graph()
-    for mode, (ge, pe, le, spread) in results.items():
-        # per-sample arithmetic is identical; only fp32 summation orders (wgrad split-K over a different pixel count, loss
-        # mean, NCCL ring) differ.  Adam's m/sqrt(v) turns a relative gradient error e into an update error of about e.
-        assert ge < 2e-3 and le < 1e-4 and pe < 2e-2 and spread == 0.0, (mode, ge, pe, le, spread)
+    for mode, (ce, ge, le, spread) in results.items():
+        # (1) the exchange itself (per-block buckets, side stream, AdamW behind each bucket, graph replay) reproduces the plain
+        #     average of the ranks' gradients up to fp32 summation order;
+        # (2) against ONE rank on the concatenated batch the per-sample arithmetic is the same but batch 4 and batch 2 take
+        #     different tile / split-K plans, so the two sides are two bf16 evaluations of the same step: the bound is the
+        #     gradient distance of any two bf16 evaluations (tests/test_fullsize_parity_gpu.py: 0.9e-2 global), not 1e-6.
+        assert ce < 1e-4 and ge < 2e-2 and le < 1e-3 and spread == 0.0, (mode, ce, ge, le, spread)
     print(f"[rank {rank}] ddp nccl parity ok", flush=True)
     dist.barrier()
     dist.destroy_process_group()

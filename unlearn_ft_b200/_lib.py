@@ -75,7 +75,9 @@ _SIGS = {
     "b200pdm_conv_dgrad_workspace": [i32, i32, i32, i32, i32, i32],
     "b200pdm_conv_dgrad": [c_p, i64, c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, c_p, sz, c_p],
     "b200pdm_conv_wgrad": [c_p, i64, c_p, i64, c_p, i64, i32, i32, i32, i32, i32, i32, i32, c_p],
-    "b200pdm_groupnorm_fwd": [c_p, i64, c_p, c_p, c_p, i64, c_p, i32, i32, i32, i32, f32, i32, c_p],
+    "b200pdm_groupnorm_scratch_floats": [i32, i32, i32],
+    "b200pdm_groupnorm_bwd_workspace_floats": [i32, i32, i32],
+    "b200pdm_groupnorm_fwd": [c_p, i64, c_p, c_p, c_p, i64, c_p, c_p, i32, i32, i32, i32, f32, i32, c_p],
     "b200pdm_groupnorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, i64, c_p, c_p, c_p, i32, i32, i32, i32, i32, c_p],
     "b200pdm_layernorm_fwd": [c_p, i64, c_p, c_p, c_p, i64, c_p, c_p, i64, i32, f32, c_p],
     "b200pdm_layernorm_bwd": [c_p, i64, c_p, i64, c_p, c_p, c_p, c_p, i64, c_p, i64, c_p, c_p, i64, i32, c_p],
@@ -116,7 +118,7 @@ _SIGS = {
     "b200pdm_diffusion_prep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, c_p],
 }
 _RESTYPES = {"b200pdm_last_error": C.c_char_p, "b200pdm_launch_count": C.c_uint64}
-_RESTYPES.update({n: C.c_size_t for n in _SIGS if n.endswith("_workspace")})
+_RESTYPES.update({n: C.c_size_t for n in _SIGS if n.endswith(("_workspace", "_floats"))})
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

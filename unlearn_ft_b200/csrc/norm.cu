@@ -105,14 +105,19 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
     float t = 0.f;
     for (int y = 0; y < RL; ++y) t += red[y * VL + vx][jj];
     const int c = (blockIdx.y * VL + vx) * 8 + (jj & 7);
-    if (c < C) atomicAdd((jj < 8 ? out0 : out1) + (int64_t)b * ldc + c, t);
+    // one plain store per (slice, sample, channel): the finalize kernel adds the slices in order, so the statistics -- and with
+    // them the whole forward pass, whose other kernels are reproducible already -- no longer depend on the order in which
+    // blocks retire.  (Round 1 accumulated with atomicAdd: the 1e-7 reordering noise flips bf16 roundings downstream, and every
+    // later rounding amplifies the difference -- sqrt(eps * ulp) per layer -- until two runs of the same step differ by the
+    // full bf16 noise level, 1e-2 in features and gradients: profiles/r2_determinism_*.txt.)
+    if (c < C) (jj < 8 ? out0 : out1)[(int64_t)s * 2 * B * ldc + (int64_t)b * ldc + c] = t;
   }
 }
 
 // fwd finalize: one thread per (b, c): group sums from planes 4/5 (sum x, sum x^2) -> the four coefficient tables.
-__global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, int B, int C, int cpg, int ldc, float inv_n,
-                                       float eps) {
+__global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __restrict__ part, int slices,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, int B, int C, int cpg,
+                                       int ldc, float inv_n, float eps) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
@@ -120,7 +125,11 @@ __global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __r
   const int g0 = (c / cpg) * cpg;
   const int64_t plane = (int64_t)B * ldc, base = (int64_t)b * ldc;
   float s = 0.f, q = 0.f;
-  for (int k = 0; k < cpg; ++k) s += tab[4 * plane + base + g0 + k], q += tab[5 * plane + base + g0 + k];
+  for (int k = 0; k < cpg; ++k)
+    for (int sl = 0; sl < slices; ++sl) {
+      const float* pp = part + (int64_t)sl * 2 * plane + base + g0 + k;
+      s += pp[0], q += pp[plane];
+    }
   const float mean = s * inv_n;
   const float var = fmaxf(q * inv_n - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
@@ -179,27 +188,35 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int64_t ldx, const f
   }
 }
 
-// bwd finalize: one thread per (b, c).  ws[0] = sum dz, ws[1] = sum dz*xhat per (b, c)  ->
-//   dgamma[c] += ws1, dbeta[c] += ws0 ;  ws[2] <- P = -rstd^2 * s2/n ,  ws[3] <- Q = -rstd*s1/n + mean*rstd^2*s2/n
-__global__ void gn_bwd_finalize_kernel(float* __restrict__ ws, const float* __restrict__ tab,
-                                       const float* __restrict__ gamma, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int B, int C, int cpg, int ldc, float inv_n) {
+// bwd finalize: one thread per (b, c).  sum0 = sum dz, sum1 = sum dz*xhat per (b, c)  ->
+//   (per-slice partial sums in `part`, added in slice order)  dgamma[c] += sum1, dbeta[c] += sum0 ;
+//   ws[0] <- P = -rstd^2 * s2/n ,  ws[1] <- Q = -rstd*s1/n + mean*rstd^2*s2/n
+__global__ void gn_bwd_finalize_kernel(float* __restrict__ ws, const float* __restrict__ part, int slices,
+                                       const float* __restrict__ tab, const float* __restrict__ gamma,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int cpg, int ldc,
+                                       float inv_n) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
   const int g0 = (c / cpg) * cpg;
   const int64_t plane = (int64_t)B * ldc, base = (int64_t)b * ldc;
-  float s1 = 0.f, s2 = 0.f;
+  float s1 = 0.f, s2 = 0.f, own0 = 0.f, own1 = 0.f;
   for (int k = 0; k < cpg; ++k) {
     const float ga = gamma[g0 + k];
-    s1 += ga * ws[base + g0 + k], s2 += ga * ws[plane + base + g0 + k];
+    float t0 = 0.f, t1 = 0.f;
+    for (int sl = 0; sl < slices; ++sl) {
+      const float* pp = part + (int64_t)sl * 2 * plane + base + g0 + k;
+      t0 += pp[0], t1 += pp[plane];
+    }
+    s1 += ga * t0, s2 += ga * t1;
+    if (g0 + k == c) own0 = t0, own1 = t1;
   }
-  atomicAdd(dbeta + c, ws[base + c]);
-  atomicAdd(dgamma + c, ws[plane + base + c]);
+  atomicAdd(dbeta + c, own0);
+  atomicAdd(dgamma + c, own1);
   const float rstd = tab[2 * plane + base + c], mr = tab[3 * plane + base + c];
-  ws[2 * plane + base + c] = -rstd * rstd * s2 * inv_n;
-  ws[3 * plane + base + c] = -rstd * s1 * inv_n + mr * rstd * s2 * inv_n;
+  ws[base + c] = -rstd * rstd * s2 * inv_n;
+  ws[plane + base + c] = -rstd * s1 * inv_n + mr * rstd * s2 * inv_n;
 }
 
 // dx = scale * dz + x * P + Q (+ residual)
@@ -218,8 +235,8 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, int64_t lddy, c
   const float* wp = ws + (int64_t)b * ldc + c0;
   const float4 s0 = *reinterpret_cast<const float4*>(tp), s1 = *reinterpret_cast<const float4*>(tp + 4);
   const float4 h0 = *reinterpret_cast<const float4*>(tp + plane), h1 = *reinterpret_cast<const float4*>(tp + plane + 4);
-  const float4 q0 = *reinterpret_cast<const float4*>(wp + 2 * plane), q1 = *reinterpret_cast<const float4*>(wp + 2 * plane + 4);
-  const float4 r0 = *reinterpret_cast<const float4*>(wp + 3 * plane), r1 = *reinterpret_cast<const float4*>(wp + 3 * plane + 4);
+  const float4 q0 = *reinterpret_cast<const float4*>(wp), q1 = *reinterpret_cast<const float4*>(wp + 4);
+  const float4 r0 = *reinterpret_cast<const float4*>(wp + plane), r1 = *reinterpret_cast<const float4*>(wp + plane + 4);
   const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
   const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
   const float P[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
@@ -486,7 +503,8 @@ static int occupancy_of(Kern kern, int* cache) {
 
 extern "C" {
 
-// stats: fp32 [6][batch][round8(C)]: coefficient tables scale, shift, rstd, mean*rstd (+ 2 planes of scratch sums).
+// stats: fp32 [4][batch][round8(C)]: coefficient tables scale, shift, rstd, mean*rstd (saved for the backward pass);
+// scratch: b200pdm_groupnorm_scratch_floats() fp32 of per-slice partial sums (contents irrelevant on entry).
 // Launch geometry of the GroupNorm apply passes: VL lanes across 8-channel vectors (the narrowest of 8 / 16 / 32 that wastes
 // the fewest lanes on the last chunk), 256 / VL row lanes, and enough row slices for ~8 blocks per SM.
 struct ApplyGeom {
@@ -521,8 +539,30 @@ static ApplyGeom apply_geom(int batch, int hw, int cvec, int occ) {
   g.grid = dim3(batch, chunks, slices), g.block = dim3(best_vl, rl), g.slices = slices;
   return g;
 }
+// Upper bound of the row slices apply_geom() can choose (it depends on the kernel's measured occupancy, at most 8 blocks of 256
+// threads per SM): sizes the per-slice partial-sum scratch without a device query.
+static int max_stat_slices(int batch, int hw, int cvec) {
+  int best_vl = 32, best_waste = 1 << 30;
+  for (int vl = 8; vl <= 32; vl *= 2) {
+    const int waste = (cvec + vl - 1) / vl * vl - cvec;
+    if (waste < best_waste || (waste == best_waste && vl > best_vl)) best_waste = waste, best_vl = vl;
+  }
+  const int chunks = (cvec + best_vl - 1) / best_vl, rl = 256 / best_vl;
+  int max_slices = hw / (4 * rl);
+  if (max_slices < 1) max_slices = 1;
+  const int by_grid = 148 * 8 * 4 / (batch * chunks) + 1;
+  return max_slices < by_grid ? max_slices : by_grid;
+}
+size_t b200pdm_groupnorm_scratch_floats(int batch, int hw, int C) {
+  const int ldc = (C + 7) / 8 * 8;
+  return (size_t)2 * max_stat_slices(batch, hw, (C + 7) / 8) * batch * ldc;
+}
+size_t b200pdm_groupnorm_bwd_workspace_floats(int batch, int hw, int C) {
+  const int ldc = (C + 7) / 8 * 8;
+  return (size_t)2 * batch * ldc + b200pdm_groupnorm_scratch_floats(batch, hw, C);
+}
 int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
-                          float* stats, int batch, int hw, int C, int groups, float eps, int silu,
+                          float* stats, float* scratch, int batch, int hw, int C, int groups, float eps, int silu,
                           b200pdm_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (groups <= 0 || C % groups || ldx % 8 || ldy % 8) {
@@ -532,27 +572,28 @@ int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
   const int cpg = C / groups;
   const int ldc = (C + 7) / 8 * 8;
   const int64_t plane = (int64_t)batch * ldc;
-  if (cudaMemsetAsync(stats, 0, sizeof(float) * 6 * plane, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
+  if (!stats || !scratch) return B200PDM_ERR_ARG;
   const int cvec = (C + 7) / 8;
   static int occ_stats = 0, occ_apply = 0;
   const ApplyGeom sg = apply_geom(batch, hw, cvec, occupancy_of(gn_colstats_kernel<GN_FWD_STATS>, &occ_stats));
+  if (sg.slices > max_stat_slices(batch, hw, cvec)) return B200PDM_ERR_ARG;
   const bf16* xb = reinterpret_cast<const bf16*>(x);
-  launch_pdl(gn_colstats_kernel<GN_FWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, nullptr, 0, nullptr, stats + 4 * plane,
-             stats + 5 * plane, batch, hw, C, ldc, 0, sg.slices);
+  launch_pdl(gn_colstats_kernel<GN_FWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, nullptr, 0, nullptr, scratch,
+             scratch + plane, batch, hw, C, ldc, 0, sg.slices);
   B200_CHECK_LAUNCH();
   const int n = batch * C;
-  launch_pdl(gn_fwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, stats, gamma, beta, batch, C, cpg, ldc,
+  launch_pdl(gn_fwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, stats, scratch, sg.slices, gamma, beta, batch, C, cpg, ldc,
                                                              1.f / ((float)hw * cpg), eps);
   B200_CHECK_LAUNCH();
   const ApplyGeom ag = apply_geom(batch, hw, cvec, occupancy_of(gn_apply_kernel, &occ_apply));
   launch_pdl(gn_apply_kernel, ag.grid, ag.block, 0, stream, xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc,
              silu, ag.slices);
   B200_CHECK_LAUNCH();
-  g_launches += 4;
+  g_launches += 3;
   return B200PDM_OK;
 }
 
-// workspace: fp32 [4][batch][round8(C)].
+// workspace: fp32, b200pdm_groupnorm_bwd_workspace_floats() elements ([2][batch][round8(C)] coefficients + per-slice partial sums).
 int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const float* gamma,
                           const float* beta, const float* stats, const void* residual, int64_t ldr, void* dx,
                           int64_t lddx, float* dgamma, float* dbeta, float* workspace, int batch, int hw, int C,
@@ -563,24 +604,25 @@ int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   const int cpg = C / groups;
   const int ldc = (C + 7) / 8 * 8;
   const int64_t plane = (int64_t)batch * ldc;
-  if (cudaMemsetAsync(workspace, 0, sizeof(float) * 4 * plane, stream) != cudaSuccess) return B200PDM_ERR_CUDA;
   const int cvec = (C + 7) / 8;
   static int occ_stats = 0, occ_apply = 0;
   const ApplyGeom sg = apply_geom(batch, hw, cvec, occupancy_of(gn_colstats_kernel<GN_BWD_STATS>, &occ_stats));
+  if (!workspace || sg.slices > max_stat_slices(batch, hw, cvec)) return B200PDM_ERR_ARG;
+  float* part = workspace + 2 * plane;
   const bf16* xb = reinterpret_cast<const bf16*>(x);
   const bf16* dyb = reinterpret_cast<const bf16*>(dy);
-  launch_pdl(gn_colstats_kernel<GN_BWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, dyb, lddy, stats, workspace,
-             workspace + plane, batch, hw, C, ldc, silu, sg.slices);
+  launch_pdl(gn_colstats_kernel<GN_BWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, dyb, lddy, stats, part,
+             part + plane, batch, hw, C, ldc, silu, sg.slices);
   B200_CHECK_LAUNCH();
   const int n = batch * C;
-  launch_pdl(gn_bwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, workspace, stats, gamma, dgamma, dbeta, batch, C, cpg, ldc,
-                                                             1.f / ((float)hw * cpg));
+  launch_pdl(gn_bwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, workspace, part, sg.slices, stats, gamma, dgamma, dbeta,
+             batch, C, cpg, ldc, 1.f / ((float)hw * cpg));
   B200_CHECK_LAUNCH();
   const ApplyGeom ag = apply_geom(batch, hw, cvec, occupancy_of(gn_bwd_apply_kernel, &occ_apply));
   launch_pdl(gn_bwd_apply_kernel, ag.grid, ag.block, 0, stream, dyb, lddy, xb, ldx, stats, workspace,
              reinterpret_cast<const bf16*>(residual), ldr, reinterpret_cast<bf16*>(dx), lddx, batch, hw, C, ldc, silu, ag.slices);
   B200_CHECK_LAUNCH();
-  g_launches += 4;
+  g_launches += 3;
   return B200PDM_OK;
 }
 

@@ -208,10 +208,16 @@ def groupnorm_fwd(x, gamma, beta, B, hw, groups, eps, silu, out=None):
     Cn = x.shape[1]
     if out is None:
         out = alloc2d(B * hw, Cn, x.device)
-    stats = torch.empty(6 * B * round8(Cn), device=x.device, dtype=F32)  # 4 coefficient tables + 2 scratch planes
-    check(_lib.lib().b200pdm_groupnorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-                                           out.stride(0), stats.data_ptr(), B, hw, Cn, groups, eps, int(silu),
-                                           _stream()), "groupnorm_fwd")
+    L = _lib.lib()
+    stats = torch.empty(4 * B * round8(Cn), device=x.device, dtype=F32)  # coefficient tables (kept for the backward pass)
+    key = ("gns", B, hw, Cn)
+    n = _WS_BYTES.get(key)
+    if n is None:
+        n = _WS_BYTES[key] = int(L.b200pdm_groupnorm_scratch_floats(B, hw, Cn))
+    scratch = torch.empty(n, device=x.device, dtype=F32)
+    check(L.b200pdm_groupnorm_fwd(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                  out.stride(0), stats.data_ptr(), scratch.data_ptr(), B, hw, Cn, groups, eps, int(silu),
+                                  _stream()), "groupnorm_fwd")
     return out, stats
 
 
@@ -220,7 +226,11 @@ def groupnorm_bwd(dy, x, gamma, beta, stats, dgamma, dbeta, B, hw, groups, silu,
     Cn = x.shape[1]
     if out is None:
         out = alloc2d(B * hw, Cn, x.device)
-    ws = torch.empty(4 * B * round8(Cn), device=x.device, dtype=F32)
+    key = ("gnb", B, hw, Cn)
+    n = _WS_BYTES.get(key)
+    if n is None:
+        n = _WS_BYTES[key] = int(_lib.lib().b200pdm_groupnorm_bwd_workspace_floats(B, hw, Cn))
+    ws = torch.empty(n, device=x.device, dtype=F32)
     check(_lib.lib().b200pdm_groupnorm_bwd(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), gamma.data_ptr(),
                                            beta.data_ptr(), stats.data_ptr(), _ptr(residual),
                                            residual.stride(0) if residual is not None else 0, out.data_ptr(),
