@@ -20,6 +20,7 @@ void set_err(const char* fmt, const char* a);
 // gradient of its slice and ONE row of partial sums {diff, kd, block} into the workspace, and the block that finishes last
 // adds the rows up in block order -- a two-stage reduction whose result does not depend on scheduling (no float atomics).
 constexpr int kMaxFeaturePairs = 16;
+constexpr int kLossMaxBlocks = 148 * 12;   // 12 blocks of 256 threads per SM keep enough 16-byte loads in flight for HBM
 struct LossSeg {
   const void* s;     // student map (bf16) | pred (fp32)
   const void* t;     // teacher map (bf16) | unused
@@ -98,10 +99,15 @@ __global__ void __launch_bounds__(256) kd_loss_fused_kernel(const LossArgs a) {
     const float gscale = a.w_block * a.inv_maps * 2.f * inv_n;
     const long long nvec = sg.numel >> 3;
     float acc = 0.f;
-    for (long long i = (long long)lb * blockDim.x + threadIdx.x; i < nvec; i += (long long)sg.blocks * blockDim.x) {
+    const long long stride = (long long)sg.blocks * blockDim.x;
+    for (long long i = (long long)lb * blockDim.x + threadIdx.x; i < nvec; i += 2 * stride) {
+      const long long i2 = i + stride;
+      const bool two = i2 < nvec;
+      const bf16x8 xa = reinterpret_cast<const bf16x8*>(s)[i], ya = reinterpret_cast<const bf16x8*>(t)[i];
+      const bf16x8 xb = reinterpret_cast<const bf16x8*>(s)[two ? i2 : i], yb = reinterpret_cast<const bf16x8*>(t)[two ? i2 : i];
       float x[8], y[8], g[8];
-      unpack8(reinterpret_cast<const bf16x8*>(s)[i], x);
-      unpack8(reinterpret_cast<const bf16x8*>(t)[i], y);
+      unpack8(xa, x);
+      unpack8(ya, y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = x[j] - y[j];
@@ -109,6 +115,17 @@ __global__ void __launch_bounds__(256) kd_loss_fused_kernel(const LossArgs a) {
         g[j] = gscale * d;
       }
       if (ds) reinterpret_cast<bf16x8*>(ds)[i] = pack8(g);
+      if (two) {
+        unpack8(xb, x);
+        unpack8(yb, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = x[j] - y[j];
+          acc += d * d;
+          g[j] = gscale * d;
+        }
+        if (ds) reinterpret_cast<bf16x8*>(ds)[i2] = pack8(g);
+      }
     }
     if (lb == 0) {   // scalar tail
       for (long long i = (nvec << 3) + threadIdx.x; i < sg.numel; i += blockDim.x) {
@@ -224,7 +241,7 @@ extern "C" {
 
 size_t b200pdm_kd_loss_workspace(int n_pairs) {
   (void)n_pairs;
-  return (size_t)(148 * 4) * 4 * sizeof(float) + 16;   // one partial row per block + the arrival counter
+  return (size_t)kLossMaxBlocks * 4 * sizeof(float) + 16;   // one partial row per block + the arrival counter
 }
 
 int b200pdm_kd_loss_fused(const float* pred, const float* target, const float* teacher, const float* snr_w,
@@ -239,7 +256,7 @@ int b200pdm_kd_loss_fused(const float* pred, const float* target, const float* t
     set_err("kd_loss_fused: workspace too small or misaligned", "");
     return B200PDM_ERR_ARG;
   }
-  const int max_blocks = 148 * 4;
+  const int max_blocks = kLossMaxBlocks;
   LossArgs a;
   memset(&a, 0, sizeof(a));
   a.n_seg = 1 + n_pairs;

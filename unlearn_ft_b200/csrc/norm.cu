@@ -115,29 +115,44 @@ __global__ void gn_colstats_kernel(const bf16* __restrict__ x, int64_t ldx, cons
 }
 
 // fwd finalize: one thread per (b, c): group sums from planes 4/5 (sum x, sum x^2) -> the four coefficient tables.
+// Slice sums of the channels [c_lo, c_hi) of sample b into shared memory, each channel by one thread in slice order (coalesced:
+// consecutive threads read consecutive channels of a slice plane).
+__device__ __forceinline__ void gn_gather_slices(const float* __restrict__ part, int slices, int64_t plane, int64_t base, int c_lo,
+                                                 int c_hi, float* sh0, float* sh1) {
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+    float t0 = 0.f, t1 = 0.f;
+    const float* pp = part + base + c;
+    for (int sl = 0; sl < slices; ++sl, pp += 2 * plane) t0 += pp[0], t1 += pp[plane];
+    sh0[c - c_lo] = t0, sh1[c - c_lo] = t1;
+  }
+  __syncthreads();
+}
+constexpr int kGnGroupsPerBlock = 8;
+constexpr int kGnMaxCpg = 160;   // channels per group (widest: 5120-channel maps never occur; 2560 / 32 = 80)
+
+// fwd finalize: grid (B, ceil(groups / 8)); per-slice partial sums (sum x, sum x^2) -> the four coefficient tables.
 __global__ void gn_fwd_finalize_kernel(float* __restrict__ tab, const float* __restrict__ part, int slices,
                                        const float* __restrict__ gamma, const float* __restrict__ beta, int B, int C, int cpg,
                                        int ldc, float inv_n, float eps) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int b = i / C, c = i - b * C;
-  const int g0 = (c / cpg) * cpg;
+  __shared__ float sh0[kGnGroupsPerBlock * kGnMaxCpg], sh1[kGnGroupsPerBlock * kGnMaxCpg];
+  const int b = blockIdx.x;
+  const int c_lo = blockIdx.y * kGnGroupsPerBlock * cpg, c_hi = min(C, c_lo + kGnGroupsPerBlock * cpg);
   const int64_t plane = (int64_t)B * ldc, base = (int64_t)b * ldc;
-  float s = 0.f, q = 0.f;
-  for (int k = 0; k < cpg; ++k)
-    for (int sl = 0; sl < slices; ++sl) {
-      const float* pp = part + (int64_t)sl * 2 * plane + base + g0 + k;
-      s += pp[0], q += pp[plane];
-    }
-  const float mean = s * inv_n;
-  const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  const float sc = gamma[c] * rstd;
-  tab[base + c] = sc;
-  tab[plane + base + c] = beta[c] - mean * sc;
-  tab[2 * plane + base + c] = rstd;
-  tab[3 * plane + base + c] = mean * rstd;
+  gn_gather_slices(part, slices, plane, base, c_lo, c_hi, sh0, sh1);
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+    const int g0 = ((c - c_lo) / cpg) * cpg;
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < cpg; ++k) s += sh0[g0 + k], q += sh1[g0 + k];
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float sc = gamma[c] * rstd;
+    tab[base + c] = sc;
+    tab[plane + base + c] = beta[c] - mean * sc;
+    tab[2 * plane + base + c] = rstd;
+    tab[3 * plane + base + c] = mean * rstd;
+  }
 }
 
 // y = act(x * scale + shift)
@@ -196,27 +211,24 @@ __global__ void gn_bwd_finalize_kernel(float* __restrict__ ws, const float* __re
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int cpg, int ldc,
                                        float inv_n) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int b = i / C, c = i - b * C;
-  const int g0 = (c / cpg) * cpg;
+  __shared__ float sh0[kGnGroupsPerBlock * kGnMaxCpg], sh1[kGnGroupsPerBlock * kGnMaxCpg];
+  const int b = blockIdx.x;
+  const int c_lo = blockIdx.y * kGnGroupsPerBlock * cpg, c_hi = min(C, c_lo + kGnGroupsPerBlock * cpg);
   const int64_t plane = (int64_t)B * ldc, base = (int64_t)b * ldc;
-  float s1 = 0.f, s2 = 0.f, own0 = 0.f, own1 = 0.f;
-  for (int k = 0; k < cpg; ++k) {
-    const float ga = gamma[g0 + k];
-    float t0 = 0.f, t1 = 0.f;
-    for (int sl = 0; sl < slices; ++sl) {
-      const float* pp = part + (int64_t)sl * 2 * plane + base + g0 + k;
-      t0 += pp[0], t1 += pp[plane];
+  gn_gather_slices(part, slices, plane, base, c_lo, c_hi, sh0, sh1);
+  for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
+    const int g0 = ((c - c_lo) / cpg) * cpg;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      const float ga = gamma[c_lo + g0 + k];
+      s1 += ga * sh0[g0 + k], s2 += ga * sh1[g0 + k];
     }
-    s1 += ga * t0, s2 += ga * t1;
-    if (g0 + k == c) own0 = t0, own1 = t1;
+    atomicAdd(dbeta + c, sh0[c - c_lo]);
+    atomicAdd(dgamma + c, sh1[c - c_lo]);
+    const float rstd = tab[2 * plane + base + c], mr = tab[3 * plane + base + c];
+    ws[base + c] = -rstd * rstd * s2 * inv_n;
+    ws[plane + base + c] = -rstd * s1 * inv_n + mr * rstd * s2 * inv_n;
   }
-  atomicAdd(dbeta + c, own0);
-  atomicAdd(dgamma + c, own1);
-  const float rstd = tab[2 * plane + base + c], mr = tab[3 * plane + base + c];
-  ws[base + c] = -rstd * rstd * s2 * inv_n;
-  ws[plane + base + c] = -rstd * s1 * inv_n + mr * rstd * s2 * inv_n;
 }
 
 // dx = scale * dz + x * P + Q (+ residual)
@@ -581,9 +593,10 @@ int b200pdm_groupnorm_fwd(const void* x, int64_t ldx, const float* gamma, const 
   launch_pdl(gn_colstats_kernel<GN_FWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, nullptr, 0, nullptr, scratch,
              scratch + plane, batch, hw, C, ldc, 0, sg.slices);
   B200_CHECK_LAUNCH();
-  const int n = batch * C;
-  launch_pdl(gn_fwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, stats, scratch, sg.slices, gamma, beta, batch, C, cpg, ldc,
-                                                             1.f / ((float)hw * cpg), eps);
+  if (cpg > kGnMaxCpg) return B200PDM_ERR_UNSUPPORTED;
+  const dim3 fgrid(batch, (groups + kGnGroupsPerBlock - 1) / kGnGroupsPerBlock);
+  launch_pdl(gn_fwd_finalize_kernel, fgrid, 256, 0, stream, stats, scratch, sg.slices, gamma, beta, batch, C, cpg, ldc,
+             1.f / ((float)hw * cpg), eps);
   B200_CHECK_LAUNCH();
   const ApplyGeom ag = apply_geom(batch, hw, cvec, occupancy_of(gn_apply_kernel, &occ_apply));
   launch_pdl(gn_apply_kernel, ag.grid, ag.block, 0, stream, xb, ldx, stats, reinterpret_cast<bf16*>(y), ldy, batch, hw, C, ldc,
@@ -614,8 +627,9 @@ int b200pdm_groupnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t l
   launch_pdl(gn_colstats_kernel<GN_BWD_STATS>, sg.grid, sg.block, 0, stream, xb, ldx, dyb, lddy, stats, part,
              part + plane, batch, hw, C, ldc, silu, sg.slices);
   B200_CHECK_LAUNCH();
-  const int n = batch * C;
-  launch_pdl(gn_bwd_finalize_kernel, (n + 255) / 256, 256, 0, stream, workspace, part, sg.slices, stats, gamma, dgamma, dbeta,
+  if (cpg > kGnMaxCpg) return B200PDM_ERR_UNSUPPORTED;
+  const dim3 fgrid(batch, (groups + kGnGroupsPerBlock - 1) / kGnGroupsPerBlock);
+  launch_pdl(gn_bwd_finalize_kernel, fgrid, 256, 0, stream, workspace, part, sg.slices, stats, gamma, dgamma, dbeta,
              batch, C, cpg, ldc, 1.f / ((float)hw * cpg));
   B200_CHECK_LAUNCH();
   const ApplyGeom ag = apply_geom(batch, hw, cvec, occupancy_of(gn_bwd_apply_kernel, &occ_apply));
