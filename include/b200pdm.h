@@ -324,6 +324,11 @@ int b200pdm_adamw_step_dyn(float* p, float* g, float* m, float* v, void* shadow_
                            b200pdm_stream_t stream);
 /* shadow = bf16(p) (after load_state_dict / a foreign optimizer touched the masters). */
 int b200pdm_refresh_shadow(const float* p, void* shadow_bf16, int64_t n, b200pdm_stream_t stream);
+/* Same pass, also zeroing `zero[0..n)` (fp32, may be NULL).  Sharded data-parallel update ("ZeRO-1 style sharding of
+ * the AdamW update + all-gather"): a rank runs b200pdm_adamw_step on its own 1/world slice of a gradient bucket only; for the
+ * slices it received by all-gather it needs the bf16 shadow of the new masters and a zeroed gradient -- 10 B/param instead of
+ * AdamW's 34. */
+int b200pdm_refresh_shadow_zero(const float* p, void* shadow_bf16, float* zero, int64_t n, b200pdm_stream_t stream);
 
 /* Sampling: one denoising step of the classifier-free-guidance loop, pdm/pipelines/pruning_pipelines.py:957-978
  * = chunk(2) + guidance combine (:972-974) + diffusers DDIMScheduler.step (eta 0, v_prediction, "leading" timesteps,

@@ -115,6 +115,7 @@ _SIGS = {
     "b200pdm_cfg_ddim_step": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, i32, i32, f32, c_p],
     "b200pdm_adamw_step_dyn": [c_p, c_p, c_p, c_p, c_p, i64, c_p, f32, f32, f32, f32, f32, i32, c_p],
     "b200pdm_refresh_shadow": [c_p, c_p, i64, c_p],
+    "b200pdm_refresh_shadow_zero": [c_p, c_p, c_p, i64, c_p],
     "b200pdm_diffusion_prep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, c_p],
 }
 _RESTYPES = {"b200pdm_last_error": C.c_char_p, "b200pdm_launch_count": C.c_uint64}

@@ -217,11 +217,12 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
   }
 }
 
-__global__ void refresh_shadow_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, int64_t n) {
+__global__ void refresh_shadow_kernel(const float* __restrict__ p, bf16* __restrict__ shadow, int64_t n, float* __restrict__ zero) {
   pdl_trigger();   // PDL: successors may start their prologue while this grid runs
   const int64_t nvec = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pv = reinterpret_cast<const float4*>(p)[i];
+    if (zero) reinterpret_cast<float4*>(zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -229,7 +230,10 @@ __global__ void refresh_shadow_kernel(const float* __restrict__ p, bf16* __restr
     reinterpret_cast<uint2*>(shadow)[i] = pk;
   }
   if (blockIdx.x == 0)
-    for (int64_t i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) shadow[i] = __float2bfloat16(p[i]);
+    for (int64_t i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      shadow[i] = __float2bfloat16(p[i]);
+      if (zero) zero[i] = 0.f;
+    }
 }
 
 }  // namespace b200
@@ -331,12 +335,23 @@ int b200pdm_adamw_step_dyn(float* p, float* g, float* m, float* v, void* shadow_
   return B200PDM_OK;
 }
 
+int b200pdm_refresh_shadow_zero(const float* p, void* shadow_bf16, float* zero, int64_t n, b200pdm_stream_t stream) {
+  if (!p || !shadow_bf16 || n <= 0) return B200PDM_ERR_ARG;
+  int64_t blocks = ((n >> 2) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  launch_pdl(refresh_shadow_kernel, (int)blocks, 256, 0, STREAM, p, reinterpret_cast<bf16*>(shadow_bf16), n, zero);
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+
 int b200pdm_refresh_shadow(const float* p, void* shadow_bf16, int64_t n, b200pdm_stream_t stream) {
   if (!p || !shadow_bf16 || n <= 0) return B200PDM_ERR_ARG;
   int64_t blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  launch_pdl(refresh_shadow_kernel, (int)blocks, 256, 0, STREAM, p, reinterpret_cast<bf16*>(shadow_bf16), n);
+  launch_pdl(refresh_shadow_kernel, (int)blocks, 256, 0, STREAM, p, reinterpret_cast<bf16*>(shadow_bf16), n, static_cast<float*>(nullptr));
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

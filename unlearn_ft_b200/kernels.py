@@ -529,6 +529,12 @@ def adamw_step_dyn(p, g, m, v, shadow, dyn, beta1, beta2, eps, wd, grad_scale=1.
           "adamw_step_dyn")
 
 
+def refresh_shadow_zero(p, shadow, grad):
+    """shadow = bf16(p) and grad = 0 in one pass (received slices of a sharded optimizer step)."""
+    check(_lib.lib().b200pdm_refresh_shadow_zero(p.data_ptr(), shadow.data_ptr(), _ptr(grad), p.numel(), _stream()),
+          "refresh_shadow_zero")
+
+
 def refresh_shadow(p, shadow):
     check(_lib.lib().b200pdm_refresh_shadow(p.data_ptr(), shadow.data_ptr(), p.numel(), _stream()), "refresh_shadow")
 

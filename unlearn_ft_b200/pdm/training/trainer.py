@@ -280,6 +280,10 @@ class GradReducer:
         self.arena = model.arena
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        # optimizer sharded over the ranks (see _sharded_update); B200PDM_NO_SHARD=1 keeps the replicated update (A/B)
+        self.shard = not os.environ.get("B200PDM_NO_SHARD")
+        self.shards = {}        # (start, end) of every sharded bucket -> slice length
         on_gpu = torch.cuda.is_available() and getattr(self.arena.grad, "is_cuda", False)
         self.stream = torch.cuda.Stream() if on_gpu else None
         self.pending = []
@@ -345,6 +349,11 @@ class GradReducer:
         self.stream_used = True
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
+            if self.world > 1 and self.shard and self.on_landed is not None:
+                self.done.append((start, end))
+                self._sharded_update(start, end)
+                self.consumed.append((start, end))
+                return
             work = None
             if self.world > 1:
                 self.done.append((start, end))
@@ -356,6 +365,44 @@ class GradReducer:
                 self.consumed.append((start, end))
             else:
                 self.pending.append((work, start, end))
+
+    @torch.no_grad()
+    def _sharded_update(self, start: int, end: int):
+        """Bucket [start, end) with the optimizer sharded over the ranks ("ZeRO-1 style sharding of the AdamW update
+        + all-gather"): reduce-scatter(avg) the gradient -- each rank receives the mean of ITS 1/world slice --, AdamW on that
+        slice only (`on_landed`), all-gather the updated fp32 masters, then one light pass over the bucket (bf16 shadow of the
+        received masters + gradient zeroing, 10 B/param).  Same bytes on the wire as the all-reduce it replaces (all-reduce =
+        reduce-scatter + all-gather), same parameters on every rank afterwards, but 34 B/param of optimizer traffic on only
+        1/world of the bucket.  The AdamW moments of a slice live on its owner (`gather_optimizer_state` for checkpoints).
+        The remainder that does not split into `world` 256-byte-aligned slices (< world * 64 elements) is all-reduced and
+        updated redundantly."""
+        a = self.arena
+        W, r = self.world, self.rank
+        unit = W * 64
+        m = (end - start) // unit * unit
+        if m > 0:
+            s = m // W
+            lo = start + r * s
+            g = a.grad[start:start + m]
+            dist.reduce_scatter_tensor(a.grad[lo:lo + s], g, op=dist.ReduceOp.AVG, group=self.group, async_op=True).wait()
+            self.on_landed(lo, lo + s)
+            master = a.master.detach()
+            dist.all_gather_into_tensor(master[start:start + m], master[lo:lo + s], group=self.group, async_op=True).wait()
+            K.refresh_shadow_zero(master[start:start + m], a.shadow[start:start + m], a.grad[start:start + m])
+            self.shards[(start, start + m)] = s
+        if start + m < end:
+            dist.all_reduce(a.grad[start + m:end], op=dist.ReduceOp.AVG, group=self.group, async_op=True).wait()
+            self.on_landed(start + m, end)
+
+    @torch.no_grad()
+    def gather_optimizer_state(self, *optimizers):
+        """Make every rank hold the complete AdamW moments (checkpointing): all-gather the owner slices of every sharded bucket."""
+        if self.world == 1 or not self.shards:
+            return
+        for opt in optimizers:
+            for (lo, hi), s in self.shards.items():
+                for buf in (opt.exp_avg, opt.exp_avg_sq):
+                    dist.all_gather_into_tensor(buf[lo:hi], buf[lo + self.rank * s:lo + (self.rank + 1) * s].clone(), group=self.group)
 
     def _join(self):
         """Current stream waits for the reducer's stream -- only if this step put work on it (inside a graph capture, waiting
@@ -546,6 +593,7 @@ class UnetFineTuner:
         `<dir>/<subfolder>/{config.json, diffusion_pytorch_model.safetensors}`, `<dir>/arch_vector.pt`, optimizer + scheduler
         state (`optimizer.bin` / `scheduler.bin`, the accelerate file names)."""
         self.student.save_pretrained(os.path.join(output_dir, subfolder))
+        self.reducer.gather_optimizer_state(self.optimizer)          # (moments are sharded over the ranks, see GradReducer)
         self._save_optim(output_dir, self.optimizer, self.lr_scheduler, "")
 
     @staticmethod
@@ -666,6 +714,7 @@ class BilevelUnetFineTuner(UnetFineTuner):
     def save_checkpoint(self, output_dir, subfolder="unet"):
         """Both prepared optimizer / scheduler pairs, as the reference saves them (trainer.py:2720-2724)."""
         super().save_checkpoint(output_dir, subfolder)
+        self.reducer.gather_optimizer_state(self.upper_optimizer)
         self._save_optim(output_dir, self.upper_optimizer, self.upper_lr_scheduler, "_1")
 
     def load_checkpoint(self, input_dir, subfolder="unet"):
