@@ -329,10 +329,10 @@ def sampling_bench(args, rank, world, local_rank):
 
     n0 = _lib.launch_count()
     sampler.use_cuda_graph, keep = False, sampler.use_cuda_graph
-    sampler.steps, full = 1, sampler.steps
+    sampler.evals, full = 1, sampler.evals
     sampler.sample(*dev[0])                                       # one eager step: kernels per denoising step
     launches_per_call = (_lib.launch_count() - n0) * full
-    sampler.steps, sampler.use_cuda_graph = full, keep
+    sampler.evals, sampler.use_cuda_graph = full, keep
     for i in range(max(1, min(args.warmup, 2))):
         sampler.sample(*dev[i % 2])
     barrier()

@@ -341,6 +341,16 @@ int b200pdm_cfg_ddim_step(const float* model_out, float* latents, float* latent_
                           const int64_t* timesteps, int* state, int64_t* t_dev, int n, int64_t chw, int num_steps,
                           int train_timesteps, float guidance_scale, b200pdm_stream_t stream);
 
+/* The same fused step for diffusers PNDMScheduler(skip_prk_steps=True, steps_offset=1, set_alpha_to_one=False, v_prediction):
+ * the scheduler scripts/metrics/generate_fid_images.py:113 loads for FID image generation.  Linear multistep over the last
+ * four guided model outputs (step_plms): timesteps = int64[num_steps + 1] as PNDMScheduler.set_timesteps builds them (the
+ * second entry repeated: num_steps + 1 U-Net evaluations); ets = fp32 [4][n*chw] ring of model outputs, cur_sample = fp32
+ * [n*chw] (the sample the warm-up evaluation returns to); state = int32[4] {counter, done, #ets, ring head}, zeroed before a
+ * loop.  Everything step-dependent lives on the device: one captured step replays num_steps + 1 times.                  */
+int b200pdm_cfg_pndm_step(const float* model_out, float* latents, float* latent_in, const float* alphas_cumprod,
+                          const int64_t* timesteps, int* state, int64_t* t_dev, float* ets, float* cur_sample, int n, int64_t chw,
+                          int num_steps, int train_timesteps, float guidance_scale, b200pdm_stream_t stream);
+
 /* Forward diffusion (diffusers DDIMScheduler.add_noise / get_velocity at trainer.py:2430,2443):
  * noisy = sa[t_b] x0 + sb[t_b] eps ; target = sa[t_b] eps - sb[t_b] x0 ; fp32.                             */
 int b200pdm_diffusion_prep(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,

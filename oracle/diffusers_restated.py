@@ -893,3 +893,58 @@ class DDIMSchedulerLite:
         pred_eps = a_t ** 0.5 * model_output + b_t ** 0.5 * sample
         direction = (1 - a_prev) ** 0.5 * pred_eps                            # sigma_t = 0
         return a_prev ** 0.5 * pred_x0 + direction
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# diffusers.schedulers.PNDMScheduler -- what scripts/metrics/generate_fid_images.py:113 loads from the SD-2.1 hub folder
+# (scheduler_config.json: skip_prk_steps True, steps_offset 1, set_alpha_to_one False, timestep_spacing "leading",
+# prediction_type v_prediction).  Restated from diffusers 0.30.3 `scheduling_pndm.py` (set_timesteps / step_plms /
+# _get_prev_sample); unpinned like the rest of this file.
+# ----------------------------------------------------------------------------------------------------------------
+class PNDMSchedulerLite(DDIMSchedulerLite):
+    def set_timesteps(self, num_inference_steps, device=None):
+        T = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        step_ratio = T // num_inference_steps
+        base = (torch.arange(0, num_inference_steps) * step_ratio).round().to(torch.int64) + 1            # steps_offset = 1
+        plms = torch.cat([base[:-1], base[-2:-1], base[-1:]]).flip(0)                                      # skip_prk_steps
+        self.timesteps = plms.to(device) if device is not None else plms
+        self.init_noise_sigma = 1.0
+        self.ets, self.counter, self.cur_sample = [], 0, None
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0):
+        """PNDMScheduler.step -> step_plms (the PRK phase is skipped): fourth-order linear multistep."""
+        t = int(timestep)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        prev_t = t - ratio
+        if self.counter != 1:
+            self.ets = self.ets[-3:]
+            self.ets.append(model_output)
+        else:
+            prev_t = t
+            t = t + ratio
+        if len(self.ets) == 1 and self.counter == 0:
+            self.cur_sample = sample
+        elif len(self.ets) == 1 and self.counter == 1:
+            model_output = (model_output + self.ets[-1]) / 2
+            sample = self.cur_sample
+            self.cur_sample = None
+        elif len(self.ets) == 2:
+            model_output = (3 * self.ets[-1] - self.ets[-2]) / 2
+        elif len(self.ets) == 3:
+            model_output = (23 * self.ets[-1] - 16 * self.ets[-2] + 5 * self.ets[-3]) / 12
+        else:
+            model_output = (1 / 24) * (55 * self.ets[-1] - 59 * self.ets[-2] + 37 * self.ets[-3] - 9 * self.ets[-4])
+        self.counter += 1
+        return self._get_prev_sample(sample, t, prev_t, model_output)
+
+    def _get_prev_sample(self, sample, t, prev_t, model_output):
+        acp = self.alphas_cumprod.to(sample.device)
+        a_t = acp[t]
+        a_prev = acp[prev_t] if prev_t >= 0 else acp[0]                       # final_alpha_cumprod (set_alpha_to_one False)
+        b_t, b_prev = 1 - a_t, 1 - a_prev
+        assert self.config.prediction_type == "v_prediction"
+        model_output = a_t ** 0.5 * model_output + b_t ** 0.5 * sample        # v -> epsilon
+        sample_coeff = (a_prev / a_t) ** 0.5
+        denom = a_t * b_prev ** 0.5 + (a_t * b_t * a_prev) ** 0.5
+        return sample_coeff * sample - (a_prev - a_t) * model_output / denom

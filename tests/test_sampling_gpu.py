@@ -75,3 +75,61 @@ def test_cfg_sampling_loop_matches_oracle(graph, steps, guidance):
     print(f"sampling loop (steps {steps}, guidance {guidance}, graph {graph}): ours vs fp32 oracle {l2(out, ref):.4f} / "
           f"{l2(out2, ref):.4f}, torch bf16 autocast vs fp32 oracle {yard:.4f}")
     assert l2(out, ref) < 2 * yard and l2(out2, ref) < 2 * yard
+
+
+@pytest.mark.parametrize("steps", [50, 7])
+def test_cfg_pndm_step_kernel_matches_oracle(steps):
+    """The fused CFG + PNDM (PLMS, skip_prk_steps) step -- the scheduler scripts/metrics/generate_fid_images.py:113 loads --
+    against the oracle's restated PNDMScheduler over all num_steps + 1 evaluations (warm-up pair, 2nd/3rd/4th-order steps)."""
+    from oracle import diffusers_restated as D
+    from unlearn_ft_b200 import kernels as K
+    n, c, h, w, g = 3, 4, 16, 16, 7.5
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    sched = D.PNDMSchedulerLite()
+    sched.set_timesteps(steps, device="cuda")
+    assert len(sched.timesteps) == steps + 1 and int(sched.timesteps[1]) == int(sched.timesteps[2])
+    lat = torch.randn(n, c, h, w, device="cuda", generator=gen)
+    lat_ref = lat.clone()
+    lat_in = torch.zeros(2 * n, c, h, w, device="cuda")
+    state = torch.zeros(4, device="cuda", dtype=torch.int32)
+    ets = torch.zeros(4, n, c, h, w, device="cuda")
+    cur = torch.zeros(n, c, h, w, device="cuda")
+    t_dev = torch.full((2 * n,), int(sched.timesteps[0]), device="cuda", dtype=torch.int64)
+    acp = sched.alphas_cumprod.cuda()
+    for i, t in enumerate(sched.timesteps):
+        assert int(t_dev[0]) == int(t) and int(state[0]) == i
+        out = torch.randn(2 * n, c, h, w, device="cuda", generator=gen)
+        K.cfg_pndm_step(out, lat, lat_in, acp, sched.timesteps, state, t_dev, ets, cur, steps, 1000, g)
+        u, cnd = out.chunk(2)
+        lat_ref = sched.step(u + g * (cnd - u), t, lat_ref)
+        assert rel(lat, lat_ref) < 2e-5, i
+        assert torch.equal(lat_in[:n], lat) and torch.equal(lat_in[n:], lat)
+    assert int(state[0]) == steps + 1 and int(state[1]) == 0
+
+
+def test_cfg_pndm_sampling_loop_matches_oracle():
+    from oracle import diffusers_restated as D
+    from oracle import pdm_restated as P
+    from unlearn_ft_b200.pdm.pipelines import CFGSampler
+    from tests.test_unet_gpu import build_pair
+    gold = torch.load(GOLD, weights_only=False)
+    mine, orc = build_pair(gold["small64_r055"]["arch_vector"], trainable=False)
+    n, steps, guidance = 2, 6, 7.5
+    gen = torch.Generator().manual_seed(12)
+    lat0 = torch.randn(n, 4, 16, 16, generator=gen).cuda()
+    pos = torch.randn(n, 77, 64, generator=gen).cuda()
+    neg = torch.randn(1, 77, 64, generator=gen).cuda().expand(n, -1, -1).contiguous()
+    ref = P.cfg_sample_loop(orc, D.PNDMSchedulerLite(), lat0.clone(), pos, neg, steps, guidance)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref_bf = P.cfg_sample_loop(orc, D.PNDMSchedulerLite(), lat0.clone(), pos, neg, steps, guidance)
+
+    def l2(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+    yard = max(l2(ref_bf, ref), 5e-3)
+    sampler = CFGSampler(mine, num_inference_steps=steps, guidance_scale=guidance, use_cuda_graph=True, scheduler="pndm")
+    assert sampler.evals == steps + 1
+    out = sampler.sample(lat0, pos, neg).clone()
+    out2 = sampler.sample(lat0, pos, neg).clone()
+    print(f"PNDM loop: ours vs fp32 oracle {l2(out, ref):.4f}, torch bf16 autocast vs fp32 oracle {yard:.4f}")
+    assert l2(out, ref) < 2 * yard and torch.equal(out, out2)        # (graph replay of a bit-reproducible forward)

@@ -113,6 +113,7 @@ _SIGS = {
                               f32, c_p, c_p, C.c_size_t, c_p],
     "b200pdm_adamw_step": [c_p, c_p, c_p, c_p, c_p, i64, f32, f32, f32, f32, f32, i64, f32, i32, c_p],
     "b200pdm_cfg_ddim_step": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, i32, i32, f32, c_p],
+    "b200pdm_cfg_pndm_step": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, i32, i64, i32, i32, f32, c_p],
     "b200pdm_adamw_step_dyn": [c_p, c_p, c_p, c_p, c_p, i64, c_p, f32, f32, f32, f32, f32, i32, c_p],
     "b200pdm_refresh_shadow": [c_p, c_p, i64, c_p],
     "b200pdm_refresh_shadow_zero": [c_p, c_p, c_p, i64, c_p],

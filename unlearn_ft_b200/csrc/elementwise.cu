@@ -515,6 +515,77 @@ __global__ void cfg_ddim_step_kernel(const float* __restrict__ model_out, float*
   }
 }
 
+// Same fused step for diffusers PNDMScheduler(skip_prk_steps=True) -- the scheduler of the SD-2.1 hub config that
+// scripts/metrics/generate_fid_images.py:113 loads: linear multistep (PLMS) over the last four guided model outputs.
+// `timesteps` holds the N + 1 entries of PNDMScheduler.set_timesteps (the second one repeated); `ets` is a ring of the last four
+// model outputs [4][n*chw], `cur_sample` the sample kept by the warm-up step; state = {counter, done counter, ets count, ring head}.
+__global__ void cfg_pndm_step_kernel(const float* __restrict__ model_out, float* __restrict__ latents, float* __restrict__ latent_in,
+                                     const float* __restrict__ alphas_cumprod, const int64_t* __restrict__ timesteps,
+                                     int* __restrict__ state, int64_t* __restrict__ t_dev, float* __restrict__ ets,
+                                     float* __restrict__ cur_sample, int n, int64_t chw, int num_steps, int train_T, float guidance) {
+  pdl_trigger();
+  const int k = state[0], n_ets0 = state[2], head0 = state[3];
+  const int ratio = train_T / num_steps;
+  int64_t t = timesteps[k < num_steps + 1 ? k : num_steps], t_prev = t - ratio;
+  if (k == 1) t_prev = t, t = t + ratio;                       // second evaluation of the first interval (step_plms, counter == 1)
+  const bool push = k != 1;
+  const int n_ets = push ? min(n_ets0 + 1, 4) : n_ets0;
+  const int head = push ? (head0 + 1) & 3 : head0;             // ring slot of the newest entry
+  const float a_t = alphas_cumprod[t];
+  const float a_prev = t_prev >= 0 ? alphas_cumprod[t_prev] : alphas_cumprod[0];   // set_alpha_to_one = False
+  const float b_t = 1.f - a_t, b_prev = 1.f - a_prev;
+  const float sample_coeff = sqrtf(a_prev / a_t);
+  const float denom = a_t * sqrtf(b_prev) + sqrtf(a_t * b_t * a_prev);
+  const float sa = sqrtf(a_t), sb = sqrtf(b_t);
+  const int64_t total = (int64_t)n * chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = model_out[i], c = model_out[total + i];
+    const float g = u + guidance * (c - u);
+    if (push) ets[(int64_t)head * total + i] = g;
+    const float e1 = push ? g : ets[(int64_t)head * total + i];
+    float m;
+    float x = latents[i];
+    if (k == 0) {
+      m = g;
+      cur_sample[i] = x;
+    } else if (k == 1) {
+      m = 0.5f * (g + e1);
+      x = cur_sample[i];
+    } else {
+      const float e2 = ets[(int64_t)((head + 3) & 3) * total + i];
+      if (n_ets == 2) {
+        m = 0.5f * (3.f * e1 - e2);
+      } else {
+        const float e3 = ets[(int64_t)((head + 2) & 3) * total + i];
+        if (n_ets == 3) {
+          m = (23.f * e1 - 16.f * e2 + 5.f * e3) * (1.f / 12.f);
+        } else {
+          const float e4 = ets[(int64_t)((head + 1) & 3) * total + i];
+          m = (1.f / 24.f) * (55.f * e1 - 59.f * e2 + 37.f * e3 - 9.f * e4);
+        }
+      }
+    }
+    const float eps = sa * m + sb * x;                         // v-prediction -> epsilon (_get_prev_sample)
+    const float xp = sample_coeff * x - (a_prev - a_t) * eps / denom;
+    latents[i] = xp;
+    latent_in[i] = xp;
+    latent_in[total + i] = xp;
+  }
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(state + 1), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    const int next = k + 1;
+    const int64_t tn = timesteps[next < num_steps + 1 ? next : num_steps];
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) t_dev[i] = tn;
+    if (threadIdx.x == 0) state[0] = next, state[1] = 0, state[2] = n_ets, state[3] = head;
+  }
+}
+
 // ---------------------------------------------------------------- forward diffusion prep
 __global__ void diffusion_prep_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                       const int64_t* __restrict__ t, const float* __restrict__ sa,
@@ -769,6 +840,18 @@ int b200pdm_cfg_ddim_step(const float* model_out, float* latents, float* latent_
   launch_pdl(cfg_ddim_step_kernel, grid_for((int64_t)n * chw, 256), 256, 0, STREAM, 
       model_out, latents, latent_in, alphas_cumprod, timesteps, state, t_dev, n, chw, num_steps, train_timesteps, guidance_scale,
       reinterpret_cast<unsigned int*>(state + 1));
+  B200_CHECK_LAUNCH();
+  g_launches++;
+  return B200PDM_OK;
+}
+int b200pdm_cfg_pndm_step(const float* model_out, float* latents, float* latent_in, const float* alphas_cumprod,
+                          const int64_t* timesteps, int* state, int64_t* t_dev, float* ets, float* cur_sample, int n, int64_t chw,
+                          int num_steps, int train_timesteps, float guidance_scale, b200pdm_stream_t stream) {
+  if (!model_out || !latents || !latent_in || !alphas_cumprod || !timesteps || !state || !t_dev || !ets || !cur_sample || n <= 0 ||
+      chw <= 0 || num_steps <= 0 || train_timesteps < num_steps)
+    return B200PDM_ERR_ARG;
+  launch_pdl(cfg_pndm_step_kernel, grid_for((int64_t)n * chw, 256), 256, 0, STREAM, model_out, latents, latent_in, alphas_cumprod,
+             timesteps, state, t_dev, ets, cur_sample, n, chw, num_steps, train_timesteps, guidance_scale);
   B200_CHECK_LAUNCH();
   g_launches++;
   return B200PDM_OK;

@@ -259,7 +259,10 @@ constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kAtomBytes = 64 * 64 * 2;              // one [64 k][64 mn] MN-major atom = 8 KiB
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
-constexpr int kMaxEpiGroups = 2;                      // epilogue warpgroups (4 warps each); 2 for epilogue-bound shapes
+#ifndef B200PDM_MAX_EPI_GROUPS
+#define B200PDM_MAX_EPI_GROUPS 2
+#endif
+constexpr int kMaxEpiGroups = B200PDM_MAX_EPI_GROUPS;   // epilogue warpgroups (4 warps each)
 constexpr int kMaxThreads = 64 + 128 * kMaxEpiGroups;
 
 template <bool PAIR>
@@ -1321,8 +1324,8 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
       const char* e = getenv("B200PDM_EPI_GROUPS");
       env_eg = e ? atoi(e) : 0;
     }
-    p.epi_groups = 2;   // measured: never slower than one group, up to 1.4x faster on small-K shapes
-    if (env_eg == 1 || env_eg == 2) p.epi_groups = env_eg;
+    p.epi_groups = kMaxEpiGroups;   // measured: never slower than one group, up to 1.4x faster on small-K shapes
+    if (env_eg >= 1 && env_eg <= kMaxEpiGroups) p.epi_groups = env_eg;
   }
   const int stage_bytes = p.m_sub * kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
   const int fixed_bytes = 1024 + (2 * 8 + 6) * 8 + 64 + 128 + 4 * p.epi_groups * 1024;
@@ -1483,7 +1486,7 @@ int b200pdm_gemm_plan(int64_t n, int n_groups, int b_mn, int tiles_m, int Z, int
   if (!out || n <= 0 || n_groups <= 0 || tiles_m <= 0 || Z <= 0 || kblocks <= 0) return B200PDM_ERR_ARG;
   const Plan plan = plan_gemm(n, n_groups, b_mn != 0, tiles_m, Z, kblocks, can_split != 0, split_needs_finalize != 0, 0);
   if (plan.bn <= 0) return B200PDM_ERR_ARG;
-  const int epi_groups = 2;
+  const int epi_groups = kMaxEpiGroups;
   const int stage_bytes = plan.m_sub * kStageABytes + (plan.pair ? plan.bn / 2 : plan.bn) * 128;
   const int fixed_bytes = 1024 + (2 * 8 + 6) * 8 + 64 + 128 + 4 * epi_groups * 1024;
   int stages = (227 * 1024 - fixed_bytes) / stage_bytes;

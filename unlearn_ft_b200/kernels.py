@@ -548,6 +548,17 @@ def cfg_ddim_step(model_out, latents, latent_in, alphas_cumprod, timesteps, stat
                                            n, chw, num_steps, train_timesteps, float(guidance), _stream()), "cfg_ddim_step")
 
 
+def cfg_pndm_step(model_out, latents, latent_in, alphas_cumprod, timesteps, state, t_dev, ets, cur_sample, num_steps,
+                  train_timesteps, guidance):
+    """Fused CFG combine + PNDM (PLMS) step (see include/b200pdm.h); in place, all state on the device."""
+    n = latents.shape[0]
+    chw = latents.numel() // n
+    check(_lib.lib().b200pdm_cfg_pndm_step(model_out.data_ptr(), latents.data_ptr(), latent_in.data_ptr(), alphas_cumprod.data_ptr(),
+                                           timesteps.data_ptr(), state.data_ptr(), t_dev.data_ptr(), ets.data_ptr(),
+                                           cur_sample.data_ptr(), n, chw, num_steps, train_timesteps, float(guidance), _stream()),
+          "cfg_pndm_step")
+
+
 def diffusion_prep(x0, noise, t, sqrt_acp, sqrt_1macp):
     B = x0.shape[0]
     noisy, vt = torch.empty_like(x0), torch.empty_like(x0)
