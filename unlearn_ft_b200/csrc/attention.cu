@@ -61,9 +61,10 @@ struct AttnFwdParams {
 //                       is rare), written as bf16 P into a swizzle-128B tile for the second MMA
 // Both roles issue from warp-uniform code through elect.sync.  O leaves TMEM once, at the end.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int kFwd2Threads = 320;
+constexpr int kFwd2Threads = 64 + 4 * 128;   // TMA warp, MMA warp, four softmax warpgroups
 constexpr int kKVStages = 3;
 constexpr float kRescaleThreshold = 8.f;   // log2 domain
+constexpr int kPCol = 384;                 // TMEM: S_t at 128 t, O_t at 256 + 64 t, P_t (bf16 pairs) at 384 + 64 t
 
 __global__ void __launch_bounds__(kFwd2Threads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -102,7 +103,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
@@ -164,14 +165,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tc_fence_after();
       }
       for (int t = 0; t < n_qt; ++t) {
-        mbar_wait(&p_full[t], j & 1);   // P_t(j) is in smem, S_t(j) has been read out of TMEM
+        const bool mprof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+        const long long tm0 = mprof ? clock64() : 0;
+        mbar_wait(&p_full[t], j & 1);   // P_t(j) is in tensor memory, S_t(j) has been read out of it
         tc_fence_after();
+        if (mprof) p.dbg[4 + t * 8] += clock64() - tm0;
         if (elect_one()) {
-          const uint32_t a = p_lo + t * (2 * kTileBytes >> 4), bv = kv_lo + (stage * 2 * kTileBytes + kTileBytes) / 16;
+          const uint32_t bv = kv_lo + (stage * 2 * kTileBytes + kTileBytes) / 16;
 #pragma unroll
-          for (int k = 0; k < kKV / 16; ++k)
-            umma_bf16(tmem + 256 + t * 64, dk | (a + (k >> 2) * (kTileBytes >> 4) + (k & 3) * 2), dv | (bv + k * 128), idesc_o,
-                      (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kKV / 16; ++k)   // A = P_t straight from tensor memory: 8 columns (16 bf16 keys) per K step
+            umma_bf16_ts(tmem + 256 + t * 64, tmem + kPCol + t * 64 + k * 8, dv | (bv + k * 128), idesc_o,
+                         (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(&pv_done[t]);
           if (j + 1 < p.nkv) issue_s(t, nstage);
         }
@@ -179,133 +183,181 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (elect_one()) umma_commit(&kv_empty[stage]);   // both tiles' PV(j) (and S(j), long before) have read this stage
       stage = nstage, phase = nphase;
     }
-  } else if (((warp - 2) >> 2) < n_qt) {
+  } else if (((warp - 2) >> 3) < n_qt) {
     // ===================== softmax warpgroups =====================
-    const int t = (warp - 2) >> 2;
+    // FOUR warpgroups: query tile t = wg >> 1, key half = wg & 1.  A thread owns one query row (= TMEM lane) and 64 of the 128
+    // keys of a block.  It reads its 64 scores out of tensor memory ONCE (TMEM reads run at 64 B/clk/SM: the two passes of the
+    // round-1 kernel -- maximum, then exponentials -- cost 4096 cycles per pair of 128x128 tiles, twice the MUFU bound and
+    // exactly what that kernel measured), keeps them in registers, exponentiates at once against the STALE running maximum
+    // while the second half of the read is still in flight, and writes the bf16 probabilities back into tensor memory, where the
+    // PV MMA takes them as its A operand (no shared-memory round trip for P).  The two threads of a row agree on the block
+    // maximum afterwards through a 4-byte shared-memory exchange and a 64-thread named barrier; only if a row's maximum grew
+    // by more than 2^8 -- rare after the first blocks -- is the accumulator rescaled and the block redone from registers.
+    const int wg = (warp - 2) >> 2;
+    const int t = wg >> 1, half = wg & 1;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t tmem_s = tmem + t * 128 + lane_base, tmem_o = tmem + 256 + t * 64 + lane_base;
-    const uint32_t p_row = smem_u32(sP) + t * 2 * kTileBytes + r * 128;
-    const int sw = r & 7;
+    const uint32_t tmem_s = tmem + t * 128 + half * 64 + lane_base;          // this thread's 64 score columns
+    const uint32_t tmem_o = tmem + 256 + t * 64 + half * 32 + lane_base;     // the 32 O columns it rescales / writes
+    const uint32_t tmem_p = tmem + kPCol + t * 64 + half * 32 + lane_base;   // its 64 probabilities = 32 packed columns
+    float* xch = reinterpret_cast<float*>(bars + 32);                        // [parity 2][tile 2][quarter 4][half 2][32 lanes]
+    const int bar_id = 1 + t * 4 + qd;                                       // the two warps that share these 32 rows
+    auto xslot = [&](int par, int hh) { return xch + (((par * 2 + t) * 4 + qd) * 2 + hh) * 32 + lane; };
     float m = -INFINITY, l = 0.f;
+    // One 32-key chunk: p = exp2(s * c - mref) -> 16 packed bf16 columns of this row's P; accumulates the row sum (lsum) and
+    // the running maximum of the raw scores (mx).
+    auto exp_chunk = [&](const uint32_t(&vv)[32], int c, int vh, float mref, float& lsum, float& mx) {
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-mref, -mref);
+      float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float l4 = 0.f, mxa = mx, mxb = mx;
+      uint32_t pk[16];
+      if (vh == 64) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {   // packed pairs: one FFMA2 + one FADD2 per two scores
+          const float s0 = __uint_as_float(vv[2 * i]), s1 = __uint_as_float(vv[2 * i + 1]);
+          mxa = fmaxf(mxa, s0), mxb = fmaxf(mxb, s1);
+          const float2 xs = ffma2(make_float2(s0, s1), sc2, nm2);
+          // (kExpFmaMask: share of the exponentials evaluated on the FMA pipe instead of MUFU.EX2, see the top of the file)
+          const float2 e = make_float2(((2 * i) & kExpFmaMask) == kExpFmaMask ? exp2_fma(xs.x) : exp2f(xs.x),
+                                       ((2 * i + 1) & kExpFmaMask) == kExpFmaMask ? exp2_fma(xs.y) : exp2f(xs.y));
+          ls2[i & 1] = fadd2(ls2[i & 1], e);
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e.x, e.y);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float e2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const bool ok = c * 32 + 2 * i + u < vh;
+            const float sv = __uint_as_float(vv[2 * i + u]);
+            if (ok) mxa = fmaxf(mxa, sv);
+            e2[u] = ok ? exp2f(fmaf(sv, p.scale_log2, -mref)) : 0.f;
+            l4 += e2[u];
+          }
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e2[0], e2[1]);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+      }
+      tmem_st_32x16(tmem_p + c * 16, pk);
+      lsum += l4 + ((ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y));
+      mx = fmaxf(mxa, mxb);
+    };
+    auto max_chunk = [&](const uint32_t(&vv)[32], int c, int vh, float& mx) {
+      float m4[4] = {mx, mx, mx, mx};
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (vh == 64 || c * 32 + i < vh) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(vv[i]));
+      mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    };
+    // Optional MUFU turn-taking between the two query tiles (-DB200PDM_ATTN_PINGPONG; named barriers 9 / 10 pass a token between
+    // the tiles' 256 threads each).  Phase timers (make diag, B200PDM_ATTN_DBG) show the tiles running IN PHASE: both
+    // exponentiate at the MUFU rate (2300-2700 cycles per key block) and then both wait ~1100 cycles for their PV / next-S MMAs.
+    // Taking turns does not help: with only one tile's two warps per scheduler active, the in-order MUFU -> FADD2 / F2FP
+    // dependence (ptxas places consumers one pair behind their producers) makes a tile's exponentials latency-bound at ~1750
+    // cycles, and 2 x 1750 equals the in-phase period.  Measured equal (568 us), so it stays off.
+#ifdef B200PDM_ATTN_PINGPONG
+    const bool pingpong = n_qt == 2;
+#else
+    const bool pingpong = false;
+#endif
+    auto token_wait = [&]() {
+      if (pingpong) asm volatile("bar.sync %0, 512;" ::"r"(9 + t) : "memory");
+    };
+    auto token_pass = [&]() {
+      if (pingpong) asm volatile("bar.arrive %0, 512;" ::"r"(9 + (t ^ 1)) : "memory");
+    };
+    if (pingpong && t == 1) asm volatile("bar.arrive %0, 512;" ::"r"(9) : "memory");   // tile 0 goes first
     for (int j = 0; j < p.nkv; ++j) {
       int valid = min(kKV, p.Lk - j * kKV);  // keys in this block
       if (p.causal) valid = min(valid, q0 + t * kQ + r - j * kKV + 1);   // ... that this row may attend (can be <= 0)
-      const bool prof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 64 || threadIdx.x == 192);
-      const int pslot = (threadIdx.x == 64) ? 0 : 8;
-      long long tp0 = prof ? clock64() : 0;
+      const int vh = min(64, max(0, valid - half * 64));                 // ... of them in this thread's half
+      const bool prof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && qd == 2 && half == 0;
+      const long long tp0 = prof ? clock64() : 0;
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      long long tp1 = prof ? clock64() : 0;
-      // pass 1: row maximum of the block (two rounds of 64 columns; masking only on the ragged last block)
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(tmem_s + hh * 64, va);
-        tmem_ld_32x32(tmem_s + hh * 64 + 32, vb);
-        tmem_ld_wait();
-        if (valid == kKV) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (hh * 64 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(va[i]));
-            if (hh * 64 + 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(vb[i]));
-          }
-        }
-      }
-      float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
-      if (valid <= 0) m_tile = (j == 0) ? 0.f : m;      // (causal: nothing to attend in this block -- all its p are 0)
+      const long long tp1 = prof ? clock64() : 0;
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_s, v0);
+      tmem_ld_wait();
+      const long long tp2 = prof ? clock64() : 0;
+      tmem_ld_32x32(tmem_s + 32, v1);                   // in flight while the first chunk is processed
+      float mx = -INFINITY, lsum = 0.f;
+      bool redo = false;
       if (j == 0) {
-        m = m_tile;
+        // first block: no reference maximum yet -- maximum first, then the exponentials
+        max_chunk(v0, 0, vh, mx);
+        tmem_ld_wait();
+        max_chunk(v1, 1, vh, mx);
+        *xslot(0, half) = mx * p.scale_log2;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        m = fmaxf(mx * p.scale_log2, *xslot(0, half ^ 1));
+        if (valid <= 0) m = 0.f;                        // (causal: nothing to attend in this block -- all its p are 0)
+        redo = true;
       } else {
-        // lazy rescaling: keep the stale maximum unless this row's maximum grew by more than 2^8
+        mbar_wait(&pv_done[t], (j - 1) & 1);            // PV(j-1) has consumed P_t (it preceded S_t(j) on the tensor pipe)
+        token_wait();
+        exp_chunk(v0, 0, vh, m, lsum, mx);
+        tmem_ld_wait();
+        exp_chunk(v1, 1, vh, m, lsum, mx);
+        token_pass();
+        *xslot(j & 1, half) = mx * p.scale_log2;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        float m_tile = fmaxf(mx * p.scale_log2, *xslot(j & 1, half ^ 1));
+        if (valid <= 0) m_tile = m;
         const bool grow = m_tile - m > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {
+        if (__any_sync(0xffffffffu, grow)) {              // (both warps of these rows see the same values: same branch)
           const float alpha = grow ? exp2f(m - m_tile) : 1.f;
           if (grow) m = m_tile;
           l *= alpha;
-          mbar_wait(&pv_done[t], (j - 1) & 1);   // O_t holds every PV up to block j-1
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(tmem_o + c * 32, o);
+          for (int hh = 0; hh < 2; ++hh) {      // 16 columns at a time: the 64 scores stay in registers meanwhile
+            uint32_t o[16];
+            tmem_ld_32x16(tmem_o + hh * 16, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(tmem_o + c * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(tmem_o + hh * 16, o);
           }
-          tmem_st_wait();
+          redo = true;
         }
       }
-      long long tp2 = prof ? clock64() : 0;
-      if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);   // PV(j-1) has finished reading this tile's P buffer
-      long long tp3 = prof ? clock64() : 0;
-      // pass 2: probabilities -> bf16 P tile (K-major, swizzle-128B); the next chunk's TMEM load is in flight meanwhile
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
-      float2 ls2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m, -m);
-      uint32_t vbuf[2][32];
-      tmem_ld_32x32(tmem_s, vbuf[0]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld_wait();
-        if (c < 3) tmem_ld_32x32(tmem_s + (c + 1) * 32, vbuf[(c + 1) & 1]);
-        const uint32_t(&vv)[32] = vbuf[c & 1];
-        float pf[32];
-        if (valid == kKV) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {   // packed pairs: one FFMA2 + one FADD2 per two scores
-            const float2 xs = ffma2(make_float2(__uint_as_float(vv[2 * i]), __uint_as_float(vv[2 * i + 1])), sc2, nm2);
-            pf[2 * i] = ((2 * i & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs.x) : exp2f(xs.x);
-            pf[2 * i + 1] = (((2 * i + 1) & kExpFmaMask) == kExpFmaMask) ? exp2_fma(xs.y) : exp2f(xs.y);
-            ls2[i & 1] = fadd2(ls2[i & 1], make_float2(pf[2 * i], pf[2 * i + 1]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = exp2f(fmaf(__uint_as_float(vv[i]), p.scale_log2, -m));
-            e = (c * 32 + i < valid) ? e : 0.f;
-            pf[i] = e;
-            l4[i & 3] += e;
-          }
-        }
-        const uint32_t base = p_row + (c >> 1) * kTileBytes;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          __nv_bfloat162 a0 = __floats2bfloat162_rn(pf[g * 8 + 0], pf[g * 8 + 1]);
-          __nv_bfloat162 a1 = __floats2bfloat162_rn(pf[g * 8 + 2], pf[g * 8 + 3]);
-          __nv_bfloat162 a2 = __floats2bfloat162_rn(pf[g * 8 + 4], pf[g * 8 + 5]);
-          __nv_bfloat162 a3 = __floats2bfloat162_rn(pf[g * 8 + 6], pf[g * 8 + 7]);
-          const int chunk = ((c & 1) * 4 + g) ^ sw;
-          sts128(base + chunk * 16, *reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1),
-                 *reinterpret_cast<uint32_t*>(&a2), *reinterpret_cast<uint32_t*>(&a3));
-        }
+      if (redo) {
+        if (j == 0) token_wait();
+        lsum = 0.f;
+        float dummy = -INFINITY;
+        exp_chunk(v0, 0, vh, m, lsum, dummy);
+        exp_chunk(v1, 1, vh, m, lsum, dummy);
+        if (j == 0) token_pass();
       }
-      l += ((l4[0] + l4[1]) + (l4[2] + l4[3])) + ((ls2[0].x + ls2[0].y) + (ls2[1].x + ls2[1].y));
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      l += lsum;
+      const long long tp3 = prof ? clock64() : 0;
+      tmem_st_wait();       // P_t (and a rescaled O_t) are in tensor memory
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
       if (prof) {
         const long long tp4 = clock64();
-        p.dbg[pslot + 0] += tp1 - tp0, p.dbg[pslot + 1] += tp2 - tp1, p.dbg[pslot + 2] += tp3 - tp2, p.dbg[pslot + 3] += tp4 - tp3;
+        long long* d = p.dbg + t * 8;
+        d[0] += tp1 - tp0, d[1] += tp2 - tp1, d[2] += tp3 - tp2, d[3] += tp4 - tp3;
       }
     }
     mbar_wait(&pv_done[t], (p.nkv - 1) & 1);
     tc_fence_after();
+    // row sum over both halves
+    const int par = p.nkv & 1;                      // a slot the last block's exchange did not use
+    *xslot(par, half) = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    const float l_tot = l + *xslot(par, half ^ 1);
     const int q = q0 + t * kQ + r;
-    const float inv = 1.f / l;
-    bf16* dst = p.out + (static_cast<int64_t>(b) * p.Lq + q) * p.ldo + h * kD;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    const float inv = 1.f / l_tot;
+    bf16* dst = p.out + (static_cast<int64_t>(b) * p.Lq + q) * p.ldo + h * kD + half * 32;
+    {
       uint32_t o[32];
-      tmem_ld_32x32(tmem_o + c * 32, o);
+      tmem_ld_32x32(tmem_o, o);
       tmem_ld_wait();
       if (q < p.Lq) {
 #pragma unroll
@@ -313,11 +365,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           float t8[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) t8[i] = __uint_as_float(o[g * 8 + i]) * inv;
-          *reinterpret_cast<bf16x8*>(dst + c * 32 + g * 8) = pack8(t8);
+          *reinterpret_cast<bf16x8*>(dst + g * 8) = pack8(t8);
         }
       }
     }
-    if (q < p.Lq && p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = m + log2f(l);
+    if (half == 0 && q < p.Lq && p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Lq + q] = m + log2f(l_tot);
     tc_fence_before();
   }
   tc_fence_before();
@@ -380,7 +432,7 @@ extern "C" int b200pdm_attention_fwd_ex(const void* q, int64_t ldq, const void* 
   p.dbg = dbg_on ? dbg_buf : nullptr;
 #endif
   cudaError_t e;
-  const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256;
+  const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256 + 4096;   // tiles, barriers, row-maximum exchange
   static bool attr_set = false;   // once, not per launch (graph capture)
   if (!attr_set) {
     e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -403,8 +455,9 @@ extern "C" int b200pdm_attention_fwd_ex(const void* q, int64_t ldq, const void* 
     long long hbuf[16];
     cudaStreamSynchronize(stream);
     cudaMemcpy(hbuf, dbg_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[attn dbg] Lq=%d Lk=%d nkv=%d | wg0: wait_s=%lld pass1=%lld wait_pv=%lld pass2=%lld | wg1: wait_s=%lld pass1=%lld "
-            "wait_pv=%lld pass2=%lld\n", lq, lk, p.nkv, hbuf[0], hbuf[1], hbuf[2], hbuf[3], hbuf[8], hbuf[9], hbuf[10], hbuf[11]);
+    fprintf(stderr, "[attn dbg] Lq=%d Lk=%d nkv=%d | tile0: wait_s=%lld tmem_ld=%lld exp+max+xchg=%lld st_wait+arrive=%lld mma_wait_p=%lld | "
+            "tile1: wait_s=%lld tmem_ld=%lld exp+max+xchg=%lld st_wait+arrive=%lld mma_wait_p=%lld (cycles of CTA 0, summed over the key blocks)\n",
+            lq, lk, p.nkv, hbuf[0], hbuf[1], hbuf[2], hbuf[3], hbuf[4], hbuf[8], hbuf[9], hbuf[10], hbuf[11], hbuf[12]);
   }
 #endif
   return B200PDM_OK;
