@@ -102,6 +102,21 @@ def test_world1_is_noop():
     assert torch.equal(red.arena.grad, g)
 
 
+def test_optimizer_shards_partition_every_bucket():
+    """Sharded optimizer (GradReducer._sharded_update): the owner slices of a bucket are disjoint, 256-byte aligned relative to
+    the bucket start, cover its first m elements exactly once over the ranks, and leave fewer than world * 64 elements to the
+    replicated remainder -- for every world size the bench runs and ragged bucket lengths."""
+    from unlearn_ft_b200.pdm.training.trainer import GradReducer
+    for world in (2, 4, 8):
+        for start, end in ((0, 1000), (128, 128 + 64 * world), (4096, 4096 + 10_000_019), (64, 64 + world * 64 - 1)):
+            spans = [GradReducer.shard_span(start, end, world, r) for r in range(world)]
+            m, s = spans[0][0], spans[0][1]
+            assert all(sp[0] == m and sp[1] == s for sp in spans)
+            assert m % (world * 64) == 0 and s * world == m and 0 <= (end - start) - m < world * 64
+            assert [sp[2] for sp in spans] == [start + r * s for r in range(world)]
+            assert all((sp[2] - start) % 64 == 0 for sp in spans)
+
+
 def test_block_buckets_partition_the_arena():
     """Per-block buckets (fired from each block's backward) are disjoint, contiguous arena slices; together with the
     complement handled by reduce_all() every gradient element is exchanged exactly once."""

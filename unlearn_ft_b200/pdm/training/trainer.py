@@ -377,12 +377,8 @@ class GradReducer:
         The remainder that does not split into `world` 256-byte-aligned slices (< world * 64 elements) is all-reduced and
         updated redundantly."""
         a = self.arena
-        W, r = self.world, self.rank
-        unit = W * 64
-        m = (end - start) // unit * unit
+        m, s, lo = self.shard_span(start, end, self.world, self.rank)
         if m > 0:
-            s = m // W
-            lo = start + r * s
             g = a.grad[start:start + m]
             dist.reduce_scatter_tensor(a.grad[lo:lo + s], g, op=dist.ReduceOp.AVG, group=self.group, async_op=True).wait()
             self.on_landed(lo, lo + s)
@@ -393,6 +389,16 @@ class GradReducer:
         if start + m < end:
             dist.all_reduce(a.grad[start + m:end], op=dist.ReduceOp.AVG, group=self.group, async_op=True).wait()
             self.on_landed(start + m, end)
+
+    @staticmethod
+    def shard_span(start: int, end: int, world: int, rank: int):
+        """(m, s, lo): the first m elements of bucket [start, end) split into `world` slices of s elements (s a multiple of 64
+        elements = 256 bytes of fp32, so every slice keeps the 128-bit alignment of the arena kernels); this rank owns
+        [lo, lo + s); the remainder [start + m, end) has fewer than world * 64 elements."""
+        unit = world * 64
+        m = (end - start) // unit * unit
+        s = m // world
+        return m, s, start + rank * s
 
     @torch.no_grad()
     def gather_optimizer_state(self, *optimizers):
