@@ -196,3 +196,24 @@ def test_encoder_state_dict_keys_match_their_dependencies():
     vae = AutoencoderKL(device="meta", seed=None)
     assert {k: tuple(v.shape) for k, v in vo.state_dict().items()} == {k: tuple(v.shape) for k, v in vae.state_dict().items()}
     assert sum(p.numel() for p in vae.parameters()) == 34_163_664
+
+
+def test_encoder_from_pretrained_reads_the_dependency_folder_layout(tmp_path):
+    """`CLIPTextModel.from_pretrained(root, subfolder="text_encoder")` on a folder written by transformers' own save_pretrained
+    (config.json with many more keys than we use + model.safetensors): config values are taken over, every key is found (strict
+    load).  Meta device: no GPU, no compute."""
+    import pytest
+    import torch
+    from transformers import CLIPTextConfig
+    from transformers import CLIPTextModel as HF
+
+    from unlearn_ft_b200.pdm.models import CLIPTextModel
+    cfg = CLIPTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                         max_position_embeddings=77, hidden_act="gelu", layer_norm_eps=1e-5, projection_dim=64)
+    HF(cfg).save_pretrained(tmp_path / "text_encoder", safe_serialization=True)
+    m = CLIPTextModel.from_pretrained(str(tmp_path), subfolder="text_encoder", device="meta", revision=None)
+    assert (m.config.hidden_size, m.config.num_hidden_layers, m.config.vocab_size) == (128, 2, 1000)
+    assert len(m.text_model.encoder.layers) == 2
+    (tmp_path / "text_encoder" / "model.safetensors").unlink()
+    with pytest.raises(FileNotFoundError):
+        CLIPTextModel.from_pretrained(str(tmp_path), subfolder="text_encoder", device="meta")

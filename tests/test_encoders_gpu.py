@@ -101,6 +101,26 @@ def test_clip_text_encoder_matches_transformers():
     assert torch.equal(emb, out[0]) and emb.dtype == torch.bfloat16
 
 
+def test_encoders_load_from_checkpoint_folders(tmp_path):
+    """`from_pretrained(root, subfolder=...)` (reference trainer.py:2126-2143) on folders in the dependencies' own layout: a
+    transformers CLIPTextModel saved with ITS save_pretrained (config.json + model.safetensors) loads and evaluates equal to the
+    in-memory load; the VAE round-trips through save_pretrained / from_pretrained bit for bit."""
+    from unlearn_ft_b200.pdm.models import AutoencoderKL, CLIPTextModel
+    hf = _hf_text()
+    hf.save_pretrained(tmp_path / "text_encoder", safe_serialization=True)
+    a = CLIPTextModel.from_pretrained(str(tmp_path), subfolder="text_encoder", revision=None, variant=None)
+    b = CLIPTextModel(seed=None)
+    b.load_state_dict(hf.state_dict())
+    ids = torch.randint(0, 49406, (2, 77), generator=torch.Generator().manual_seed(5)).cuda()
+    assert torch.equal(a(ids)[0], b(ids)[0])
+    v = AutoencoderKL(seed=9)
+    v.save_pretrained(str(tmp_path / "vae"))
+    w = AutoencoderKL.from_pretrained(str(tmp_path), subfolder="vae")
+    assert w.config.scaling_factor == 0.18215 and w.config.block_out_channels == (128, 256, 512, 512)
+    x = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(6)).cuda()
+    assert torch.equal(v.encode(x).latent_dist.mean, w.encode(x).latent_dist.mean)
+
+
 @pytest.mark.parametrize("B,HW", [(2, 256), (1, 512)])
 def test_vae_encoder_matches_oracle(B, HW):
     from oracle.make_golden import deterministic_fill

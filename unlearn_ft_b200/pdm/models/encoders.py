@@ -56,6 +56,45 @@ class _Frozen(nn.Module):
         self.arena.shadow_fresh = False
         return out
 
+    _WEIGHTS = ()              # file names tried in order inside the checkpoint folder (set by the subclasses)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, device=None, **kwargs):
+        """Local checkpoint folder in the dependency's own layout: ``<root>/<subfolder>/config.json`` + the safetensors (or
+        .bin) weight file -- the call the reference makes at pdm/training/trainer.py:2126-2143 (`AutoencoderKL.from_pretrained(
+        path, subfolder="vae")`, `CLIPTextModel.from_pretrained(path, subfolder="text_encoder")`).  Hub-only keyword arguments
+        (revision, variant, torch_dtype ...) are accepted and ignored; there is no download path."""
+        import json
+        import os
+        root = os.path.join(str(pretrained_model_name_or_path), subfolder) if subfolder else str(pretrained_model_name_or_path)
+        with open(os.path.join(root, "config.json")) as f:
+            raw = json.load(f)
+        known = cls._default_config()
+        cfg = {k: (tuple(v) if isinstance(v, list) else v) for k, v in raw.items() if k in known}
+        model = cls(cfg, device=device, seed=None)
+        for name in cls._WEIGHTS:
+            path = os.path.join(root, name)
+            if os.path.exists(path):
+                if name.endswith(".safetensors"):
+                    from safetensors.torch import load_file
+                    sd = load_file(path)
+                else:
+                    sd = torch.load(path, map_location="cpu", weights_only=True)
+                model.load_state_dict(sd)
+                return model
+        raise FileNotFoundError(f"none of {cls._WEIGHTS} under {root}")
+
+    def save_pretrained(self, save_directory):
+        """config.json + the first of `_WEIGHTS` (safetensors, fp32, the dependency's key names)."""
+        import json
+        import os
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump({k: (list(v) if isinstance(v, tuple) else v) for k, v in self._config.items()}, f, indent=1)
+        sd = {k: v.detach().float().cpu().contiguous() for k, v in self.state_dict().items()}
+        save_file(sd, os.path.join(save_directory, self._WEIGHTS[0]), metadata={"format": "pt"})
+
     def _check(self):
         if self.arena.device.type != "cuda":
             raise RuntimeError("forward needs a CUDA (sm_100a) device: there is no CPU fallback")
@@ -183,6 +222,11 @@ class _LatentDist:
 
 class AutoencoderKL(_Frozen):
     """Encoder half of diffusers.AutoencoderKL (keys ``encoder.*`` and ``quant_conv.*``; decoder keys are ignored on load)."""
+    _WEIGHTS = ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin")
+
+    @staticmethod
+    def _default_config():
+        return SD21_VAE_CONFIG
 
     def __init__(self, config: Optional[dict] = None, device=None, seed: Optional[int] = 2, **overrides):
         super().__init__()
@@ -287,6 +331,11 @@ class _ClipTextTransformer(nn.Module):
 class CLIPTextModel(_Frozen):
     """transformers.CLIPTextModel (keys ``text_model.*``): ``model(input_ids)[0]`` = last hidden state after the final
     LayerNorm, [B, 77, 1024] (bf16), as pdm/utils/data_utils.py:180 takes it."""
+    _WEIGHTS = ("model.safetensors", "pytorch_model.bin")
+
+    @staticmethod
+    def _default_config():
+        return SD21_TEXT_CONFIG
 
     def __init__(self, config: Optional[dict] = None, device=None, seed: Optional[int] = 3, **overrides):
         super().__init__()
