@@ -23,6 +23,16 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+try:        # DRAM bytes per launch of the roofline kernels, from the committed `ncu --set full` capture (not measurable in-process)
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        NCU_TRAFFIC = json.load(_f)
+except OSError:
+    NCU_TRAFFIC = {}
+
+
+def ncu_traffic(key):
+    t = NCU_TRAFFIC.get(key)
+    return (t["dram_bytes_read"] + t["dram_bytes_write"]) if t else None
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -220,7 +230,7 @@ def attention_roofline(torch, K, batch, peaks):
     peak = peaks.get("bf16_tflops", 1590.0)
     return {"bound": "tensor", "kernel": "b200::attn_fwd2_kernel (tcgen05 flash-style attention forward)",
             "shape": f"batch {B}, {H} heads, Lq = Lk = {L}, head_dim 64", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
-            "frac": tf / peak, "ms_per_launch": ms, "traffic": None}
+            "frac": tf / peak, "ms_per_launch": ms, "traffic": ncu_traffic("attn_fwd_L4096_h5_b16") if batch == 16 else None}
 
 
 def gemm_class_roofline(torch, _lib, one_eager_step, peaks):
@@ -628,9 +638,11 @@ def main():
         "roofline_hbm": hbm,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": tf / peak_burst,
-                     # not measurable from inside the process: the per-round `ncu --set full` capture of this launch is
-                     # committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum) and cited in DESIGN.md
-                     "traffic": None, "algorithmic_bytes": 2.0 * (B * L * L * 960 + 170 * 9 * 960 + B * L * L * 170),
+                     # not measurable from inside the process: dram__bytes_read.sum + dram__bytes_write.sum of this launch
+                     # from the committed `ncu --set full` capture (profiles/ncu_traffic.json names its source file)
+                     "traffic": ncu_traffic("conv3x3_960_170_b16") if B == 16 else None,
+                     "traffic_source": NCU_TRAFFIC.get("source"),
+                     "algorithmic_bytes": 2.0 * (B * L * L * 960 + 170 * 9 * 960 + B * L * L * 170),
                      "kernel": "b200::gemm_kernel<0,0,true> (tcgen05 cta_group::2 implicit-GEMM conv)",
                      "shape": conv_desc,
                      "ms_per_launch": conv_ms,

@@ -649,7 +649,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const bool o16 = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.ldo % 8 == 0);
             const bool a16 = p.aux && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux % 8 == 0) && (p.geglu_F % 8 == 0);
             auto store32 = [&](bf16* dst, const float* f, int nv, bool vec16) {
-              if (nv == 32 && vec16) {
+              if (vec16) {   // whole 8-column groups as 128-bit stores, the rest element-wise
+                int done = 0;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                   uint32_t pk[4];
@@ -658,8 +659,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 2 * j], f[g4 * 8 + 2 * j + 1]);
                     pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
                   }
-                  *reinterpret_cast<uint4*>(dst + g4 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  if (g4 * 8 + 8 <= nv) {
+                    *reinterpret_cast<uint4*>(dst + g4 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    done = g4 * 8 + 8;
+                  }
                 }
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j >= done && j < nv) dst[j] = __float2bfloat16(f[j]);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -779,11 +786,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const int nv = min(32, n_cols - c0);                  // valid columns in this chunk
             if (p.dbg_mode & 128) continue;
             // ---- residual does not depend on the accumulator: issue its loads first
+            // (partial chunks -- block_n % 32 == 16, pruned widths such as 170 = 5 * 32 + 10 -- keep the vector accesses for
+            // their whole 16- / 8-column groups: element-wise tails cost more than the rest of the tile)
             uint32_t resv[2][8];
-            const bool res_fast = res_row && res_v32 && nv == 32;
+            const bool res_fast = res_row && res_v32 && nv >= 16;
             if (res_fast) {
               ldg256(res_row + c0, resv[0]);
-              ldg256(res_row + c0 + 16, resv[1]);
+              if (nv == 32) ldg256(res_row + c0 + 16, resv[1]);
             }
             // ---- TMEM -> registers (lane == row).  (Issuing the next chunk's load early was measured: no gain.)
             uint32_t v[32];
@@ -821,9 +830,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (res_fast) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const uint32_t w = resv[j >> 3][j & 7];
-                f[2 * j] += __uint_as_float(w << 16);
-                f[2 * j + 1] += __uint_as_float(w & 0xffff0000u);
+                if (j < 8 || nv == 32) {
+                  const uint32_t w = resv[j >> 3][j & 7];
+                  f[2 * j] += __uint_as_float(w << 16);
+                  f[2 * j + 1] += __uint_as_float(w & 0xffff0000u);
+                }
+              }
+              if (nv < 32) {
+#pragma unroll
+                for (int j = 16; j < 32; ++j)
+                  if (j < nv) f[j] += __bfloat162float(res_row[c0 + j]);
               }
             } else if (res_row) {
 #pragma unroll
@@ -851,6 +867,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                   for (int g = 0; g < 4; ++g)
                     *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                 }
+              } else if (out_v16) {   // partial chunk: whole 8-column groups as 128-/256-bit stores, the rest element-wise
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                  pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                int done = 0;
+                if (out_v32 && nv >= 16) {
+                  const uint32_t lo[8] = {pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]};
+                  stg256(o, lo);
+                  done = 16;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  if (8 * g >= done && 8 * g + 8 <= nv) {
+                    *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                    done = 8 * g + 8;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j >= done && j < nv) o[j] = __float2bfloat16(f[j]);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -879,9 +918,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
                 }
               } else {
+                int done = 0;
+                if (out_v16) {
+#pragma unroll
+                  for (int g = 0; g < 8; ++g) {
+                    if (4 * g + 4 <= nv) {
+                      if (p.accumulate)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + g * 4), "f"(f[g * 4]),
+                                     "f"(f[g * 4 + 1]), "f"(f[g * 4 + 2]), "f"(f[g * 4 + 3])
+                                     : "memory");
+                      else
+                        *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                      done = 4 * g + 4;
+                    }
+                  }
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                  if (j < nv) {
+                  if (j >= done && j < nv) {
                     if (p.accumulate)
                       atomicAdd(o + j, f[j]);
                     else

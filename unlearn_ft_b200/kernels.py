@@ -31,8 +31,14 @@ def round8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def round16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
 def alloc2d(rows: int, cols: int, device=None, dtype=BF16, zero: bool = False) -> torch.Tensor:
-    ld = round8(cols)
+    """[rows, cols] matrix whose row pitch is a multiple of 16 elements: every row of a bf16 matrix starts on a 32-byte sector
+    (the GEMM epilogue's 256-bit row accesses need that; TMA needs 16 bytes), also for pruned widths such as 170 / 340 / 680."""
+    ld = round16(cols)
     buf = (torch.zeros if zero else torch.empty)(rows, ld, device=device or "cuda", dtype=dtype)
     return buf[:, :cols] if ld != cols else buf
 
@@ -405,10 +411,10 @@ def cast_f32_to_bf16(x, out=None):
 
 
 def cast2d_f32_to_bf16(x):
-    """fp32 [rows, C] made by alloc2d (pitch round8(C)) -> bf16 matrix with the same pitch."""
+    """fp32 [rows, C] made by alloc2d (pitch round16(C)) -> bf16 matrix with the same pitch."""
     rows, cols = x.shape
     ld = x.stride(0)
-    if ld != round8(cols) or x.stride(1) != 1:
+    if ld != round16(cols) or x.stride(1) != 1:
         raise ValueError("cast2d_f32_to_bf16 expects an alloc2d-style fp32 matrix")
     out = torch.empty(rows, ld, device=x.device, dtype=BF16)
     check(_lib.lib().b200pdm_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), rows * ld - (ld - cols), _stream()), "cast2d")
