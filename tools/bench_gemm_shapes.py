@@ -25,7 +25,7 @@ def time_it(fn, iters=12):
 
 def conv_case(B, H, W, Ci, Co, nbuf=4):
     xs = [K.alloc2d(B * H * W, Ci).normal_() for _ in range(nbuf)]
-    w = torch.randn(Co, 9, Ci, device="cuda", dtype=torch.bfloat16) * 0.02
+    w = (torch.randn(Co, 9, K.round8(Ci), device="cuda", dtype=torch.bfloat16) * 0.02)[:, :, :Ci]
     out = K.alloc2d(B * H * W, Co)
     ms = time_it(lambda i: K.conv_fwd(xs[i % nbuf], w, B, H, W, Co, 3, 1, out=out))
     fl = 2.0 * B * H * W * Co * 9 * Ci
@@ -49,6 +49,13 @@ if which in ("conv", "all"):
     conv_case(16, 32, 32, 1280, 1280)
     conv_case(16, 16, 16, 1280, 1280)
     conv_case(16, 8, 8, 1280, 1280)
+    conv_case(16, 64, 64, 320, 170)
+    conv_case(16, 64, 64, 170, 320)
+    conv_case(16, 32, 32, 640, 340)
+    conv_case(16, 32, 32, 340, 640)
+    conv_case(16, 32, 32, 1920, 640)
+    conv_case(16, 16, 16, 1280, 680)
+    conv_case(16, 16, 16, 2560, 1280)
 if which in ("lin", "all"):
     lin_case(8192, 8192, 8192)
     lin_case(65536, 256, 8192)

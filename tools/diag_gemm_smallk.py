@@ -15,17 +15,25 @@ MODES = [(0, "full"), (8, "no stores"), (128, "no epilogue"), (6, "no loads"), (
          (6 | 128 | 1, "skeleton")]
 
 
-def time_it(fn, iters=20):
-    for _ in range(3):
+def time_it(fn, iters=24):
+    """Average duration of one launch inside a replayed CUDA graph of `iters` launches (eager back-to-back launches of kernels
+    under ~20 us measure the host's launch rate instead)."""
+    for _ in range(2):
         fn(0)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i)
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / (3 * iters)
 
 
 def sweep(name, fn, flops, bytes_):
@@ -64,3 +72,6 @@ if __name__ == "__main__":
     lin_case(4096, 3840, 1280)
     lin_case(4096, 1280, 5120, res=True, bias=True)
     lin_case(1024, 1280, 1280, res=True, bias=True)
+    lin_case(65536, 320, 128, res=True, bias=True)
+    lin_case(16, 1280, 1280, bias=True)
+    lin_case(128, 128, 64)

@@ -196,6 +196,17 @@ struct GemmDev {
   int geglu_F;     // F (0 = off)
   bf16* aux;       // optional [M, 2F] pre-activations (value | gate) saved for the backward pass
   int64_t ld_aux;
+  // Row-shared 3x3 taps ("kh3", stride-1 "same" convolutions whose CTA rows are R whole image rows): K runs over
+  // (channel block, kw, kh), kh innermost.  One TMA box of R + 2 image rows (x shifted by kw - 1, zero-filled outside the
+  // image) is staged per (channel block, kw) and serves the three kh taps: tap kh reads the box from image row kh on
+  // (W * 128 bytes = whole swizzle atoms, so only the descriptor start address moves).  A-operand bytes through
+  // L2 -> shared memory drop to (R + 2) / (3 R) of one box per tap; the B tiles keep their own, finer ring.
+  int kh3;           // 0 = off
+  int a_slots;       // A ring depth (kh3)
+  int a_slot_bytes;  // (R + 2) * W * 128
+  int kh_row_bytes;  // W * 128: one image row of a 64-channel block
+  int rank_stride;   // first 128-row block of CTA `rank` in a super tile: m_super * cluster * m_sub + rank * rank_stride
+  int sub_stride;    // ... and of its sub-tile s: + s * sub_stride   (normal: 1 / cluster; kh3: m_sub / 1 = contiguous rows)
 };
 
 // Where a tile sits: decoded once per tile by each role.
@@ -216,7 +227,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int t, int ti
   c.z1 = z - c.z2 * p.a.Z1;
   const int m_super = fdiv(r, p.fd_tiles_n);
   const int n_tile = r - m_super * tiles_n;
-  c.m_tile = m_super * cluster * p.m_sub + rank;   // sub-tile s of the CTA: + s * cluster
+  c.m_tile = m_super * cluster * p.m_sub + rank * p.rank_stride;   // sub-tile s of the CTA: + s * p.sub_stride
   c.grp = p.n_groups > 1 ? fdiv(n_tile, p.fd_tiles_n_per_group) : 0;
   c.nt = n_tile - c.grp * p.tiles_n_per_group;
   return c;
@@ -417,14 +428,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int stage_b_bytes = (PAIR ? p.block_n / 2 : p.block_n) * 128;
   const int stage_a_bytes = p.m_sub * kStageABytes;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + p.stages * stage_a_bytes;
+  uint8_t* sB = smem + (p.kh3 ? p.a_slots * p.a_slot_bytes : p.stages * stage_a_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + p.stages * stage_b_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tfull_bar = empty_bar + p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* afull_bar = tempty_bar + 2;        // [4]  kh3: A ring
+  uint64_t* aempty_bar = afull_bar + 4;        // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
   // per epilogue warp: 1 KiB slice holding (bias + time-embedding row bias) of the tile's columns, read back as broadcasts
-  uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tempty_bar + 4) + 127) & ~uintptr_t(127));
+  uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(aempty_bar + 6) + 127) & ~uintptr_t(127));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.tiles_n_per_group * p.n_groups;
@@ -448,6 +461,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], (pair ? 8 : 4) * p.epi_groups);   // pair: the leader's MMA waits for both CTAs' epilogue warps
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&afull_bar[i], 1);
+      mbar_init(&aempty_bar[i], mcast);
     }
     fence_barrier_init();
   }
@@ -474,7 +491,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   }
 
   if (warp == 0) {
-    {
+    if (p.kh3) {
+      // ===================== TMA producer, row-shared 3x3 taps (see GemmDev::kh3) =====================
+      int stage = 0, slot = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
+        const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
+        const ACursor ac = make_a_cursor(p.a, tc, tc.m_tile);   // (x0 - 1 = -1, first image row - 1, image)
+        BCursor bc;
+        bc.n0 = tc.nt * p.block_n;
+        bc.kh = bc.kw = 0;
+        const int g0 = (tc.split * p.kb_per_split) / 3;
+        const int g1 = min(p.kblocks, (tc.split + 1) * p.kb_per_split) / 3;
+        int cb = g0 / 3;
+        int kw = g0 - 3 * cb;
+        for (int g = g0; g < g1; ++g) {
+          mbar_wait(&aempty_bar[slot], aphase ^ 1);
+          if (elect_one()) {
+            if (!pair || rank == 0) mbar_expect_tx(&afull_bar[slot], (pair ? 2 : 1) * p.a_slot_bytes);
+            ld4<PAIR>(sA + slot * p.a_slot_bytes, &tma_a, &afull_bar[slot], cb * kBlockK, ac.c1 + kw, ac.c2, ac.c3);
+          }
+          for (int kh = 0; kh < 3; ++kh) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              if (!pair || rank == 0) mbar_expect_tx(&full_bar[stage], (pair ? 2 : 1) * stage_b_bytes);
+              // the weight tap whose window offset is (kh, kw) on the activation side (dgrad walks the window mirrored)
+              const int tap = p.a.flip ? (2 - kh) * 3 + (2 - kw) : kh * 3 + kw;
+              load_b<PAIR>(p.b, &tma_b, sB + stage * stage_b_bytes, &full_bar[stage], bc, tc, p.block_n, 0, cb, tap, mcast, rank, 0);
+            }
+            if (++stage == p.stages) stage = 0, phase ^= 1;
+          }
+          if (++kw == 3) kw = 0, ++cb;
+          if (++slot == p.a_slots) slot = 0, aphase ^= 1;
+        }
+      }
+    } else {
       // ===================== TMA producer =====================
       // On the critical path of every k-block: no divisions, operand cursors hoisted per tile, and the whole warp runs the
       // loop so that every TMA operand is warp-uniform (one elected lane issues).
@@ -485,7 +536,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const TileCoord tc = decode_tile(p, t, tiles_per_split, tiles_n, cluster, rank);
         const ACursor ac0 = make_a_cursor(p.a, tc, tc.m_tile);
-        const ACursor ac1 = make_a_cursor(p.a, tc, tc.m_tile + cluster);   // second sub-tile of a tall tile
+        const ACursor ac1 = make_a_cursor(p.a, tc, tc.m_tile + p.sub_stride);   // second sub-tile of a tall tile
         BCursor bc;
         bc.n0 = p.geglu_F ? tc.nt * (p.block_n / 2) : tc.nt * p.block_n;
         tap_offsets(p.b.taps, tc.grp, 0, &bc.kh, &bc.kw);
@@ -533,6 +584,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       uint32_t unit = 0;   // accumulator units issued so far: unit u lives in TMEM slot u & 1, barrier phase (u >> 1) & 1
+      if (p.kh3) {
+        // row-shared 3x3 taps: one A box per (channel block, kw), three B stages (kh = 0, 1, 2) read it at row offsets
+        int slot = 0;
+        uint32_t aphase = 0;
+        for (int t = first_tile; t < total_tiles; t += tile_step) {
+          const int split = p.splits > 1 ? fdiv(t, p.fd_tiles_per_split) : 0;
+          const int kb0 = split * p.kb_per_split;
+          const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+          for (int kb = kb0; kb < kb1; kb += 3) {
+            mbar_wait(&afull_bar[slot], aphase);
+            for (int kh = 0; kh < 3; ++kh) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + stage * (stage_b_bytes >> 4);
+              for (int sub = 0; sub < p.m_sub; ++sub) {
+                const uint32_t u = unit + sub, acc = u & 1;
+                if (kb == kb0 && kh == 0) {
+                  mbar_wait(&tempty_bar[acc], ((u >> 1) & 1) ^ 1);
+                  tc_fence_after();
+                }
+                const uint32_t tmem_d = tmem_base + acc * kAccStride;
+                const uint32_t a_lo = a_lo0 + (slot * p.a_slot_bytes + kh * p.kh_row_bytes + sub * kStageABytes) / 16;
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t adesc = a_hi | (a_lo + k * a_kstep), bdesc = b_hi | (b_lo + k * b_kstep);
+                    const uint32_t accum = (kb > kb0 || kh > 0 || k > 0) ? 1u : 0u;
+                    if (pair)
+                      umma_bf16_2sm(tmem_d, adesc, bdesc, p.idesc, accum);
+                    else
+                      umma_bf16(tmem_d, adesc, bdesc, p.idesc, accum);
+                  }
+                  if (sub == p.m_sub - 1) {
+                    if (pair) {
+                      umma_commit_2sm_mc(&empty_bar[stage], 3);
+                      if (kh == 2) umma_commit_2sm_mc(&aempty_bar[slot], 3);
+                    } else if (cluster == 1) {
+                      umma_commit(&empty_bar[stage]);
+                      if (kh == 2) umma_commit(&aempty_bar[slot]);
+                    } else {
+                      umma_commit_mc(&empty_bar[stage], cmask);
+                      if (kh == 2) umma_commit_mc(&aempty_bar[slot], cmask);
+                    }
+                  }
+                  if (kb + 3 >= kb1 && kh == 2) {
+                    if (pair)
+                      umma_commit_2sm_mc(&tfull_bar[acc], 3);
+                    else
+                      umma_commit(&tfull_bar[acc]);
+                  }
+                }
+              }
+              if (++stage == p.stages) stage = 0, phase ^= 1;
+            }
+            if (++slot == p.a_slots) slot = 0, aphase ^= 1;
+          }
+          unit += p.m_sub;
+        }
+      } else
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const int split = p.splits > 1 ? fdiv(t, p.fd_tiles_per_split) : 0;
         const int kb0 = split * p.kb_per_split;
@@ -626,7 +736,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
             const int acc = unit & 1;
             const uint32_t acc_phase = (unit >> 1) & 1;
-            const int row = (tc.m_tile + sub * cluster) * kBlockM + q * 32 + lane;
+            const int row = (tc.m_tile + sub * p.sub_stride) * kBlockM + q * 32 + lane;
             const bool row_ok = row < p.M;
             {   // bias of the tile's accumulator columns -> this warp's smem slice (value half, then gate half)
               float b8[8];
@@ -719,7 +829,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int sub = 0; sub < p.m_sub; ++sub, ++unit) {
           const int acc = unit & 1;
           const uint32_t acc_phase = (unit >> 1) & 1;
-          const int m_tile = tc.m_tile + sub * cluster;
+          const int m_tile = tc.m_tile + sub * p.sub_stride;
           const int row = m_tile * kBlockM + q * 32 + lane;      // own row (TMEM lane)
           const bool row_ok = row < p.M;
           const int64_t out_off =
@@ -739,7 +849,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (nt_sub == p.m_sub) nt_t = t + tile_step, nt_sub = 0;
             if (nt_t < total_tiles) {
               const TileCoord nc = (nt_t == t) ? tc : decode_tile(p, nt_t, tiles_per_split, tiles_n, cluster, rank);
-              const int nrow = (nc.m_tile + nt_sub * cluster) * kBlockM + q * 32 + lane;
+              const int nrow = (nc.m_tile + nt_sub * p.sub_stride) * kBlockM + q * 32 + lane;
               if (nrow < p.M) {
                 const int ncol = nc.nt * p.block_n;
                 const int ncols = min(p.block_n, p.n_per_group - ncol);
@@ -1011,6 +1121,20 @@ static bool pixel_box(int pixels, int Ho, int Wo, int* bw, int* bh, int* bn) {
   return true;
 }
 
+// Row-shared 3x3 taps (GemmDev::kh3): image rows R covered by one CTA's 128 * m_sub consecutive output pixels, or 0 when the
+// operand / tiling does not qualify (stride-1 "same" 3x3 window, whole image rows per CTA, no ragged last super tile).
+static int kh3_rows(const b200pdm_operand& a, int64_t M, int m_sub, int cs) {
+  static int env_off = -1;
+  if (env_off < 0) env_off = getenv("B200PDM_NO_KH3") ? 1 : 0;
+  if (env_off || a.mode != B200PDM_OP_CONV_ACT || a.taps != 9 || a.stride > 1 || a.no_pad) return 0;
+  const int W = a.w_out, H = a.h_out, rows = kBlockM * m_sub;
+  if (W < 8 || W > 128 || W % 8 || rows % W) return 0;
+  const int R = rows / W;
+  if (R < 1 || R > H || H % R || R + 2 > 256) return 0;
+  if (M % ((int64_t)rows * cs)) return 0;
+  return R;
+}
+
 static int pair_enabled() {
   static int env_pair = -1;
   if (env_pair < 0) env_pair = getenv("B200PDM_NO_PAIR") ? 0 : 1;
@@ -1028,7 +1152,8 @@ struct Plan {
   double cost = 1e30;
 };
 static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, int kblocks, bool can_split,
-                      bool split_needs_finalize, int fixed_bn, int fixed_splits = 0, int bn_step = 0) {
+                      bool split_needs_finalize, int fixed_bn, int fixed_splits = 0, int bn_step = 0,
+                      const b200pdm_operand* conv_a = nullptr, int64_t M = 0) {
   static int env_msub = -1;
   if (env_msub < 0) {
     const char* e = getenv("B200PDM_MSUB");
@@ -1051,7 +1176,12 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
       if (env_msub > 0 && m_sub != env_msub) continue;
       if (m_sub == 2 && tiles_m < 2 * cs) break;
       const long base_tiles = (long)((tiles_m + cs * m_sub - 1) / (cs * m_sub)) * tiles_n * Z;
-      const double bytes = 16384.0 * m_sub + (pair ? bn / 2 : bn) * 128.0;
+      double a_bytes = 16384.0 * m_sub;
+      if (conv_a) {   // row-shared 3x3 taps: one (R + 2)-row box per three k-blocks
+        const int R = kh3_rows(*conv_a, M, m_sub, cs);
+        if (R > 0) a_bytes = (R + 2) * conv_a->w_out * 128.0 / 3.0;
+      }
+      const double bytes = a_bytes + (pair ? bn / 2 : bn) * 128.0;
       const double kcyc = std::max(2.0 * bn * m_sub, bytes / 40.0) + 40.0;
       for (int s : split_cands) {
         if (fixed_splits > 0) {
@@ -1076,7 +1206,7 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
 }
 
 static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, CUtensorMap* map, OpDev* dev,
-                             int64_t mn_extent, int64_t k_extent, int Z1, int Z2, int cluster = 1) {
+                             int64_t mn_extent, int64_t k_extent, int Z1, int Z2, int cluster = 1, int kh3_R = 0) {
   memset(dev, 0, sizeof(*dev));
   dev->mode = op.mode;
   dev->Z1 = Z1 > 0 ? Z1 : 1;
@@ -1117,6 +1247,7 @@ static int build_operand_map(const b200pdm_operand& op, bool is_a, int block_n, 
       str[0] = 1, str[1] = op.ld, str[2] = (uint64_t)op.w_in * op.ld, str[3] = (uint64_t)op.h_in * op.w_in * op.ld;
       box[0] = 64, box[1] = bw * dev->stride, box[2] = bh * dev->stride, box[3] = bn;
       es[1] = dev->stride, es[2] = dev->stride;
+      if (kh3_R > 0) box[1] = op.w_out, box[2] = kh3_R + 2, box[3] = 1;   // R + 2 whole image rows (GemmDev::kh3)
       if (dev->taps == 1 && dev->stride == 1) {
         // 1x1: the (kw-1, kh-1) shift is zero because load_a/load_b force the centre tap
       }
@@ -1243,13 +1374,15 @@ static int shape_and_plan(const b200pdm_gemm_desc* d, bool have_workspace, Shape
   s->acc_out = d->out_fp32 && d->accumulate;
   const bool slabs_ok = have_workspace && !s->acc_out && s->Z == 1 && s->n_groups == 1 &&
                         (int64_t)d->M * d->N * 4 <= (64ll << 20);
+  const b200pdm_operand* conv_a = (d->a.mode == B200PDM_OP_CONV_ACT && d->a.taps == 9) ? &d->a : nullptr;
   if (d->geglu)   // one tile = bh value + bh gate columns of the same hidden units; never split along K
     s->plan = plan_gemm(s->n_per_group, 1, false, s->tiles_m, s->Z, s->kblocks, false, false, d->block_n, 0, 64);
   else if (d->splits > 1 && (s->acc_out || slab_pass))   // split factor fixed by the caller (accumulating outputs) / the slab pass
-    s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, false, false, d->block_n, d->splits);
+    s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, false, false, d->block_n, d->splits,
+                        0, conv_a, d->M);
   else
     s->plan = plan_gemm(s->n_per_group, s->n_groups, s->b_mn, s->tiles_m, s->Z, s->kblocks, s->acc_out || slabs_ok,
-                        !s->acc_out, d->block_n);
+                        !s->acc_out, d->block_n, 0, 0, conv_a, d->M);
   if (s->plan.bn <= 0) {
     set_err("gemm: no valid tile plan (bad block_n?)");
     return B200PDM_ERR_ARG;
@@ -1258,7 +1391,8 @@ static int shape_and_plan(const b200pdm_gemm_desc* d, bool have_workspace, Shape
       // slab count the finalize pass adds up must equal the number of slabs that get written
     int sp = s->plan.splits > s->kblocks ? s->kblocks : s->plan.splits;
     if (sp < 1) sp = 1;
-    const int per = cdiv(s->kblocks, sp);
+    int per = cdiv(s->kblocks, sp);
+    if (conv_a) per = (per + 2) / 3 * 3;   // 3x3 taps: a split owns whole (channel block, kw) groups of three k-blocks
     s->plan.splits = cdiv(s->kblocks, per);
   }
   s->ldws = s->slab = 0;
@@ -1326,6 +1460,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
   int splits = plan.splits;
   if (splits > kblocks) splits = kblocks;
   p.kb_per_split = cdiv(kblocks, splits);
+  if (d->a.mode == B200PDM_OP_CONV_ACT && d->a.taps == 9) p.kb_per_split = (p.kb_per_split + 2) / 3 * 3;   // as in shape_and_plan
   splits = cdiv(kblocks, p.kb_per_split);
   p.splits = splits;
 
@@ -1349,8 +1484,11 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
   p.m_sub = plan.m_sub;
   p.tiles_m_super = cdiv(p.tiles_m, cluster * p.m_sub);
 
+  const int kh3_R = kh3_rows(d->a, d->M, p.m_sub, cluster);
+  p.rank_stride = kh3_R ? p.m_sub : 1;
+  p.sub_stride = kh3_R ? 1 : cluster;
   CUtensorMap map_a, map_b;
-  int rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2);
+  int rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2, 1, kh3_R);
   if (rc) return rc;
   // (GEGLU: the weight has 2F rows and is always fetched in half-tile boxes, one for the value and one for the gate rows)
   rc = build_operand_map(d->b, false, block_n, &map_b, &p.b, d->geglu ? 2 * d->N : d->N, d->K, Z1, Z2, d->geglu ? 2 : cluster);
@@ -1381,9 +1519,24 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
     p.epi_groups = kMaxEpiGroups;   // measured: never slower than one group, up to 1.4x faster on small-K shapes
     if (env_eg >= 1 && env_eg <= kMaxEpiGroups) p.epi_groups = env_eg;
   }
-  const int stage_bytes = p.m_sub * kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
-  const int fixed_bytes = 1024 + (2 * 8 + 6) * 8 + 64 + 128 + 4 * p.epi_groups * 1024;
-  int stages = (227 * 1024 - fixed_bytes) / stage_bytes;
+  int stage_bytes = p.m_sub * kStageABytes + (p.pair ? block_n / 2 : block_n) * 128;
+  const int fixed_bytes = 1024 + (2 * 8 + 6 + 8) * 8 + 64 + 128 + 4 * p.epi_groups * 1024;
+  int a_region = 0;
+  if (kh3_R > 0) {   // A ring of 3 (else 2) boxes, the rest of shared memory for B stages (at least 3)
+    const int a_slot = (kh3_R + 2) * d->a.w_out * 128, b_stage = (p.pair ? block_n / 2 : block_n) * 128;
+    const int room = 227 * 1024 - fixed_bytes;
+    int slots = 3;
+    if ((room - slots * a_slot) / b_stage < 4) slots = 2;
+    if ((room - slots * a_slot) / b_stage >= 3) {
+      p.kh3 = 1, p.a_slots = slots, p.a_slot_bytes = a_slot, p.kh_row_bytes = d->a.w_out * 128;
+      a_region = slots * a_slot, stage_bytes = b_stage;
+    } else {   // does not fit: fall back to one box per tap (needs the standard tensor map and row mapping)
+      p.rank_stride = 1, p.sub_stride = cluster;
+      rc = build_operand_map(d->a, true, block_n, &map_a, &p.a, d->M, d->K, Z1, Z2);
+      if (rc) return rc;
+    }
+  }
+  int stages = (227 * 1024 - fixed_bytes - a_region) / stage_bytes;
   if (stages > 8) stages = 8;
   static int env_stages = -1;
   if (env_stages < 0) {
@@ -1423,7 +1576,7 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
   }
   p.dbg = dbg_on ? dbg_buf : nullptr;
 #endif
-  const size_t smem = (size_t)fixed_bytes + (size_t)stages * stage_bytes;
+  const size_t smem = (size_t)fixed_bytes + (size_t)a_region + (size_t)stages * stage_bytes;
   const int threads = 64 + 128 * p.epi_groups;
 #ifdef B200PDM_DIAG
   {
@@ -1490,9 +1643,9 @@ static int launch_gemm(const b200pdm_gemm_desc* d, void* workspace, size_t ws_by
       cudaEventElapsedTime(&ms, t0, t1);
       char key[256];
       const double kk = (double)kblocks * 64;
-      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d msub=%d split=%d tiles=%ld grid=%d stages=%d cl=%d",
+      snprintf(key, sizeof(key), "a%d b%d M=%lld N=%d(x%d) K=%.0f Z=%d bn=%d msub=%d split=%d tiles=%ld grid=%d stages=%d cl=%d kh3=%d",
                d->a.mode, d->b.mode, (long long)d->M, p.n_per_group, p.n_groups, kk, p.Z, block_n, p.m_sub, p.splits,
-               total_tiles, grid, stages, cluster);
+               total_tiles, grid, stages, cluster, p.kh3 ? p.a_slots : 0);
 #ifdef B200PDM_DIAG
       if (p.dbg) {
         long long h[16];
