@@ -57,7 +57,41 @@ def lin_case(M, N, Kd, res=False, bias=False, nbuf=6):
           2.0 * M * N * Kd, 2.0 * (M * Kd + N * Kd + M * N * (2 if res else 1)))
 
 
+def wgrad_lin_case(M, N, Kd, nbuf=4):
+    """dw[N, Kd] += dy[M, N]^T x[M, Kd]  (GEMM M=N, N=Kd, K=M pixels)."""
+    dys = [K.alloc2d(M, N).normal_() for _ in range(nbuf)]
+    xs = [K.alloc2d(M, Kd).normal_() for _ in range(nbuf)]
+    dw = K.alloc2d(N, Kd, dtype=torch.float32, zero=True)
+    sweep(f"wgrad linear pixels={M} dW={N}x{Kd}", lambda i: K.linear_wgrad(dys[i % nbuf], xs[i % nbuf], dw),
+          2.0 * M * N * Kd, 2.0 * (M * Kd + M * N) + 4.0 * N * Kd)
+
+
+def wgrad_conv_case(B, H, W, Ci, Co, nbuf=4):
+    dys = [K.alloc2d(B * H * W, Co).normal_() for _ in range(nbuf)]
+    xs = [K.alloc2d(B * H * W, Ci).normal_() for _ in range(nbuf)]
+    dw = torch.zeros(Co, 9, K.round8(Ci), device="cuda")[:, :, :Ci]
+    sweep(f"wgrad conv {Ci}->{Co} @{H}x{W} B{B}", lambda i: K.conv_wgrad(dys[i % nbuf], xs[i % nbuf], dw, B, H, W, 3, 1),
+          2.0 * B * H * W * Co * 9 * Ci, 2.0 * B * H * W * (Ci + Co) + 4.0 * Co * 9 * Ci)
+
+
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "wgrad":
+        MODES[:] = [(0, "full"), (1, "quarter MMA"), (2, "no A loads"), (4, "no B loads"), (6, "no loads"), (128, "no epilogue"),
+                    (6 | 128, "no loads, no epilogue")]
+        wgrad_lin_case(65536, 320, 320)
+        wgrad_lin_case(65536, 320, 1360)
+        wgrad_lin_case(16384, 640, 640)
+        wgrad_lin_case(4096, 1280, 1280)
+        wgrad_lin_case(4096, 1280, 5440)
+        wgrad_conv_case(16, 64, 64, 170, 320)
+        wgrad_conv_case(16, 64, 64, 320, 170)
+        wgrad_conv_case(16, 64, 64, 640, 640)
+        wgrad_conv_case(16, 32, 32, 340, 640)
+        wgrad_conv_case(16, 32, 32, 1280, 1280)
+        wgrad_conv_case(16, 16, 16, 680, 1280)
+        wgrad_conv_case(16, 8, 8, 680, 1280)
+        sys.exit(0)
     lin_case(65536, 320, 320)
     lin_case(65536, 320, 320, res=True, bias=True)
     lin_case(65536, 960, 320)
