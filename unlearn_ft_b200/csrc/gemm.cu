@@ -883,6 +883,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             __syncwarp();
           }
 
+          // ---- the residual does not depend on the accumulator: the loads of a chunk are issued one chunk ahead (those of the
+          // first chunk before the wait for the accumulator), so their L2 latency hides behind the previous chunk's TMEM read,
+          // arithmetic and stores.  (Partial chunks -- block_n % 32 == 16, pruned widths such as 170 = 5 * 32 + 10 -- keep the
+          // vector accesses for their whole 16- / 8-column groups: element-wise tails cost more than the rest of the tile.)
+          uint32_t resn[2][8];
+          auto res_issue = [&](int c0) {
+            const int nv = min(32, n_cols - c0);
+            if (res_row && res_v32 && nv >= 16) {
+              ldg256(res_row + c0, resn[0]);
+              if (nv == 32) ldg256(res_row + c0 + 16, resn[1]);
+            }
+          };
+          if (wg * 32 < n_cols && !(p.dbg_mode & 128)) res_issue(wg * 32);
+
           if (dbg_thread) {
             DBG_WAIT(3, mbar_wait(&tfull_bar[acc], acc_phase));
           } else {
@@ -895,15 +909,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int c0 = wg * 32; c0 < n_cols; c0 += 32 * p.epi_groups) {
             const int nv = min(32, n_cols - c0);                  // valid columns in this chunk
             if (p.dbg_mode & 128) continue;
-            // ---- residual does not depend on the accumulator: issue its loads first
-            // (partial chunks -- block_n % 32 == 16, pruned widths such as 170 = 5 * 32 + 10 -- keep the vector accesses for
-            // their whole 16- / 8-column groups: element-wise tails cost more than the rest of the tile)
             uint32_t resv[2][8];
             const bool res_fast = res_row && res_v32 && nv >= 16;
-            if (res_fast) {
-              ldg256(res_row + c0, resv[0]);
-              if (nv == 32) ldg256(res_row + c0 + 16, resv[1]);
-            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) resv[0][j] = resn[0][j], resv[1][j] = resn[1][j];
+            if (c0 + 32 * p.epi_groups < n_cols) res_issue(c0 + 32 * p.epi_groups);
             // ---- TMEM -> registers (lane == row).  (Issuing the next chunk's load early was measured: no gain.)
             uint32_t v[32];
             if (p.block_n - c0 >= 32) {
@@ -1159,6 +1169,12 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
     const char* e = getenv("B200PDM_MSUB");
     env_msub = e ? atoi(e) : 0;
   }
+#ifdef B200PDM_DIAG   // plan sweeps (tools/sweep_gemm_plans.py): B200PDM_PLAN="bn,m_sub,pair,splits", 0 / -1 = planner's choice
+  int f_bn = 0, f_msub = 0, f_pair = -1, f_splits = 0;
+  if (const char* e = getenv("B200PDM_PLAN")) sscanf(e, "%d,%d,%d,%d", &f_bn, &f_msub, &f_pair, &f_splits);
+  if (f_bn > 0 && fixed_bn <= 0) fixed_bn = f_bn;
+  if (f_splits > 0 && fixed_splits <= 0 && (can_split || f_splits == 1)) fixed_splits = f_splits;
+#endif
   const int g = bn_step > 0 ? bn_step : (b_mn ? 64 : 16);   // (fused GEGLU: halves of 32-column chunks -> steps of 64)
   const int n_pad = static_cast<int>((n + g - 1) / g * g);
   static const int split_cands[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64};
@@ -1168,12 +1184,19 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
     if (fixed_bn <= 0 && bn > n_pad) break;
     if (fixed_bn <= 0 && bn < 64 && bn != n_pad) continue;   // tiny tiles only when N itself is tiny
     const int tiles_n = static_cast<int>((n + bn - 1) / bn) * n_groups;
-    const int pair = (pair_enabled() && tiles_m >= 2 && (b_mn ? ((bn / 64) % 2 == 0) : true)) ? 1 : 0;
+    int pair = (pair_enabled() && tiles_m >= 2 && (b_mn ? ((bn / 64) % 2 == 0) : true)) ? 1 : 0;
+#ifdef B200PDM_DIAG
+    if (f_pair == 0) pair = 0;
+    if (f_pair == 1 && !pair) continue;
+#endif
     const int cs = pair ? 2 : 1;
     const int slots = 148 / cs;
     const double epi_unit = 400.0 * ((bn + 31) / 32) / 2.0;   // two epilogue warpgroups
     for (int m_sub = 1; m_sub <= 2; ++m_sub) {
       if (env_msub > 0 && m_sub != env_msub) continue;
+#ifdef B200PDM_DIAG
+      if (f_msub > 0 && m_sub != f_msub) continue;
+#endif
       if (m_sub == 2 && tiles_m < 2 * cs) break;
       const long base_tiles = (long)((tiles_m + cs * m_sub - 1) / (cs * m_sub)) * tiles_n * Z;
       double a_bytes = 16384.0 * m_sub;
