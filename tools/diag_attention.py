@@ -7,3 +7,10 @@ q = torch.randn(B * L, H * 64, device="cuda").bfloat16(); k = torch.randn_like(q
 for _ in range(2):
     K.attention_fwd(q, k, v, B, H, L, L, 0.125)
 torch.cuda.synchronize()
+# backward phase timers of CTA 0 (diag build, B200PDM_ATTN_DBG=1): printed by the library on stderr
+do = torch.randn_like(q)
+out, lse = K.attention_fwd(q, k, v, B, H, L, L, 0.125, want_lse=True)
+dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+for _ in range(2):
+    K.attention_bwd(q, k, v, out, do, lse, dq, dk, dv, B, H, L, L, 0.125)
+torch.cuda.synchronize()

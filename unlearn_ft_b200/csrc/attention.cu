@@ -548,7 +548,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_full = bars + 7;
   uint64_t* dq_empty = bars + 8;
   uint64_t* acc_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* sdp_read = bars + 10;  // the softmax warps hold S_i and dP_i in registers: the TMEM columns may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -570,6 +571,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 8);
     mbar_init(acc_full, 1);
+    mbar_init(sdp_read, 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -604,31 +606,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(kv_full, 0);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-      for (int i = 0; i < p.nq; ++i) {
-        const int s = i & 1;
-        mbar_wait(&qdo_full[s], (i >> 1) & 1);
+      // S_j = Q_j K^T and dP_j = dO_j V^T of query tile j.  Tile j + 1's pair is issued as soon as the softmax warps have
+      // pulled S_j / dP_j out of tensor memory (sdp_read), i.e. it runs on the tensor core WHILE they exponentiate tile j;
+      // round 1 issued it after dV_j / dK_j, which left the tensor core idle for the whole softmax phase.
+      auto issue_s_dp = [&](int j) {
+        const int sj = j & 1;
+        mbar_wait(&qdo_full[sj], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + s * kTileBytes), do_addr = smem_u32(sdO + s * kTileBytes);
+        const uint32_t qa = smem_u32(sQ + sj * kTileBytes), da = smem_u32(sdO + sj * kTileBytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S = Q K^T
-          umma_bf16(t_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+          umma_bf16(t_s, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
                     id_kk128, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dP = dO V^T
-          umma_bf16(t_dp, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
+          umma_bf16(t_dp, make_smem_desc_sw128(da + k * 32, 16, 1024),
                     make_smem_desc_sw128(v_addr + k * 32, 16, 1024), id_kk128, k > 0);
         umma_commit(s_full);
+      };
+      issue_s_dp(0);
+      for (int i = 0; i < p.nq; ++i) {
+        const int s = i & 1;
+        const uint32_t q_addr = smem_u32(sQ + s * kTileBytes), do_addr = smem_u32(sdO + s * kTileBytes);
+        if (i + 1 < p.nq) {
+          mbar_wait(sdp_read, i & 1);
+          tc_fence_after();
+          issue_s_dp(i + 1);
+        }
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
-        if (i > 0) {
-          mbar_wait(dq_empty, (i - 1) & 1);
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ_i = dS K  (A K-major over the two sub-tiles, B = K tile read MN-major)
-          umma_bf16(t_dq, make_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), id_km64, k > 0);
-        umma_commit(dq_full);   // first, so that the softmax threads drain dQ while dV / dK (and the next S, dP) run
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dV += P^T dO   (A: M' = keys over the two sub-tiles (LBO), K' = query rows)
           umma_bf16(t_dv, make_smem_desc_sw128(p_addr + k * 2048, kTileBytes, 1024),
@@ -637,7 +643,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int k = 0; k < 8; ++k)   // dK += dS^T Q
           umma_bf16(t_dk, make_smem_desc_sw128(ds_addr + k * 2048, kTileBytes, 1024),
                     make_smem_desc_sw128(q_addr + k * 2048, 8192, 1024), id_mm64, (i > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&qdo_empty[s]);
+        umma_commit(&qdo_empty[s]);   // Q_i / dO_i may be refilled
+        if (i > 0) {   // dQ_{i-1} is drained one tile late (after the softmax of tile i), so nobody ever waits for a dQ MMA
+          mbar_wait(dq_empty, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_i = dS K  (A K-major over the two sub-tiles, B = K tile read MN-major)
+          umma_bf16(t_dq, make_smem_desc_sw128(ds_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(k_addr + k * 2048, 8192, 1024), id_km64, k > 0);
+        umma_commit(dq_full);   // ... and, MMAs completing in order, P / dS of tile i may be overwritten
       }
       umma_commit(acc_full);
     }
@@ -650,6 +665,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int sw = r & 7;
     const int valid_k = min(kKV, p.Lk - k0);
     const int64_t bh = (int64_t)b * p.H + h;
+    // dQ tile j: TMEM -> fp32 smem tile -> ONE bulk tensor reduce-add per 32-column half (instead of 2048 vector atomics).
+    // The caller has waited for dq_full of tile j.
+    auto drain_dq = [&](int j) {
+      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile left smem
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        uint32_t v0[32];
+        tmem_ld_32x32(t_dq + lane_base + half * 32, v0);
+        tmem_ld_wait();
+        const uint32_t row0 = smem_u32(sDQ) + half * kTileBytes + r * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) sts128(row0 + ((g ^ sw) << 4), v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);   // the TMEM accumulator may be overwritten by the next dQ
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tm_dq)),
+                       "r"(smem_u32(sDQ + c * kTileBytes)), "r"(h * kD + c * 32), "r"(j * kQ), "r"(b)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
     for (int i = 0; i < p.nq; ++i) {
       const int q = i * kQ + r;
       const bool q_ok = q < p.Lq;
@@ -665,14 +708,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint32_t sv[2][32], dv_[2][32];
       tmem_ld_32x32(t_s + lane_base + half * 64, sv[0]);
       tmem_ld_32x32(t_dp + lane_base + half * 64, dv_[0]);
+      tmem_ld_32x32(t_s + lane_base + half * 64 + 32, sv[1]);
+      tmem_ld_32x32(t_dp + lane_base + half * 64 + 32, dv_[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_read);   // S / dP live in registers now: the MMA warp may issue the next tile's pair
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = half * 2 + cc;
-        tmem_ld_wait();
-        if (cc == 0) {   // the second chunk's loads are in flight while the first is processed
-          tmem_ld_32x32(t_s + lane_base + (c + 1) * 32, sv[1]);
-          tmem_ld_32x32(t_dp + lane_base + (c + 1) * 32, dv_[1]);
-        }
         const uint32_t(&s_)[32] = sv[cc];
         const uint32_t(&d_)[32] = dv_[cc];
         float pf[32], dsf[32];
@@ -695,6 +739,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             dsf[j] = pe * (__uint_as_float(d_[j]) - dlt) * p.scale;
           }
         }
+        if (cc == 0 && i > 0) {   // dQ_{i-1} (hence dV_{i-1}, dK_{i-1}) has read P / dS of the previous tile
+          mbar_wait(dq_full, (i - 1) & 1);
+          tc_fence_after();
+        }
         st_tile_row32(p_row, c, sw, pf);
         st_tile_row32(ds_row, c, sw, dsf);
       }
@@ -703,39 +751,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
       const long long tp2 = prof ? clock64() : 0;
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      const long long tp3 = prof ? clock64() : 0;
-      // dQ tile: TMEM -> fp32 smem tile -> ONE bulk tensor reduce-add per 32-column half (instead of 2048 vector atomics)
-      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile left smem
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      {
-        uint32_t v0[32];
-        tmem_ld_32x32(t_dq + lane_base + half * 32, v0);
-        tmem_ld_wait();
-        const uint32_t row0 = smem_u32(sDQ) + half * kTileBytes + r * 128;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) sts128(row0 + ((g ^ sw) << 4), v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3]);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);   // the TMEM accumulator may be overwritten by the next dQ
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 64) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tm_dq)),
-                       "r"(smem_u32(sDQ + c * kTileBytes)), "r"(h * kD + c * 32), "r"(i * kQ), "r"(b)
-                       : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
+      if (i > 0) drain_dq(i - 1);   // one tile late: its MMA finished during this tile's softmax, nothing to wait for
       if (prof) {
         const long long tp4 = clock64();
-        p.dbg[0] += tp1 - tp0, p.dbg[1] += tp2 - tp1, p.dbg[2] += tp3 - tp2, p.dbg[3] += tp4 - tp3;
+        p.dbg[0] += tp1 - tp0, p.dbg[1] += tp2 - tp1, p.dbg[3] += tp4 - tp2;
       }
     }
+    mbar_wait(dq_full, (p.nq - 1) & 1);
+    tc_fence_after();
+    drain_dq(p.nq - 1);
     if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reduces have been performed
     // accumulated dV / dK for key row k0 + r
     mbar_wait(acc_full, 0);
