@@ -81,7 +81,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint64_t* s_full = kv_empty + kKVStages;      // [2]
   uint64_t* p_full = s_full + 2;                // [2]
   uint64_t* pv_done = p_full + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_read = pv_done + 2;               // [2] the softmax warps hold S_t(j) in registers: S_t(j + 1) may overwrite it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_read + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -105,6 +106,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 8);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_read[i], 8);
     }
     fence_barrier_init();
   }
@@ -163,6 +165,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (j + 1 < p.nkv) {
         mbar_wait(&kv_full[nstage], nphase);
         tc_fence_after();
+        // S_t(j + 1) goes out as soon as the softmax warps have pulled S_t(j) into registers -- it runs on the tensor core
+        // while they exponentiate block j.  (Issued after PV_t(j), as before the scores were read in a single pass, it left
+        // every softmax warp waiting ~1500 cycles per key block for its next S.)
+        for (int t = 0; t < n_qt; ++t) {
+          mbar_wait(&s_read[t], j & 1);
+          tc_fence_after();
+          if (elect_one()) issue_s(t, nstage);
+        }
       }
       for (int t = 0; t < n_qt; ++t) {
         const bool mprof = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
@@ -177,7 +187,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             umma_bf16_ts(tmem + 256 + t * 64, tmem + kPCol + t * 64 + k * 8, dv | (bv + k * 128), idesc_o,
                          (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(&pv_done[t]);
-          if (j + 1 < p.nkv) issue_s(t, nstage);
         }
       }
       if (elect_one()) umma_commit(&kv_empty[stage]);   // both tiles' PV(j) (and S(j), long before) have read this stage
@@ -281,9 +290,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const long long tp1 = prof ? clock64() : 0;
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(tmem_s, v0);
+      tmem_ld_32x32(tmem_s + 32, v1);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_read[t]);           // the 64 scores live in registers from here on
+      // PV_t(j - 1) must have consumed the previous P_t (and updated O_t) before this block writes P_t: its MMA is issued AFTER
+      // S_t(j) now, so this is a real -- short -- wait (a completed phase returns at once, also for j = 0)
+      mbar_wait(&pv_done[t], (j + 1) & 1);
+      tc_fence_after();
       const long long tp2 = prof ? clock64() : 0;
-      tmem_ld_32x32(tmem_s + 32, v1);                   // in flight while the first chunk is processed
       float mx = -INFINITY, lsum = 0.f;
       bool redo = false;
       if (j == 0) {
@@ -297,7 +313,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (valid <= 0) m = 0.f;                        // (causal: nothing to attend in this block -- all its p are 0)
         redo = true;
       } else {
-        mbar_wait(&pv_done[t], (j - 1) & 1);            // PV(j-1) has consumed P_t (it preceded S_t(j) on the tensor pipe)
         token_wait();
         exp_chunk(v0, 0, vh, m, lsum, mx);
         tmem_ld_wait();
