@@ -25,11 +25,13 @@ int make_map_f32_3d(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
                     uint32_t box_rows);
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
-// Share of the exponentials moved from MUFU.EX2 to the FMA pipe (exp2_fma): elements with (i & mask) == mask; 3 -> 25 %,
-// 1 -> 50 %, 64 -> none.  Measured on B200 (L = 4096): 0 % 689 us fwd / 1757 us bwd, 25 % 691 / 1765, 50 % 719 / 1815 -- the
-// softmax warps are issue-bound, not MUFU-bound (the polynomial costs 9 issue slots per element), so it stays off.
+// Share of the forward exponentials moved from MUFU.EX2 to the FMA pipe (exp2_fma): elements with (i & mask) == mask; 7 -> 12.5 %,
+// 3 -> 25 %, 1 -> 50 %, 64 -> none.  While the softmax warps still waited ~1500 cycles per key block for their next S the share
+// made no difference (round-2 experiment F: 25 % / 50 % slower); with S issued early (s_read barrier) the exponential phase of
+// the two in-phase query tiles IS the MUFU rate (2100 of 2048 cycles per key block), and a small share pays: L = 4096, 5 heads,
+// batch 16, same box: none 525.8 us, 25 % 512.6 us, 12.5 % 508.4 us.  (The polynomial costs 9 issue slots per element.)
 #ifndef B200PDM_EXP_FMA_MASK
-#define B200PDM_EXP_FMA_MASK 64
+#define B200PDM_EXP_FMA_MASK 7
 #endif
 constexpr int kExpFmaMask = B200PDM_EXP_FMA_MASK;
 constexpr int kTileBytes = 128 * 128;  // [128 rows][64 bf16] swizzle-128B tile
