@@ -759,18 +759,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const bool o16 = ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && (p.ldo % 8 == 0);
             const bool a16 = p.aux && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux % 8 == 0) && (p.geglu_F % 8 == 0);
             auto store32 = [&](bf16* dst, const float* f, int nv, bool vec16) {
-              if (vec16) {   // whole 8-column groups as 128-bit stores, the rest element-wise
+              if (vec16) {   // whole 16- / 8-column groups as 256- / 128-bit stores (full 32-byte sectors where the row piece
+                             // is sector-aligned: 128-bit row stores reach less than half the store rate), the rest element-wise
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                  pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                const bool v32 = (reinterpret_cast<uintptr_t>(dst) & 31) == 0;
                 int done = 0;
+                if (v32 && nv >= 16) {
+                  const uint32_t lo[8] = {pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]};
+                  stg256(dst, lo);
+                  done = 16;
+                  if (nv == 32) {
+                    const uint32_t hi[8] = {pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]};
+                    stg256(dst + 16, hi);
+                    done = 32;
+                  }
+                }
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
-                  uint32_t pk[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[g4 * 8 + 2 * j], f[g4 * 8 + 2 * j + 1]);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&h2);
-                  }
-                  if (g4 * 8 + 8 <= nv) {
-                    *reinterpret_cast<uint4*>(dst + g4 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  if (g4 * 8 >= done && g4 * 8 + 8 <= nv) {
+                    *reinterpret_cast<uint4*>(dst + g4 * 8) = make_uint4(pk[4 * g4], pk[4 * g4 + 1], pk[4 * g4 + 2], pk[4 * g4 + 3]);
                     done = g4 * 8 + 8;
                   }
                 }
