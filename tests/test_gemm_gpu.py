@@ -96,6 +96,14 @@ CONV_CASES = [
     (2, 32, 32, 320, 640, 1, 1),
     (2, 64, 64, 320, 320, 3, 2),
     (2, 16, 16, 1280, 1280, 3, 2),
+    # row-shared 3x3 taps (GemmDev::kh3) and its fall-backs: one image per CTA pair, ragged super tiles (M not a multiple of
+    # the pair's rows -> one box per tap), a single 16x16 image, many k-groups with split-K at 16x16, wide images
+    (1, 64, 64, 64, 64, 3, 1),
+    (5, 16, 16, 320, 320, 3, 1),
+    (1, 16, 16, 128, 256, 3, 1),
+    (4, 16, 16, 2560, 1280, 3, 1),
+    (2, 32, 32, 1280, 128, 3, 1),
+    (1, 32, 128, 64, 96, 3, 1),
 ]
 
 
