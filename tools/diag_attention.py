@@ -1,5 +1,9 @@
+"""Phase timers of the attention kernels (diag build: `make -C unlearn_ft_b200/csrc diag`, then
+B200PDM_LIB=libb200pdm_diag.so B200PDM_ATTN_DBG=1 python tools/diag_attention.py): the library prints, for CTA 0, the cycles its softmax
+warps and its MMA warp spent in each phase (forward: wait for S, TMEM read, exponentials, P store; backward: wait for S/dP, softmax,
+dQ drain), summed over the key / query blocks, at L = 4096, 5 heads, batch 16.  Durations only."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unlearn_ft_b200 import kernels as K
 B, H, L = 16, 5, 4096

@@ -1,4 +1,4 @@
-"""Decomposition of the small-K (epilogue-bound) GEMM shapes with the kernel's diagnostic modes:
+"""(diag build: make -C unlearn_ft_b200/csrc diag; run with B200PDM_LIB=libb200pdm_diag.so)  Decomposition of the small-K (epilogue-bound) GEMM shapes with the kernel's diagnostic modes:
 1 = quarter MMA, 2|4 = no operand loads, 8 = epilogue math but no stores, 128 = epilogue skips its chunks entirely."""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

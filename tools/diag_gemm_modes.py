@@ -1,4 +1,4 @@
-"""Diagnostics: time GEMM/conv shapes with operand streams / MMA switched off (B200PDM_GEMM_DBGMODE) to see which
+"""(diag build: make -C unlearn_ft_b200/csrc diag; run with B200PDM_LIB=libb200pdm_diag.so)  Diagnostics: time GEMM/conv shapes with operand streams / MMA switched off (B200PDM_GEMM_DBGMODE) to see which
 pipeline bounds the kernel.  Results of modes != 0 are garbage by construction; only their durations matter."""
 import os
 import statistics

@@ -1,5 +1,5 @@
 """Diagnostics for the small-K projection GEMMs (K = 320 ... 1280, the epilogue-side of the kernel): time each shape with parts
-of the kernel switched off (diag build: B200PDM_LIB=unlearn_ft_b200/libb200pdm_diag.so, B200PDM_GEMM_DBGMODE bits: 1 quarter of
+of the kernel switched off (diag build: B200PDM_LIB=libb200pdm_diag.so, B200PDM_GEMM_DBGMODE bits: 1 quarter of
 the MMAs, 2 no A loads, 4 no B loads, 8 no epilogue stores, 128 no epilogue work).  Durations only; results of modes != 0 are
 garbage by construction."""
 import os
