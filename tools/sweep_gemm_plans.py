@@ -46,6 +46,11 @@ def sweep(name, fn, bns, flops):
     os.environ.pop("B200PDM_PLAN", None)
     K._WS_BYTES.clear()
     res.sort()
+    if os.environ.get("SWEEP_TSV"):
+        with open(os.environ["SWEEP_TSV"], "a") as f:
+            f.write(f"# {name}\tplanner\t{base:.2f}\n")
+            for t, bn, ms, pair, sp in res:
+                f.write(f"{name}\t{bn}\t{ms}\t{pair}\t{sp}\t{t:.2f}\n")
     top = "  ".join(f"{t:.1f}us(bn={bn} msub={ms} pair={pair} split={sp})" for t, bn, ms, pair, sp in res[:4])
     print(f"{name}: planner {base:.1f} us ({flops/base/1e6:.0f} TF/s) | best {top}", flush=True)
 
@@ -101,6 +106,16 @@ if which == "wgrad":
     wgrad_conv(16, 16, 16, 680, 1280)
     wgrad_conv(16, 16, 16, 1280, 680)
     wgrad_conv(16, 8, 8, 680, 1280)
+    wgrad_conv(16, 64, 64, 320, 320)
+    wgrad_conv(16, 32, 32, 640, 640)
+    wgrad_conv(16, 32, 32, 1280, 640)
+    wgrad_conv(16, 16, 16, 1280, 1280)
+    wgrad_conv(16, 16, 16, 2560, 1280)
+    wgrad_conv(16, 8, 8, 1280, 1280)
+    wgrad_lin(65536, 320, 128)
+    wgrad_lin(16384, 640, 320)
+    wgrad_lin(4096, 1280, 704)
+    wgrad_lin(1232, 1280, 1024)
 elif which == "lin":
     lin(65536, 320, 320)
     lin(65536, 320, 320, res=True)

@@ -1233,6 +1233,10 @@ static Plan plan_gemm(int64_t n, int n_groups, bool b_mn, int tiles_m, int Z, in
         if (s > 1) tile_cyc += epi_unit * m_sub;   // atomics epilogue is slower and less overlapped
         double cost = waves * tile_cyc + (m_sub == 1 ? epi_unit : 0.0);
         if (s > 1 && split_needs_finalize) cost += 14000.0;
+        // accumulating fp32 outputs (weight gradients): every tile of every split adds its block to the output with
+        // red.global.add -- a pass over the output per split, shared by all SMs.  Fitted on the brute-force plan sweep of the
+        // step's wgrad shapes (tools/sweep_gemm_plans.py, profiles/r2_gemm_plan_sweep.txt): regret 4.2 % -> 2.2 %.
+        if (can_split && !split_needs_finalize) cost += 0.12 * (double)tiles * bn * m_sub * 128.0 / 148.0;
         if (cost < best.cost) best.bn = bn, best.splits = s, best.pair = pair, best.m_sub = m_sub, best.cost = cost;
       }
     }
