@@ -541,7 +541,7 @@ __device__ __forceinline__ void st_tile_row32(uint32_t row_base, int c, int sw, 
   }
 }
 
-constexpr int kBwdThreads = 320;   // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter, 64 key columns each)
+constexpr int kBwdThreads = 448;   // TMA warp, MMA warp, 8 softmax warps (two per TMEM lane quarter, 64 key columns each), 4 dQ-drain warps
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -586,7 +586,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(s_full, 1);
     mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 8);
+    mbar_init(dq_empty, 4);
     mbar_init(acc_full, 1);
     mbar_init(sdp_read, 8);
     fence_barrier_init();
@@ -673,25 +673,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       umma_commit(acc_full);
     }
-  } else {
+  } else if (warp >= 10) {
+    // ===================== dQ drain warps =====================
+    // dQ tile j: TMEM -> fp32 smem tile -> ONE bulk tensor reduce-add per 32-column half (instead of 2048 vector atomics), by
+    // four warps of their own (one per TMEM lane quarter): with the softmax warps draining dQ themselves, the ~1000 cycles per
+    // query tile sat on the critical path of the kernel (softmax -> drain -> next softmax).
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;   // which 64 of the 128 key columns (and which 32 of the 64 dQ columns) this warp handles
     const int r = qd * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t p_row = smem_u32(sP) + r * 128, ds_row = smem_u32(sdS) + r * 128;
     const int sw = r & 7;
-    const int valid_k = min(kKV, p.Lk - k0);
-    const int64_t bh = (int64_t)b * p.H + h;
-    // dQ tile j: TMEM -> fp32 smem tile -> ONE bulk tensor reduce-add per 32-column half (instead of 2048 vector atomics).
-    // The caller has waited for dq_full of tile j.
-    auto drain_dq = [&](int j) {
-      if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile left smem
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      {
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    const bool issuer = threadIdx.x == 320;
+    for (int j = 0; j < p.nq; ++j) {
+      mbar_wait(dq_full, j & 1);
+      tc_fence_after();
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous tile left smem
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
         uint32_t v0[32];
-        tmem_ld_32x32(t_dq + lane_base + half * 32, v0);
+        tmem_ld_32x32(t_dq + lane_base + hh * 32, v0);
         tmem_ld_wait();
-        const uint32_t row0 = smem_u32(sDQ) + half * kTileBytes + r * 128;
+        const uint32_t row0 = smem_u32(sDQ) + hh * kTileBytes + r * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g) sts128(row0 + ((g ^ sw) << 4), v0[4 * g], v0[4 * g + 1], v0[4 * g + 2], v0[4 * g + 3]);
       }
@@ -699,8 +701,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);   // the TMEM accumulator may be overwritten by the next dQ
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (threadIdx.x == 64) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
 #pragma unroll
         for (int c = 0; c < 2; ++c)
           asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
@@ -709,7 +711,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                        : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-    };
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reduces have been performed
+  } else {
+    // ===================== softmax warps =====================
+    const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;   // which 64 of the 128 key columns this warp handles (and which of dV / dK it writes)
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t p_row = smem_u32(sP) + r * 128, ds_row = smem_u32(sdS) + r * 128;
+    const int sw = r & 7;
+    const int valid_k = min(kKV, p.Lk - k0);
+    const int64_t bh = (int64_t)b * p.H + h;
     for (int i = 0; i < p.nq; ++i) {
       const int q = i * kQ + r;
       const bool q_ok = q < p.Lq;
@@ -722,20 +735,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const long long tp1 = prof ? clock64() : 0;
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(-lse, -lse);
       const float2 nd2 = make_float2(-dlt, -dlt), ss2 = make_float2(p.scale, p.scale);
-      uint32_t sv[2][32], dv_[2][32];
-      tmem_ld_32x32(t_s + lane_base + half * 64, sv[0]);
-      tmem_ld_32x32(t_dp + lane_base + half * 64, dv_[0]);
-      tmem_ld_32x32(t_s + lane_base + half * 64 + 32, sv[1]);
-      tmem_ld_32x32(t_dp + lane_base + half * 64 + 32, dv_[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_read);   // S / dP live in registers now: the MMA warp may issue the next tile's pair
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < 2; ++cc) {   // one 32-column chunk at a time (the drain warps share the register file now)
         const int c = half * 2 + cc;
-        const uint32_t(&s_)[32] = sv[cc];
-        const uint32_t(&d_)[32] = dv_[cc];
+        uint32_t s_[32], d_[32];
+        tmem_ld_32x32(t_s + lane_base + c * 32, s_);
+        tmem_ld_32x32(t_dp + lane_base + c * 32, d_);
+        tmem_ld_wait();
+        if (cc == 1) {   // S / dP of this tile live in registers now: the MMA warp may issue the next tile's pair
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_read);
+        }
         float pf[32], dsf[32];
         if (q_ok && valid_k == kKV) {
 #pragma unroll
@@ -767,17 +778,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      const long long tp2 = prof ? clock64() : 0;
-      if (i > 0) drain_dq(i - 1);   // one tile late: its MMA finished during this tile's softmax, nothing to wait for
       if (prof) {
-        const long long tp4 = clock64();
-        p.dbg[0] += tp1 - tp0, p.dbg[1] += tp2 - tp1, p.dbg[3] += tp4 - tp2;
+        const long long tp2 = clock64();
+        p.dbg[0] += tp1 - tp0, p.dbg[1] += tp2 - tp1;
       }
     }
-    mbar_wait(dq_full, (p.nq - 1) & 1);
-    tc_fence_after();
-    drain_dq(p.nq - 1);
-    if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reduces have been performed
     // accumulated dV / dK for key row k0 + r
     mbar_wait(acc_full, 0);
     tc_fence_after();
