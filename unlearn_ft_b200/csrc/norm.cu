@@ -122,7 +122,17 @@ __device__ __forceinline__ void gn_gather_slices(const float* __restrict__ part,
   for (int c = c_lo + threadIdx.x; c < c_hi; c += blockDim.x) {
     float t0 = 0.f, t1 = 0.f;
     const float* pp = part + base + c;
-    for (int sl = 0; sl < slices; ++sl, pp += 2 * plane) t0 += pp[0], t1 += pp[plane];
+    int sl = 0;
+    // eight slices' loads in flight before the first add (same order of additions: bit-identical).  The rolled loop issued one
+    // pair of loads per L2 round trip -- with 11 ... 37 slices that chain WAS the kernel (7.6 us for 64 blocks of trivial work).
+    for (; sl + 8 <= slices; sl += 8, pp += 16 * plane) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = pp[(int64_t)(2 * u) * plane], b[u] = pp[(int64_t)(2 * u + 1) * plane];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t0 += a[u], t1 += b[u];
+    }
+    for (; sl < slices; ++sl, pp += 2 * plane) t0 += pp[0], t1 += pp[plane];
     sh0[c - c_lo] = t0, sh1[c - c_lo] = t1;
   }
   __syncthreads();
