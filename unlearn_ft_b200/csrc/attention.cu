@@ -51,17 +51,17 @@ struct AttnFwdParams {
 };
 
 // ----------------------------------------------------------------------------------------------------------------
-// Forward: one CTA = one (sample, head, 256-query block) = two 128-row query tiles that ping-pong on the tensor
-// core; one CTA per SM.
-//   warp 0            : TMA producer  - both Q tiles once, then K/V blocks of 128 keys through a 3-stage smem ring
-//   warp 1            : MMA issuer    - per key block and query tile t:  O_t += P_t V (accumulating in TMEM), then
-//                                       immediately S_t = Q_t K_next^T, so that tile t's softmax overlaps the other
-//                                       tile's MMAs
-//   warps 2..5 / 6..9 : softmax of query tile 0 / 1 - one row per thread; the 128 scores of a row are pulled out of
-//                       TMEM at once, exponentiated against a LAZILY updated running maximum (the O accumulator in
-//                       TMEM is rescaled only when a row maximum grew by more than 2^8, which after the first blocks
-//                       is rare), written as bf16 P into a swizzle-128B tile for the second MMA
-// Both roles issue from warp-uniform code through elect.sync.  O leaves TMEM once, at the end.
+// Forward: one CTA = one (sample, head, 256-query block) = two 128-row query tiles; one CTA per SM.
+//   warp 0      : TMA producer  - both Q tiles once, then K/V blocks of 128 keys through a 3-stage smem ring
+//   warp 1      : MMA issuer    - per key block j and query tile t:  S_t(j+1) = Q_t K_{j+1}^T as soon as the softmax warps
+//                                 hold S_t(j) in registers (s_read), O_t += P_t(j) V_j when P_t(j) has been written (p_full);
+//                                 P_t is the PV MMA's A operand straight from tensor memory (tcgen05.mma, TS form)
+//   warps 2..17 : four softmax warpgroups: query tile t = wg >> 1, key half = wg & 1; a thread owns one query row (= TMEM
+//                 lane) and 64 of the block's 128 keys.  The scores are read out of TMEM once and kept in registers,
+//                 exponentiated against a LAZILY updated running maximum (the O accumulator in TMEM is rescaled, and the
+//                 block redone from registers, only when a row maximum grew by more than 2^8, which after the first blocks
+//                 is rare), and written back to tensor memory as bf16 P.  12.5 % of the exponentials run on the FMA pipe.
+// O leaves TMEM once, at the end.  TMEM: S_t at 128 t, O_t at 256 + 64 t, P_t at 384 + 64 t.
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int kFwd2Threads = 64 + 4 * 128;   // TMA warp, MMA warp, four softmax warpgroups
 constexpr int kKVStages = 3;

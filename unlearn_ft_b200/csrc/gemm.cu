@@ -1,13 +1,18 @@
 // Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution core for sm_100a.
 //
-//   warp 0 (one lane)  : TMA producer   - cp.async.bulk.tensor tiles of A and B into a swizzle-128B smem ring
-//   warp 1 (one lane)  : MMA issuer     - tcgen05.mma (M=128, N=block_n, K=16) into a double-buffered TMEM accumulator
-//   warps 2..5         : epilogue       - tcgen05.ld accumulator rows, alpha/bias/time-embedding/residual, store
+//   warp 0             : TMA producer   - cp.async.bulk.tensor tiles of A and B into a swizzle-128B smem ring (3-8 stages)
+//   warp 1             : MMA issuer     - tcgen05.mma (M = 128, or 256 across a cta_group::2 pair; N = block_n; K = 16) into a
+//                                         double-buffered TMEM accumulator (tall tiles: both buffers, two 128-row sub-tiles)
+//   warps 2..9         : epilogue       - two warpgroups: tcgen05.ld accumulator rows (one row per lane), alpha / bias /
+//                                         time-embedding row bias / residual / GEGLU, 256-bit row stores; no shared memory
+//   (both single-thread roles run warp-uniform loops and issue through elect.sync)
 //
-// The A/B tiles are addressed by a small "operand program" evaluated by the producer thread, which is what turns the
-// same kernel into: linear fwd/dgrad/wgrad (K-major or MN-major 2D operands, batched), 3x3/1x1 convolution fprop
-// (NHWC activations fetched tap by tap with 4D TMA boxes; out-of-bounds = zero padding), convolution dgrad (tap
-// flip + weight matrix read MN-major) and convolution wgrad (both operands MN-major, K = output pixels).
+// The A/B tiles are addressed by a small "operand program" evaluated by the producer, which is what turns the same kernel into:
+// linear fwd/dgrad/wgrad (K-major or MN-major 2D operands, batched), 3x3/1x1 convolution fprop (NHWC activations fetched
+// with 4D TMA boxes, out-of-bounds = zero padding; stride-1 3x3: one box of R + 2 image rows per (channel block, kw) serves
+// the three kh taps -- GemmDev::kh3), convolution dgrad (tap flip + weight matrix read MN-major) and convolution wgrad (both
+// operands MN-major, K = output pixels).  A host-side cost model (plan_gemm) picks block_n, pair mode, tall tiles and split-K
+// (per-split fp32 slabs in the caller's workspace + an ordered finalize pass: deterministic).
 //
 // Reference call sites replaced: see include/b200pdm.h (linear/conv entries).
 #include "common.cuh"
