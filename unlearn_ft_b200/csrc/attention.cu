@@ -75,8 +75,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                   // 2 tiles
   uint8_t* sKV = smem + 2 * kTileBytes;                 // kKVStages x (K tile, V tile)
-  uint8_t* sP = sKV + kKVStages * 2 * kTileBytes;       // 2 query tiles x 2 [128 x 64] sub-tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kKVStages * 2 * kTileBytes);   // (P lives in tensor memory: no smem tile)
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                 // [3]
   uint64_t* kv_empty = kv_full + kKVStages;     // [3]
@@ -145,8 +144,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const uint32_t idesc_o = make_idesc_bf16(kD, 0, 1);   // PV: N = 64, B (= V) MN-major
     const uint64_t dk = make_smem_desc_sw128(0, 16, 1024);       // K-major operand template
     const uint64_t dv = make_smem_desc_sw128(0, 8192, 1024);     // MN-major (V) template
-    const uint32_t q_lo = (smem_u32(sQ) & 0x3FFFF) >> 4, kv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4,
-                   p_lo = (smem_u32(sP) & 0x3FFFF) >> 4;
+    const uint32_t q_lo = (smem_u32(sQ) & 0x3FFFF) >> 4, kv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
     auto issue_s = [&](int t, int stage) {   // S_t = Q_t K^T
       const uint32_t a = q_lo + t * (kTileBytes >> 4), bq = kv_lo + stage * (2 * kTileBytes >> 4);
 #pragma unroll
@@ -449,7 +447,7 @@ extern "C" int b200pdm_attention_fwd_ex(const void* q, int64_t ldq, const void* 
   p.dbg = dbg_on ? dbg_buf : nullptr;
 #endif
   cudaError_t e;
-  const size_t smem = (2 + 2 * kKVStages + 4) * kTileBytes + 256 + 4096;   // tiles, barriers, row-maximum exchange
+  const size_t smem = (2 + 2 * kKVStages) * kTileBytes + 256 + 4096;   // Q and K/V tiles, barriers, row-maximum exchange
   static bool attr_set = false;   // once, not per launch (graph capture)
   if (!attr_set) {
     e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
