@@ -15,7 +15,8 @@
  *     it must stay alive until the call's work has run -- allocate it from the stream-ordered / graph-pool allocator).
  *     A NULL workspace is legal for the GEMM-class calls: the planner then restricts itself to plans without scratch;
  *   - activations are bf16, channels-last ("NHWC"): a [B,C,H,W] tensor is a row-major [B*H*W, ld] matrix whose
- *     first C columns are valid, ld % 8 == 0 (16-byte rows; TMA requirement);
+ *     first C columns are valid, ld % 8 == 0 (16-byte rows; TMA requirement).  ld % 16 == 0 (rows on 32-byte sectors) lets the
+ *     GEMM epilogue use 256-bit row accesses for every width -- the host mirror allocates that way;
  *   - weights used as tensor-core operands are bf16 "shadow" copies of the fp32 masters, kept in the layout
  *     [C_out][kh*kw][C_in_ld] for convolutions and [N][K] for linears (same element order as the masters);
  *   - gradients of parameters are fp32 and are ACCUMULATED into the caller's buffers.
