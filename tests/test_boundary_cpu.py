@@ -217,3 +217,32 @@ def test_encoder_from_pretrained_reads_the_dependency_folder_layout(tmp_path):
     (tmp_path / "text_encoder" / "model.safetensors").unlink()
     with pytest.raises(FileNotFoundError):
         CLIPTextModel.from_pretrained(str(tmp_path), subfolder="text_encoder", device="meta")
+
+
+def test_fused_gelu_constants_match_their_derivation():
+    """The one-exponential erf-GELU of the fused GEGLU epilogue (csrc/common.cuh::gelu_erf_fast): its coefficients evaluated in float32
+    exactly as the kernel does (Horner, ex2, clamp at 8) stay within 2e-6 of the exact erf-GELU over [-12, 12] -- far below the bf16
+    rounding applied to the result.  Guards the constants in the source against drift from tools/fit_gelu.py.  CPU only."""
+    import os
+    import re
+
+    import numpy as np
+    from scipy.special import erf
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "unlearn_ft_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_erf_fast(float x)"):]
+    body = body[:body.index("\n}\n")]
+    assert "fminf(fabsf(x), 8.f)" in body
+    c = [np.float32(v) for v in re.findall(r"(-?\d\.\d{6,})f", body)]      # the polynomial, highest power first
+    assert len(c) == 5
+    c5, c4, c3, c2, c1 = c
+    g = np.linspace(-12, 12, 400001).astype(np.float32)
+    a = np.minimum(np.abs(g), np.float32(8.0))
+    q = a * c5 + c4
+    q = a * q + c3
+    q = a * q + c2
+    q = a * q + c1
+    e = np.exp2(-(q * a)).astype(np.float32)
+    r = (np.float32(0.5) * g * e).astype(np.float32)
+    gelu = np.where(g >= 0, g - r, r)
+    ref = 0.5 * g.astype(np.float64) * (1 + erf(g.astype(np.float64) / np.sqrt(2)))
+    assert float(np.abs(gelu - ref).max()) < 2e-6
