@@ -246,3 +246,28 @@ def test_fused_gelu_constants_match_their_derivation():
     gelu = np.where(g >= 0, g - r, r)
     ref = 0.5 * g.astype(np.float64) * (1 + erf(g.astype(np.float64) / np.sqrt(2)))
     assert float(np.abs(gelu - ref).max()) < 2e-6
+
+
+def test_fma_pipe_exp2_accuracy_claim():
+    """csrc/common.cuh::exp2_fma (the share of the attention exponentials evaluated on the FMA pipe): Cody-Waite split + degree-3
+    polynomial, restated in float32 numpy with the constants read from the source; maximum relative error below 1e-4 on the range the
+    softmax uses (x <= 8; far below bf16's 2^-9), exact zero-flush behaviour not required.  CPU only."""
+    import os
+    import re
+
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "unlearn_ft_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float exp2_fma(float x)"):]
+    body = body[:body.index("\n}\n")]
+    k3, k2 = [np.float32(v) for v in re.search(r"fmaf\(f, (\d\.\d+)f, (\d\.\d+)f\)", body).groups()]
+    k1, k0 = [np.float32(v) for v in re.findall(r"fmaf\(f, p, (\d\.\d+)f\)", body)]
+    x = np.linspace(-100, 8, 2000001).astype(np.float32)
+    magic = np.float32(12582912.0)
+    t = (x + magic).astype(np.float32)
+    f = (x - (t - magic)).astype(np.float32)
+    p = (f * k3 + k2).astype(np.float32)
+    p = (f * p + k1).astype(np.float32)
+    p = (f * p + k0).astype(np.float32)
+    y = (p.view(np.int32) + (t.view(np.int32) << 23)).view(np.float32)
+    ref = np.exp2(x.astype(np.float64))
+    assert float(np.abs(y / ref - 1).max()) < 1e-4
